@@ -1,0 +1,146 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/* from the UNMODIFIED
+reference (imported read-only from /root/reference through oracle/ref_import.py)
+and pin the restatement in oracle/unet_oracle.py against it.
+
+Run in the build container (CPU):   python -m oracle.make_golden
+Writes:
+  tests/golden/pose_grids.npz   3x3 object rotations of the shipped icosphere grids
+                                (src/poses/predefined_poses/obj_poses_level{0,2}.npy,
+                                 'all' and 'upper' per src/poses/utils.py:72-102)
+  tests/golden/cfg1_b1_n6.npz   BASELINE config 1 (N=6 because retrieval() hard-codes
+                                topk(5), model.py:265): feats, embeddings, scores, top-5
+  tests/golden/grid26_b2.npz    B=2, N=26 'upper' level-0 grid: scores, top-5, embedding
+                                digests + two full templates
+  tests/golden/unet_taps.npz    per-layer activation statistics of one UNet forward
+  tests/golden/meta.json        weight checksum, torch version, oracle-vs-reference errors
+It asserts (hard failure) that
+  * the seeded state_dict loads into the reference modules with strict=True
+  * oracle.unet_forward / encode_image / l2_similarity match the reference modules
+    to fp32 round-off (different summation order only)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import inputs, unet_oracle as orc, weights
+from .ref_import import REFERENCE_ROOT, build_reference_model, import_reference
+
+OUT = inputs.GOLDEN_DIR
+
+
+def rel_err(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def write_pose_grids():
+    pp = os.path.join(REFERENCE_ROOT, "src/poses/predefined_poses")
+    out = {}
+    for level in (0, 2):
+        obj = np.load(os.path.join(pp, f"obj_poses_level{level}.npy"))
+        cam = np.load(os.path.join(pp, f"sphere_poses_level{level}.npy"))
+        out[f"level{level}_all"] = obj[:, :3, :3].astype(np.float64)
+        out[f"level{level}_upper"] = obj[cam[:, 2, 3] >= 0][:, :3, :3].astype(np.float64)
+    np.savez_compressed(os.path.join(OUT, "pose_grids.npz"), **out)
+    return {k: v.shape[0] for k, v in out.items()}
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(OUT, exist_ok=True)
+    meta = {"torch": torch.__version__, "reference_root": REFERENCE_ROOT}
+    meta["pose_grids"] = write_pose_grids()
+
+    ref = import_reference()
+    model = build_reference_model()
+    sd = weights.make_full_state_dict(seed=0)
+    missing = model.u_net.load_state_dict(sd, strict=True)
+    meta["weights_checksum_seed0"] = weights.checksum(sd)
+    meta["n_unet_tensors"] = sum(1 for k in sd if not k.startswith("encoder."))
+    meta["n_encoder_entries"] = sum(1 for k in sd if k.startswith("encoder."))
+    print("state_dict loaded strict:", missing, meta["n_unet_tensors"], meta["n_encoder_entries"])
+    unet_sd = {k: v for k, v in sd.items() if not k.startswith("encoder.")}
+    enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+
+    errs = {}
+    with torch.no_grad():
+        # ---------------- cfg1: B=1, N=6 through the reference's own loop ----------
+        q, r = inputs.make_images(seed=0, batch=1)
+        relR, tposes = inputs.make_pose_batch("level0_upper", batch=1, n=6)
+        t0 = time.time()
+        emb_ref, _, _ = model.generate_templates(r, relR, gt_templates=None)
+        sim_ref, idx_ref = model.retrieval(q, emb_ref)
+        meta["cfg1_reference_seconds"] = time.time() - t0
+        qf_ref = model.u_net.encoder.encode_image(q)
+        rf_ref = model.u_net.encoder.encode_image(r)
+        # oracle restatement on the same inputs
+        qf = orc.encode_image(enc_sd, q)
+        rf = orc.encode_image(enc_sd, r)
+        emb = orc.generate_templates(unet_sd, rf, relR)
+        sim = orc.l2_similarity(qf, emb)
+        idx = orc.topk_lowest_index(sim, 5)
+        errs["cfg1_query_feat"] = rel_err(qf, qf_ref)
+        errs["cfg1_ref_feat"] = rel_err(rf, rf_ref)
+        errs["cfg1_emb"] = rel_err(emb, emb_ref)
+        errs["cfg1_sim"] = rel_err(sim, sim_ref)
+        assert torch.equal(idx, idx_ref), (idx, idx_ref)
+        # rotation_conversions.matrix_to_rotation_6d cross-check of inputs.relative_rot6d
+        fx = inputs.load_pose_fixture()
+        Rrel = torch.tensor(fx["level0_upper"][:6] @ np.linalg.inv(fx["level0_upper"][7]),
+                            dtype=torch.float32)
+        assert torch.equal(ref.rotation_conversions.matrix_to_rotation_6d(Rrel), relR[0])
+        np.savez_compressed(
+            os.path.join(OUT, "cfg1_b1_n6.npz"),
+            query_feat=qf_ref.numpy(), ref_feat=rf_ref.numpy(), all_relativeR=relR.numpy(),
+            emb=emb_ref.numpy(), similarity=sim_ref.numpy(), nearest_idx=idx_ref.numpy(),
+            template_poses=tposes.numpy())
+
+        # ---------------- unet taps: one hypothesis, oracle vs reference module -----
+        taps = {}
+        y = orc.unet_forward(unet_sd, rf_ref, relR[:, 0], taps=taps)
+        y_ref = model.u_net(rf_ref, relR[:, 0])
+        errs["unet_single"] = rel_err(y, y_ref)
+        tap_stats = {k: np.array([float(v.mean()), float(v.std()), float(v.abs().max())],
+                                 dtype=np.float64) for k, v in taps.items()}
+        tap_stats["out"] = np.array([float(y_ref.mean()), float(y_ref.std()),
+                                     float(y_ref.abs().max())])
+        np.savez_compressed(os.path.join(OUT, "unet_taps.npz"), **tap_stats)
+
+        # ---------------- grid26: B=2, N=26 ----------------------------------------
+        q2, r2 = inputs.make_images(seed=1, batch=2)
+        relR2, tposes2 = inputs.make_pose_batch("level0_upper", batch=2)
+        t0 = time.time()
+        emb2, _, _ = model.generate_templates(r2, relR2, gt_templates=None)
+        sim2, idx2 = model.retrieval(q2, emb2)
+        meta["grid26_reference_seconds"] = time.time() - t0
+        qf2 = model.u_net.encoder.encode_image(q2)
+        rf2 = model.u_net.encoder.encode_image(r2)
+        emb2o = orc.generate_templates(unet_sd, orc.encode_image(enc_sd, r2), relR2)
+        sim2o = orc.l2_similarity(orc.encode_image(enc_sd, q2), emb2o)
+        errs["grid26_emb"] = rel_err(emb2o, emb2)
+        errs["grid26_sim"] = rel_err(sim2o, sim2)
+        assert torch.equal(orc.topk_lowest_index(sim2o, 5), idx2)
+        srt = torch.sort(sim2, dim=1, descending=True).values
+        meta["grid26_min_adjacent_gap_rel"] = float(
+            ((srt[:, :-1] - srt[:, 1:]) / srt[:, :-1].abs()).min())
+        np.savez_compressed(
+            os.path.join(OUT, "grid26_b2.npz"),
+            query_feat=qf2.numpy(), ref_feat=rf2.numpy(), all_relativeR=relR2.numpy(),
+            similarity=sim2.numpy(), nearest_idx=idx2.numpy(),
+            emb_mean=emb2.mean(dim=(2, 3, 4)).numpy(), emb_l2=emb2.flatten(2).norm(dim=2).numpy(),
+            emb_b0_n0=emb2[0, 0].numpy(), emb_b1_n25=emb2[1, 25].numpy(),
+            template_poses=tposes2.numpy())
+
+    meta["oracle_vs_reference_rel_err"] = errs
+    print(json.dumps(meta, indent=1))
+    for k, v in errs.items():
+        assert v < 2e-5, f"oracle restatement disagrees with the reference on {k}: {v}"
+    with open(os.path.join(OUT, "meta.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
