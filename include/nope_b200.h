@@ -1,0 +1,127 @@
+/* nope_b200 -- C ABI of the B200-native NOPE inference hot path.
+ *
+ * The reference (nv-nguyen/nope) is pure Python/PyTorch and has no FFI of its own;
+ * each entry point below names the reference function it replaces (paths relative to
+ * the reference root).  All pointers are raw device pointers unless marked HOST; no
+ * torch types cross this boundary.  Every function returns 0 on success and a negative
+ * value on failure; nope_last_error() then returns a description (thread-local).
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * Layout conventions at the boundary follow the reference's tensors:
+ *   latent features   fp32 NCHW [B, C, 32, 32]           (encoder output, u_net input)
+ *   poses             fp32 [B, N, 6]                     (6-D rotations, all_relativeR)
+ *   embeddings        fp32 [B, N, C, 32, 32]             (pred_feat_templates)
+ *   similarity        fp32 [B, N]; nearest_idx int64 [B, k]
+ * Inside the library activations are NHWC fp16 and weights are repacked K-major fp16.
+ */
+#ifndef NOPE_B200_H
+#define NOPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nope_unet nope_unet_t;
+
+#define NOPE_METRIC_L2 0      /* reference "l2": -(sum_hw sqrt(sum_c (q-t)^4)), model.py:260-262 */
+#define NOPE_METRIC_COSINE 1  /* extension: cosine of flattened descriptors (not in the reference) */
+
+/* Thread-local message of the last failing call on this thread. */
+const char* nope_last_error(void);
+
+/* Library/ABI version and the SM architecture the kernels were built for ("sm_100a"). */
+int nope_abi_version(void);
+const char* nope_build_arch(void);
+
+/* ---- engine lifetime ------------------------------------------------------------
+ * Replaces construction of src/model/u_net/denoising_diffusion_pytorch/u_net.py:27-158
+ * (UNet.__init__ with use_hard_up_down=True, dim_mults=(1,2,4,8), 8 groups,
+ * pose_mlp_name="single_layer").  u_net_dim must be a multiple of 64; latent_ch <= 8;
+ * latent_hw is the latent side (32 for 256x256 images). */
+int nope_unet_create(nope_unet_t** out, int u_net_dim, int latent_ch, int latent_hw, int device);
+void nope_unet_destroy(nope_unet_t* u);
+
+/* Hand one tensor of the reference state_dict to the engine, by its reference key
+ * (e.g. "downs.0.0.block1.proj.weight").  `data` is a HOST fp32 pointer,
+ * contiguous, with `ndim` sizes in `shape`.  Unknown keys are rejected; encoder.* keys
+ * are not accepted here (the encoder stays a host-framework module in this round).
+ * Replaces nn.Module.load_state_dict for the UNet (src/utils/weight.py:6-37 semantics:
+ * shape-checked). */
+int nope_unet_load_tensor(nope_unet_t* u, const char* key, const float* data,
+                          const int64_t* shape, int ndim);
+
+/* Checks that every tensor was provided, repacks weights (OIHW fp32 -> K-major fp16,
+ * pose projections concatenated into one GEMM) and uploads them. */
+int nope_unet_finalize(nope_unet_t* u);
+
+/* Tunables: hypotheses per chunk (workspace = ~5.5 MB per hypothesis), and the
+ * convolution implementation: 0 = tcgen05 tensor cores (default), 1 = SIMT debug twin. */
+int nope_unet_set_chunk(nope_unet_t* u, int hyps_per_chunk);
+int nope_unet_set_conv_impl(nope_unet_t* u, int impl);
+
+/* ---- the hot path -----------------------------------------------------------------
+ * Sweep over the pose grid.  Replaces the Python loop of
+ * PoseConditional.generate_templates (src/model/model.py:193-252) around
+ * UNet.forward (u_net.py:160-198) and, when query_feat != NULL, the scoring and top-k of
+ * PoseConditional.retrieval (model.py:254-266) fused onto the last layer.
+ *   ref_feat   [B, C, hw, hw] fp32   encode_image(reference)
+ *   poses      [B, N, 6] fp32        all_relativeR
+ *   query_feat [B, C, hw, hw] fp32 or NULL
+ *   out_emb    [B, N, C, hw, hw] fp32 or NULL (skip materialising the templates)
+ *   out_sim    [B, N] fp32 or NULL   (requires query_feat)
+ *   out_topv / out_topi  [B, k] fp32 / int64 or NULL; descending score, ties broken by
+ *              the lowest index; indices are offset by idx_base (global index of this
+ *              shard's first pose).  k = 0 skips the ranking.
+ * Kernels are enqueued on `stream`; the call does not synchronise. */
+int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, int B, int N,
+                    const float* query_feat, float* out_emb, float* out_sim, int k,
+                    float* out_topv, int64_t* out_topi, int64_t idx_base, void* stream);
+
+/* Number of kernels the last nope_unet_sweep call enqueued (for bench.py's gpu_launches). */
+int64_t nope_unet_last_launch_count(const nope_unet_t* u);
+
+/* Score materialised templates against a query and rank them: the arithmetic of
+ * PoseConditional.retrieval (model.py:254-266) after encode_image.
+ *   query_feat [B, C, HW] fp32, emb [B, N, C, HW] fp32 -> sim [B, N], topv/topi [B, k]. */
+int nope_score_topk(const float* query_feat, const float* emb, int B, int N, int C, int HW,
+                    int metric, int k, float* out_sim, float* out_topv, int64_t* out_topi,
+                    int64_t idx_base, void* stream);
+
+/* Rank an existing similarity matrix sim [B, N] (used to merge per-GPU shards). */
+int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_topi,
+              int64_t idx_base, void* stream);
+
+/* ---- per-op entry points (parity tests drive single layers through these) -----------
+ * All tensors fp32 NCHW device pointers; conversion to the internal NHWC fp16 layout
+ * happens inside.  These calls synchronise the stream before returning.
+ * conv: mode 0 = 3x3 pad 1 (model_utils.py:240), 1 = 1x1 (model_utils.py:269),
+ *       2 = pixel-unshuffle(2)+1x1 (HardDownsample, model_utils.py:168-172; input is
+ *       [n, C0, 2H, 2W], weight [Cout, 4*C0]).  x1 (optional) is concatenated after x0
+ *       along channels (u_net.py:186).  impl as in nope_unet_set_conv_impl. */
+int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, int C1,
+                 const float* weight, const float* bias, float* out, int n_img, int H, int W,
+                 int Cout, void* stream);
+/* y = [SiLU](GroupNorm_G(x)) + chan_bias[n, c] + residual   (model_utils.py:237-253,271-279) */
+int nope_op_groupnorm(const float* x, const float* gamma, const float* beta, int G, int silu,
+                      const float* chan_bias, const float* residual, float* out, int n_img,
+                      int C, int H, int W, void* stream);
+/* LinearAttention core on qkv [n, 384, H, W] -> [n, 128, H, W] (model_utils.py:403-417) */
+int nope_op_linear_attention(const float* qkv, float* out, int n_img, int H, int W, void* stream);
+/* Attention core on qkv [n, 384, H, W] -> [n, 128, H, W], H*W <= 32 (model_utils.py:376-388) */
+int nope_op_attention(const float* qkv, float* out, int n_img, int H, int W, void* stream);
+/* nearest x2 upsample (model_utils.py:161-163) */
+int nope_op_upsample2x(const float* x, float* out, int n_img, int C, int H, int W, void* stream);
+
+/* Debug: run the sweep for B=1 and copy the activation named `tap` (oracle tap names,
+ * e.g. "downs.0.0", "mid.1", "ups.2.3", "final_conv.0") to out as fp32 NCHW [N, C, H, W]. */
+int nope_unet_debug_tap(nope_unet_t* u, const float* ref_feat, const float* poses, int N,
+                        const char* tap, float* out, int64_t out_capacity_floats,
+                        int* out_C, int* out_H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOPE_B200_H */

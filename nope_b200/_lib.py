@@ -1,0 +1,72 @@
+"""ctypes binding of include/nope_b200.h.  There is no CPU fallback: if the shared
+library is missing, or a call fails, the product path raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnope_b200.so")
+
+c_f32p = C.c_void_p   # raw device / host pointers travel as integers
+c_i64p = C.c_void_p
+
+# symbol -> (restype, argtypes); mirrors include/nope_b200.h one to one
+SIGNATURES = {
+    "nope_last_error": (C.c_char_p, []),
+    "nope_abi_version": (C.c_int, []),
+    "nope_build_arch": (C.c_char_p, []),
+    "nope_unet_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nope_unet_destroy": (None, [C.c_void_p]),
+    "nope_unet_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_f32p, C.POINTER(C.c_int64), C.c_int]),
+    "nope_unet_finalize": (C.c_int, [C.c_void_p]),
+    "nope_unet_set_chunk": (C.c_int, [C.c_void_p, C.c_int]),
+    "nope_unet_set_conv_impl": (C.c_int, [C.c_void_p, C.c_int]),
+    "nope_unet_sweep": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p,
+                                  c_f32p, C.c_int, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
+    "nope_unet_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "nope_score_topk": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, c_f32p, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
+    "nope_topk": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
+    "nope_op_conv": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, c_f32p, c_f32p,
+                               c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nope_op_groupnorm": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nope_op_linear_attention": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nope_op_attention": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nope_op_upsample2x": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nope_unet_debug_tap": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_char_p, c_f32p,
+                                      C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+}
+
+_lib = None
+
+
+class NopeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libnope_b200.so (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NopeError(
+            f"{LIB_PATH} is missing: build it with `python -m nope_b200.build` "
+            "(nope_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NopeError(load().nope_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,52 @@
+"""Build libnope_b200.so in-tree with nvcc for sm_100a (no torch extension machinery:
+the library is a plain C-ABI shared object, bound from Python with ctypes)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "csrc", "nope_b200.cu")
+DEPS = [os.path.join(HERE, "csrc", f) for f in
+        ("nope_b200.cu", "common.cuh", "conv_tc.cuh", "kernels.cuh")] + \
+       [os.path.join(ROOT, "include", "nope_b200.h")]
+OUT_DIR = os.path.join(HERE, "lib")
+OUT = os.path.join(OUT_DIR, "libnope_b200.so")
+
+
+def nvcc_path():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found; the CUDA library cannot be built")
+    return p
+
+
+def is_stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return OUT
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3",
+           "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+           "-o", OUT + ".tmp", SRC]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libnope_b200.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    os.replace(OUT + ".tmp", OUT)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,361 @@
+// nope_b200 -- implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// One kernel serves every GEMM-shaped op of the pose-conditioned UNet
+// (reference: src/model/u_net/denoising_diffusion_pytorch/model_utils.py:240
+//  conv3x3, :171 1x1-after-unshuffle, :269 res_conv, :373-374/:399-401 qkv and
+//  to_out 1x1, :261-263 the pose projection Linear):
+//
+//   out[m, n] = bias[n] + sum_k A[m, k] * Wp[n, k]
+//
+// m enumerates output pixels of all batched hypotheses (NHWC, fp16), n output
+// channels, k = (filter tap, source tensor, input channel).  A is never
+// materialised: for each K-step of 64 channels the producer thread issues ONE
+// 4-D TMA box load {64 ch, w_cnt, h_cnt, b_cnt} (= 128 pixels) from the NHWC
+// activation tensor, shifted by the tap offset (dy, dx); out-of-image rows and
+// columns are zero-filled by the TMA unit, which is exactly conv padding.  The
+// box lands in shared memory as a 128-row x 128-byte K-major SWIZZLE_128B tile,
+// the canonical tcgen05 operand layout.  Channel concatenation (skip
+// connections, u_net.py:186-194) is two source tensor maps walked by the same K
+// loop; pixel-unshuffle + 1x1 (HardDownsample) is four stride-2 tensor maps.
+//
+// CTA = 8 warps, persistent over (m_tile, n_tile) work items:
+//   warp 0 lane 0 : TMA producer      (smem ring, full/empty mbarriers)
+//   warp 1 lane 0 : tcgen05.mma issuer (accumulator in TMEM, double buffered)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue: tcgen05.ld -> +bias -> fp16 -> swizzled smem -> TMA store
+#pragma once
+#include "common.cuh"
+#include <cudaTypedefs.h>
+
+namespace nope {
+
+constexpr int kBM = 128;         // pixels per tile (UMMA M)
+constexpr int kBK = 64;          // channels per K-step (one 128-byte swizzle row)
+constexpr int kMaxSeg = 18;      // 9 taps x 2 sources
+constexpr int kConvThreads = 256;
+
+struct ConvSeg {
+  int16_t map;      // index into amap[]
+  int16_t dy, dx;   // tap offset in pixels
+  int16_t nchunks;  // channels / 64 in this segment
+};
+
+struct ConvParams {
+  CUtensorMap amap[4];
+  CUtensorMap bmap;
+  CUtensorMap omap;
+  const float* bias;  // [n_total] or nullptr
+  int nseg;
+  int ksteps;         // sum of nchunks
+  int m_tiles, n_tiles;
+  int tiles_per_img;  // H*W/128 when H*W >= 128, else 0
+  int h_cnt, b_cnt;   // box rows per tile / images per tile
+  ConvSeg seg[kMaxSeg];
+};
+
+template <int BN, int STAGES>
+struct ConvSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = (BN / 64) * kBM * 128;
+  static constexpr int kBarOffset = STAGES * kStageBytes + kOutBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int m_tile, int& b0,
+                                                 int& y0) {
+  if (p.tiles_per_img > 0) {
+    b0 = m_tile / p.tiles_per_img;
+    y0 = (m_tile - b0 * p.tiles_per_img) * p.h_cnt;
+  } else {
+    b0 = m_tile * p.b_cnt;
+    y0 = 0;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using S = ConvSmem<BN, STAGES>;
+  constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* out_stage = smem + STAGES * S::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&p.amap[i]);
+    prefetch_tmap(&p.bmap);
+    prefetch_tmap(&p.omap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      int b0, y0;
+      conv_tile_coords(p, m_tile, b0, y0);
+      int kcol = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const ConvSeg sg = p.seg[s];
+        const CUtensorMap* am = &p.amap[sg.map];
+        for (int ch = 0; ch < sg.nchunks; ++ch) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_4d(sa, am, &full_bar[stage], ch * kBK, sg.dx, y0 + sg.dy, b0);
+          tma_load_2d(sa + S::kABytes, &p.bmap, &full_bar[stage], kcol, n_tile * BN);
+          kcol += kBK;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_f16(kBM, BN, false);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int ks = 0; ks < p.ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+        const uint64_t adesc = make_sw128_kmajor_desc(sa);
+        const uint64_t bdesc = make_sw128_kmajor_desc(sa + S::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 field
+          umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (ks == p.ksteps - 1) umma_commit(&tfull_bar[acc]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;            // == warp % 4: TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;     // pixel row inside the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bool store_pending = false;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      int b0, y0;
+      conv_tile_coords(p, m_tile, b0, y0);
+      // staging buffer must have been fully read by the previous TMA store
+      if (store_pending) {
+        if (ew == 0 && lane == 0) tma_store_wait_read0();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(t_row + cc * 64, v0);
+        tmem_ld_32x32(t_row + cc * 64 + 32, v1);
+        tmem_ld_wait();
+        const float* bptr = p.bias ? p.bias + n_tile * BN + cc * 64 : nullptr;
+        uint8_t* srow = out_stage + cc * (kBM * 128) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // 8 x 16-byte chunks of 8 channels
+          uint32_t w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = j * 8 + q * 2;
+            float a = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
+            float b = __uint_as_float(c + 1 < 32 ? v0[c + 1] : v1[c + 1 - 32]);
+            if (bptr) { a += __ldg(bptr + c); b += __ldg(bptr + c + 1); }
+            w[q] = pack_half2(a, b);
+          }
+          const int phys = j ^ (row & 7);   // SWIZZLE_128B: 16-B chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(srow + phys * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      // accumulator fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      // make the generic-proxy smem writes visible to the TMA (async proxy), then store
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ew == 0 && lane == 0) {
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 64; ++cc)
+          tma_store_4d(&p.omap, out_stage + cc * (kBM * 128), n_tile * BN + cc * 64, 0, y0, b0);
+        tma_store_commit();
+      }
+      store_pending = true;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (ew == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ----------------------------------------------------------------------------
+inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// fp16 tensor map, rank 2..4, 128-byte swizzle, zero fill out of bounds.
+// dims/box are innermost-first; strides_bytes[i] is the byte stride of dim i+1.
+inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr,
+                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",
+             (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+             box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return fail(buf);
+  }
+  return 0;
+}
+
+// Tile geometry of an NHWC tensor with H x W pixels per image: 128 pixels per tile.
+struct TileGeom {
+  int W, H, w_cnt, h_cnt, b_cnt, tiles_per_img;
+};
+inline int make_geom(int H, int W, TileGeom* g) {
+  g->W = W; g->H = H; g->w_cnt = W;
+  if (W > kBM || kBM % W != 0) return fail("conv geometry: W must divide 128");
+  const int hw = H * W;
+  if (hw >= kBM) {
+    if (hw % kBM != 0) return fail("conv geometry: H*W must be a multiple of 128");
+    g->h_cnt = kBM / W; g->b_cnt = 1; g->tiles_per_img = hw / kBM;
+  } else {
+    if (kBM % hw != 0) return fail("conv geometry: H*W must divide 128");
+    g->h_cnt = H; g->b_cnt = kBM / hw; g->tiles_per_img = 0;
+  }
+  return 0;
+}
+inline int geom_m_tiles(const TileGeom& g, int n_img) {
+  return g.tiles_per_img > 0 ? n_img * g.tiles_per_img : (n_img + g.b_cnt - 1) / g.b_cnt;
+}
+
+// NHWC activation map [B, H, W, C] (contiguous), box = one 128-pixel tile x 64 channels.
+inline int make_act_map(CUtensorMap* m, const void* base, int cap_img, int C, const TileGeom& g) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)cap_img};
+  uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)g.W * C * 2, (uint64_t)g.H * g.W * C * 2};
+  uint32_t box[4] = {64, (uint32_t)g.w_cnt, (uint32_t)g.h_cnt, (uint32_t)g.b_cnt};
+  return make_tmap_f16(m, base, 4, dims, str, box);
+}
+// Stride-2 sub-lattice (p1, p2) of an NHWC tensor with 2H x 2W pixels: the input of a
+// pixel-unshuffle + 1x1 conv seen from the H x W output geometry `g`.
+inline int make_unshuffle_map(CUtensorMap* m, const void* base, int cap_img, int C,
+                              const TileGeom& g, int p1, int p2) {
+  const int W2 = g.W * 2, H2 = g.H * 2;
+  const uint8_t* b = static_cast<const uint8_t*>(base) + ((size_t)p1 * W2 + p2) * C * 2;
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)cap_img};
+  uint64_t str[3] = {(uint64_t)2 * C * 2, (uint64_t)2 * W2 * C * 2, (uint64_t)H2 * W2 * C * 2};
+  uint32_t box[4] = {64, (uint32_t)g.w_cnt, (uint32_t)g.h_cnt, (uint32_t)g.b_cnt};
+  return make_tmap_f16(m, b, 4, dims, str, box);
+}
+// Packed weights [n_total, k_total] fp16, K-major.
+inline int make_weight_map(CUtensorMap* m, const void* base, int n_total, int k_total, int bn) {
+  uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)n_total};
+  uint64_t str[1] = {(uint64_t)k_total * 2};
+  uint32_t box[2] = {64, (uint32_t)bn};
+  return make_tmap_f16(m, base, 2, dims, str, box);
+}
+
+inline int pick_bn(int n_total) {
+  if (n_total % 192 == 0) return 192;
+  if (n_total % 128 == 0) return 128;
+  if (n_total % 64 == 0) return 64;
+  return 0;
+}
+
+template <int BN, int STAGES>
+inline int launch_conv_tc_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  using S = ConvSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NOPE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  conv_tc_kernel<BN, STAGES><<<grid, kConvThreads, S::kTotal, stream>>>(p);
+  NOPE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+inline int launch_conv_tc(const ConvParams& p, int bn, int num_sms, cudaStream_t stream) {
+  switch (bn) {
+    case 192: return launch_conv_tc_t<192, 4>(p, num_sms, stream);
+    case 128: return launch_conv_tc_t<128, 5>(p, num_sms, stream);
+    case 64: return launch_conv_tc_t<64, 6>(p, num_sms, stream);
+  }
+  return fail("launch_conv_tc: unsupported BN");
+}
+
+}  // namespace nope

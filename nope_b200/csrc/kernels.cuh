@@ -1,0 +1,752 @@
+// nope_b200 -- the HBM-bound kernels around the tensor-core convolutions:
+// weight packing, pose embedding, GroupNorm(+SiLU,+pose bias,+residual), linear
+// attention, bottleneck attention, nearest upsample, the fused final 1x1 conv +
+// l2 score, top-k.  All activations are NHWC fp16; statistics, softmax and
+// scores are fp32.  Each kernel cites the reference code it reproduces (paths
+// relative to the reference root).
+#pragma once
+#include "common.cuh"
+
+namespace nope {
+
+// ----------------------------------------------------------------------------
+// weight packing (once, at load time)
+// ----------------------------------------------------------------------------
+// src fp32 [Cout][Cin][T] (OIHW with T = KH*KW, or the [Cout][Cin*4] weight of the
+// 1x1 after pixel-unshuffle, whose input channel index is c*4 + p1*2 + p2,
+// model_utils.py:168-172) -> dst fp16 [Cout][T][Cin]  (K-major for the GEMM).
+__global__ void pack_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst,
+                                   int cout, int cin, int taps, int dst_row_stride,
+                                   int dst_col_off) {
+  const long long total = (long long)cout * cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int t = (int)((i / cin) % taps);
+    const int o = (int)(i / ((long long)cin * taps));
+    dst[(long long)o * dst_row_stride + dst_col_off + t * cin + c] =
+        __float2half_rn(src[((long long)o * cin + c) * taps + t]);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// pose embedding: cs[h, :] = SiLU(W6 pose[h] + b)   (u_net.py:63-66 pose_mlp, then the
+// SiLU that opens every ResnetBlock.mlp, model_utils.py:261-263)
+// ----------------------------------------------------------------------------
+__global__ void pose_embed_kernel(const float* __restrict__ poses, const float* __restrict__ w,
+                                  const float* __restrict__ b, __half* __restrict__ cs, int n_hyp,
+                                  int rot_dim, int cemb) {
+  const int h = blockIdx.x;
+  if (h >= n_hyp) return;
+  extern __shared__ float sp[];
+  if (threadIdx.x < rot_dim) sp[threadIdx.x] = poses[(long long)h * rot_dim + threadIdx.x];
+  __syncthreads();
+  for (int j = threadIdx.x; j < cemb; j += blockDim.x) {
+    float a = b[j];
+    for (int i = 0; i < rot_dim; ++i) a = fmaf(w[j * rot_dim + i], sp[i], a);
+    cs[(long long)h * cemb + j] = __float2half_rn(silu_f(a));
+  }
+}
+
+// ----------------------------------------------------------------------------
+// init_conv (u_net.py:77,161): fp32 NCHW latent [B,Cl,H,W] -> fp16 NHWC [B,H,W,Cout],
+// direct 3x3, pad 1.  Runs once per reference image (pose independent).
+// ----------------------------------------------------------------------------
+__global__ void init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ bias, __half* __restrict__ out, int B,
+                                 int Cl, int H, int W, int Cout) {
+  const long long total = (long long)B * H * W * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % Cout);
+    const int px = (int)((i / Cout) % W);
+    const int py = (int)((i / ((long long)Cout * W)) % H);
+    const int b = (int)(i / ((long long)Cout * W * H));
+    float acc = bias[o];
+    for (int c = 0; c < Cl; ++c)
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = py + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = px + kx - 1;
+          if (xx < 0 || xx >= W) continue;
+          acc = fmaf(x[(((long long)b * Cl + c) * H + yy) * W + xx],
+                     w[((o * Cl + c) * 3 + ky) * 3 + kx], acc);
+        }
+      }
+    out[i] = __float2half_rn(acc);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// broadcast a per-reference tensor to every hypothesis of that reference, optionally
+// adding the per-hypothesis pose projection (ResnetBlock.forward, model_utils.py:274-276,
+// applied to the hoisted pose-independent block1 output).
+// out[h, p, c] = src[ref_of[h], p, c] + pb[h, pb_off + c]
+// ----------------------------------------------------------------------------
+__global__ void bcast_add_kernel(const __half* __restrict__ src, const int* __restrict__ ref_of,
+                                 const __half* __restrict__ pb, int pb_stride, int pb_off,
+                                 __half* __restrict__ out, int n_hyp, int hw, int C) {
+  const int octs = C / 8;
+  const long long total = (long long)n_hyp * hw * octs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % octs);
+    const int p = (int)((i / octs) % hw);
+    const int h = (int)(i / ((long long)octs * hw));
+    const int r = ref_of[h];
+    uint4 v = *reinterpret_cast<const uint4*>(src + ((long long)r * hw + p) * C + o * 8);
+    if (pb) {
+      const uint4 a = *reinterpret_cast<const uint4*>(pb + (long long)h * pb_stride + pb_off + o * 8);
+      __half2* vv = reinterpret_cast<__half2*>(&v);
+      const __half2* aa = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 x = __half22float2(vv[q]), y = __half22float2(aa[q]);
+        vv[q] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + ((long long)h * hw + p) * C + o * 8) = v;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// GroupNorm (model_utils.py:241-252 Block.norm, :230 PreNorm, :401 to_out[1]), eps 1e-5,
+// biased variance, fp32 statistics.  Two kernels: deterministic partial sums per
+// (hypothesis, pixel slab, group), then a fused apply:
+//   y = [SiLU](x * scale + shift) + pose_bias[h, c] + residual[res_of[h], p, c]
+// Thread mapping: blockDim = octets * rows, thread -> (8-channel octet, pixel row);
+// consecutive threads read consecutive 16-byte vectors of one pixel (coalesced).
+// ----------------------------------------------------------------------------
+__host__ __device__ inline int gn_rows(int C) {
+  const int octs = C / 8;
+  const int r = 384 / octs;
+  return r < 1 ? 1 : r;
+}
+
+__global__ void gn_stats_kernel(const __half* __restrict__ x, float2* __restrict__ partial,
+                                int hw, int C, int G, int nslab) {
+  extern __shared__ float2 s_red[];
+  const int octs = C / 8;
+  const int rows = blockDim.x / octs;
+  const int o = threadIdx.x % octs;
+  const int r = threadIdx.x / octs;
+  const int slab = blockIdx.x, h = blockIdx.y;
+  const int pps = hw / nslab;
+  const __half* base = x + ((long long)h * hw + (long long)slab * pps) * C + o * 8;
+  float s = 0.f, ss = 0.f;
+  for (int p = r; p < pps; p += rows) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + (long long)p * C);
+    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __half22float2(hv[q]);
+      s += f.x + f.y;
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+    }
+  }
+  s_red[threadIdx.x] = make_float2(s, ss);
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int opg = octs / G;
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; ++rr)
+      for (int oo = 0; oo < opg; ++oo) {
+        const float2 t = s_red[rr * octs + threadIdx.x * opg + oo];
+        a += t.x;
+        b += t.y;
+      }
+    partial[((long long)h * nslab + slab) * G + threadIdx.x] = make_float2(a, b);
+  }
+}
+
+struct GnApplyArgs {
+  const __half* x;
+  __half* y;
+  const float2* partial;  // nullptr => no normalisation (y = x + ...)
+  const float* gamma;
+  const float* beta;
+  const __half* pb;       // per-hypothesis channel bias (added after the activation) or nullptr
+  const __half* res;      // residual or nullptr
+  const int* res_of;      // hypothesis -> residual image index, nullptr => identity
+  int pb_stride, pb_off;
+  int hw, C, G, nslab_stats, nslab;
+  int silu;
+  float eps;
+};
+
+__global__ void gn_apply_kernel(const GnApplyArgs a) {
+  const int octs = a.C / 8;
+  const int rows = blockDim.x / octs;
+  const int o = threadIdx.x % octs;
+  const int r = threadIdx.x / octs;
+  const int slab = blockIdx.x, h = blockIdx.y;
+  float scale[8], shift[8], pbv[8];
+  if (a.partial) {
+    const int g = o / (octs / a.G);
+    float s = 0.f, ss = 0.f;
+    for (int i = 0; i < a.nslab_stats; ++i) {
+      const float2 t = a.partial[((long long)h * a.nslab_stats + i) * a.G + g];
+      s += t.x;
+      ss += t.y;
+    }
+    const float cnt = (float)a.hw * (float)(a.C / a.G);
+    const float mean = s / cnt;
+    const float var = fmaxf(ss / cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + a.eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      scale[i] = rstd * a.gamma[o * 8 + i];
+      shift[i] = a.beta[o * 8 + i] - mean * scale[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { scale[i] = 1.f; shift[i] = 0.f; }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    pbv[i] = a.pb ? __half2float(a.pb[(long long)h * a.pb_stride + a.pb_off + o * 8 + i]) : 0.f;
+  const int pps = a.hw / a.nslab;
+  const long long off = ((long long)h * a.hw + (long long)slab * pps) * a.C + o * 8;
+  const long long roff =
+      a.res ? ((long long)(a.res_of ? a.res_of[h] : h) * a.hw + (long long)slab * pps) * a.C + o * 8
+            : 0;
+  for (int p = r; p < pps; p += rows) {
+    const uint4 v = *reinterpret_cast<const uint4*>(a.x + off + (long long)p * a.C);
+    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 t = __half22float2(hv[q]);
+      f[2 * q] = t.x;
+      f[2 * q + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = fmaf(f[i], scale[i], shift[i]);
+      if (a.silu) t = silu_f(t);
+      f[i] = t + pbv[i];
+    }
+    if (a.res) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(a.res + roff + (long long)p * a.C);
+      const __half2* hr = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 t = __half22float2(hr[q]);
+        f[2 * q] += t.x;
+        f[2 * q + 1] += t.y;
+      }
+    }
+    uint4 w;
+    w.x = pack_half2(f[0], f[1]);
+    w.y = pack_half2(f[2], f[3]);
+    w.z = pack_half2(f[4], f[5]);
+    w.w = pack_half2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(a.y + off + (long long)p * a.C) = w;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// LinearAttention core (model_utils.py:403-417), heads = 4, dim_head = 32:
+//   q = softmax_d(q) * scale ; k = softmax_n(k) ; ctx[d,e] = sum_n k[d,n] v[e,n]
+//   out[e,n] = sum_d ctx[d,e] q[d,n]
+// qkv: [n_hyp, n, 384] fp16 (q | k | v, each (head, 32)); out: [n_hyp, n, 128] fp16.
+// One CTA per (head, hypothesis).
+// ----------------------------------------------------------------------------
+constexpr int kLinAttnThreads = 256;
+constexpr int kLinAttnTile = 128;
+
+__device__ __forceinline__ void load32h(const __half* p, float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + j * 8);
+    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 t = __half22float2(hv[q]);
+      f[j * 8 + 2 * q] = t.x;
+      f[j * 8 + 2 * q + 1] = t.y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLinAttnThreads)
+linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) {
+  __shared__ float s_red[kLinAttnThreads / 32][32];
+  __shared__ float s_kmax[32];
+  __shared__ float s_ksum[32];
+  __shared__ __align__(16) float s_ctx[32][32];
+  __shared__ __align__(16) float s_ek[kLinAttnTile][32];
+  __shared__ __align__(16) float s_v[kLinAttnTile][32];
+  const int head = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __half* base = qkv + (long long)h * n * 384;
+  const __half* qb = base + head * 32;
+  const __half* kb = base + 128 + head * 32;
+  const __half* vb = base + 256 + head * 32;
+
+  // ---- pass A: per-channel max of k over tokens
+  float mx[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) mx[d] = -INFINITY;
+  for (int i = tid; i < n; i += kLinAttnThreads) {
+    float f[32];
+    load32h(kb + (long long)i * 384, f);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) mx[d] = fmaxf(mx[d], f[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    float m = mx[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp][d] = m;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float m = s_red[0][tid];
+    for (int w = 1; w < kLinAttnThreads / 32; ++w) m = fmaxf(m, s_red[w][tid]);
+    s_kmax[tid] = m;
+  }
+  __syncthreads();
+
+  // ---- pass B: ctx = exp(k - max)^T v, ksum
+  const int cd = tid >> 3;         // ctx row d owned by this thread
+  const int ce = (tid & 7) * 4;    // 4 consecutive e
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ks = 0.f;
+  for (int t0 = 0; t0 < n; t0 += kLinAttnTile) {
+    const int tn = min(kLinAttnTile, n - t0);
+    // stage: thread -> (token, 8-channel octet) for k and v
+    for (int idx = tid; idx < tn * 4; idx += kLinAttnThreads) {
+      const int t = idx >> 2, oc = (idx & 3) * 8;
+      const uint4 kv = *reinterpret_cast<const uint4*>(kb + (long long)(t0 + t) * 384 + oc);
+      const uint4 vv = *reinterpret_cast<const uint4*>(vb + (long long)(t0 + t) * 384 + oc);
+      const __half2* hk = reinterpret_cast<const __half2*>(&kv);
+      const __half2* hv = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = __half22float2(hk[q]), b = __half22float2(hv[q]);
+        s_ek[t][oc + 2 * q] = __expf(a.x - s_kmax[oc + 2 * q]);
+        s_ek[t][oc + 2 * q + 1] = __expf(a.y - s_kmax[oc + 2 * q + 1]);
+        s_v[t][oc + 2 * q] = b.x;
+        s_v[t][oc + 2 * q + 1] = b.y;
+      }
+    }
+    __syncthreads();
+    for (int t = 0; t < tn; ++t) {
+      const float e = s_ek[t][cd];
+      const float4 v4 = *reinterpret_cast<const float4*>(&s_v[t][ce]);
+      c0 = fmaf(e, v4.x, c0);
+      c1 = fmaf(e, v4.y, c1);
+      c2 = fmaf(e, v4.z, c2);
+      c3 = fmaf(e, v4.w, c3);
+      ks += e;
+    }
+    __syncthreads();
+  }
+  if ((tid & 7) == 0) s_ksum[cd] = ks;
+  __syncthreads();
+  {
+    const float inv = 1.0f / s_ksum[cd];
+    *reinterpret_cast<float4*>(&s_ctx[cd][ce]) = make_float4(c0 * inv, c1 * inv, c2 * inv, c3 * inv);
+  }
+  __syncthreads();
+
+  // ---- pass C: out[n, e] = sum_d softmax_d(q[n,:])[d] * scale * ctx[d][e]
+  const float scale = 0.17677669529663687f;  // 32^-0.5
+  for (int i = tid; i < n; i += kLinAttnThreads) {
+    float q[32];
+    load32h(qb + (long long)i * 384, q);
+    float m = q[0];
+#pragma unroll
+    for (int d = 1; d < 32; ++d) m = fmaxf(m, q[d]);
+    float sum = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { q[d] = __expf(q[d] - m); sum += q[d]; }
+    const float qs = scale / sum;
+    float o[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) o[e] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < 32; ++d) {
+      const float qd = q[d] * qs;
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        const float4 c = *reinterpret_cast<const float4*>(&s_ctx[d][e4 * 4]);
+        o[e4 * 4 + 0] = fmaf(qd, c.x, o[e4 * 4 + 0]);
+        o[e4 * 4 + 1] = fmaf(qd, c.y, o[e4 * 4 + 1]);
+        o[e4 * 4 + 2] = fmaf(qd, c.z, o[e4 * 4 + 2]);
+        o[e4 * 4 + 3] = fmaf(qd, c.w, o[e4 * 4 + 3]);
+      }
+    }
+    __half* op = out + ((long long)h * n + i) * 128 + head * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      w.x = pack_half2(o[j * 8 + 0], o[j * 8 + 1]);
+      w.y = pack_half2(o[j * 8 + 2], o[j * 8 + 3]);
+      w.z = pack_half2(o[j * 8 + 4], o[j * 8 + 5]);
+      w.w = pack_half2(o[j * 8 + 6], o[j * 8 + 7]);
+      *reinterpret_cast<uint4*>(op + j * 8) = w;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Attention core at the bottleneck (model_utils.py:376-388), n <= 32 tokens:
+//   sim = (q*scale)^T k ; softmax_j ; out[i,d] = sum_j attn[i,j] v[d,j]
+// One CTA per hypothesis, one warp per head.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+midattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) {
+  __shared__ float s_k[4][32][32];
+  __shared__ float s_v[4][32][32];
+  const int h = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __half* base = qkv + (long long)h * n * 384;
+  for (int t = lane; t < n; t += 32) {
+    float f[32];
+    load32h(base + (long long)t * 384 + 128 + head * 32, f);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) s_k[head][t][d] = f[d];
+    load32h(base + (long long)t * 384 + 256 + head * 32, f);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) s_v[head][t][d] = f[d];
+  }
+  __syncwarp();
+  const float scale = 0.17677669529663687f;
+  for (int i = lane; i < n; i += 32) {
+    float q[32];
+    load32h(base + (long long)i * 384 + head * 32, q);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) q[d] *= scale;
+    float sim[32];
+    float m = -INFINITY;
+    for (int j = 0; j < n; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) a = fmaf(q[d], s_k[head][j][d], a);
+      sim[j] = a;
+      m = fmaxf(m, a);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < n; ++j) { sim[j] = __expf(sim[j] - m); sum += sim[j]; }
+    const float inv = 1.0f / sum;
+    float o[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float p = sim[j] * inv;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o[d] = fmaf(p, s_v[head][j][d], o[d]);
+    }
+    __half* op = out + ((long long)h * n + i) * 128 + head * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      w.x = pack_half2(o[j * 8 + 0], o[j * 8 + 1]);
+      w.y = pack_half2(o[j * 8 + 2], o[j * 8 + 3]);
+      w.z = pack_half2(o[j * 8 + 4], o[j * 8 + 5]);
+      w.w = pack_half2(o[j * 8 + 6], o[j * 8 + 7]);
+      *reinterpret_cast<uint4*>(op + j * 8) = w;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// nearest x2 upsample (HardUpsample[0], model_utils.py:161-163), NHWC fp16
+// ----------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n_img,
+                                  int H, int W, int C) {
+  const int octs = C / 8;
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long total = (long long)n_img * H2 * W2 * octs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % octs);
+    const int xx = (int)((i / octs) % W2);
+    const int yy = (int)((i / ((long long)octs * W2)) % H2);
+    const int b = (int)(i / ((long long)octs * W2 * H2));
+    const uint4 v = *reinterpret_cast<const uint4*>(
+        x + (((long long)b * H + (yy >> 1)) * W + (xx >> 1)) * C + o * 8);
+    *reinterpret_cast<uint4*>(y + (((long long)b * H2 + yy) * W2 + xx) * C + o * 8) = v;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// final_conv[1] (1x1, C -> Cl <= 8, u_net.py:156) fused with the reference's "l2" score
+// (model.py:260-262):  score[h] = -sum_p sqrt( sum_c (q[c,p] - e[c,p])^4 ).
+// x: [n_hyp, hw, C] fp16; w fp32 [Cl, C]; emb (optional) fp32 [n_hyp, Cl, hw] (NCHW);
+// query (optional) fp32 [B, Cl, hw]; partial (optional) [n_hyp, nslab] positive sums.
+// One thread per pixel, 128 pixels per CTA.
+// ----------------------------------------------------------------------------
+constexpr int kFinalThreads = 128;
+constexpr int kMaxLatent = 8;
+
+__global__ void __launch_bounds__(kFinalThreads)
+final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ w,
+                        const float* __restrict__ bias, float* __restrict__ emb,
+                        const float* __restrict__ query, const int* __restrict__ ref_of,
+                        float* __restrict__ partial, int hw, int C, int Cl) {
+  extern __shared__ float s_w[];  // [Cl][C]
+  __shared__ float s_part[kFinalThreads / 32];
+  const int slab = blockIdx.x, h = blockIdx.y, nslab = gridDim.x;
+  for (int i = threadIdx.x; i < Cl * C; i += kFinalThreads) s_w[i] = w[i];
+  __syncthreads();
+  const int p = slab * kFinalThreads + threadIdx.x;
+  float acc[kMaxLatent];
+#pragma unroll
+  for (int c = 0; c < kMaxLatent; ++c) acc[c] = (c < Cl) ? bias[c] : 0.f;
+  float dist = 0.f;
+  if (p < hw) {
+    const __half* xp = x + ((long long)h * hw + p) * C;
+    for (int k0 = 0; k0 < C; k0 += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xp + k0);
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+      float f[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 t = __half22float2(hv[q]);
+        f[2 * q] = t.x;
+        f[2 * q + 1] = t.y;
+      }
+#pragma unroll
+      for (int c = 0; c < kMaxLatent; ++c)
+        if (c < Cl) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[c] = fmaf(f[i], s_w[c * C + k0 + i], acc[c]);
+        }
+    }
+    if (emb) {
+#pragma unroll
+      for (int c = 0; c < kMaxLatent; ++c)
+        if (c < Cl) emb[((long long)h * Cl + c) * hw + p] = acc[c];
+    }
+    if (query) {
+      const float* qp = query + (long long)ref_of[h] * Cl * hw + p;
+      float s4 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxLatent; ++c)
+        if (c < Cl) {
+          const float d = qp[(long long)c * hw] - acc[c];
+          const float d2 = d * d;
+          s4 = fmaf(d2, d2, s4);
+        }
+      dist = sqrtf(s4);
+    }
+  }
+  if (partial) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dist;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < kFinalThreads / 32; ++i) t += s_part[i];
+      partial[(long long)h * nslab + slab] = t;
+    }
+  }
+}
+
+// Standalone score of materialised embeddings (PoseConditional.retrieval, model.py:254-266):
+// emb fp32 [B, N, Cl, hw], query fp32 [B, Cl, hw].  metric 0: reference "l2";
+// metric 1: cosine over the flattened descriptor (extension, eps 1e-8).
+// One CTA per (b, n).
+__global__ void __launch_bounds__(256)
+score_kernel(const float* __restrict__ query, const float* __restrict__ emb,
+             float* __restrict__ sim, int N, int Cl, int hw, int metric) {
+  __shared__ float s_a[8], s_b[8], s_c[8];
+  const int n = blockIdx.x, b = blockIdx.y;
+  const float* e = emb + ((long long)b * N + n) * Cl * hw;
+  const float* q = query + (long long)b * Cl * hw;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
+    if (metric == 0) {
+      float s4 = 0.f;
+      for (int c = 0; c < Cl; ++c) {
+        const float d = q[c * hw + p] - e[c * hw + p];
+        const float d2 = d * d;
+        s4 = fmaf(d2, d2, s4);
+      }
+      a0 += sqrtf(s4);
+    } else {
+      for (int c = 0; c < Cl; ++c) {
+        const float x = q[c * hw + p], y = e[c * hw + p];
+        a0 = fmaf(x, y, a0);
+        a1 = fmaf(x, x, a1);
+        a2 = fmaf(y, y, a2);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_a[threadIdx.x >> 5] = a0;
+    s_b[threadIdx.x >> 5] = a1;
+    s_c[threadIdx.x >> 5] = a2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t0 += s_a[i]; t1 += s_b[i]; t2 += s_c[i]; }
+    if (metric == 0)
+      sim[(long long)b * N + n] = -t0;
+    else
+      sim[(long long)b * N + n] = t0 / (fmaxf(sqrtf(t1), 1e-8f) * fmaxf(sqrtf(t2), 1e-8f));
+  }
+}
+
+// ----------------------------------------------------------------------------
+// sim = -(sum of slab partials) and top-k (model.py:265 topk(k=5)); descending score,
+// ties -> lowest index.  One CTA per batch row.  idx_base is added to the indices so a
+// shard reports global pose indices.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sim_topk_kernel(const float* __restrict__ partial, int nslab, float* __restrict__ sim, int N,
+                int k, float* __restrict__ top_val, long long* __restrict__ top_idx,
+                long long idx_base) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  __shared__ int s_chosen[64];
+  const int b = blockIdx.x;
+  float* srow = sim + (long long)b * N;
+  if (partial) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float t = 0.f;
+      for (int s = 0; s < nslab; ++s) t += partial[((long long)b * N + n) * nslab + s];
+      srow[n] = -t;
+    }
+    __syncthreads();
+  }
+  if (k <= 0) return;
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      bool used = false;
+      for (int c = 0; c < r; ++c) used |= (s_chosen[c] == n);
+      if (used) continue;
+      const float v = srow[n];
+      if (v > bv || (v == bv && n < bi) || bi == 0x7fffffff) { bv = v; bi = n; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        const float ov = s_v[w];
+        const int oi = s_i[w];
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      s_chosen[r] = bi;
+      top_val[(long long)b * k + r] = bv;
+      top_idx[(long long)b * k + r] = (bi == 0x7fffffff) ? -1 : (long long)bi + idx_base;
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------
+// SIMT implicit-GEMM convolution: a slow, obviously-correct CUDA-core twin of the
+// tcgen05 kernel (same packed weights, same segment semantics).  Debug / bring-up
+// only (NOPE_CONV_IMPL=simt); never the default path.
+// mode 0: 3x3 pad 1; mode 1: 1x1; mode 2: pixel-unshuffle(2) + 1x1 (input is 2H x 2W).
+// ----------------------------------------------------------------------------
+struct SimtConvArgs {
+  const __half* src0;
+  const __half* src1;
+  int C0, C1;
+  const __half* w;   // [Cout][K]
+  const float* bias;
+  __half* out;
+  int n_img, H, W, Cout, K, mode;
+};
+
+__global__ void conv_simt_kernel(const SimtConvArgs a) {
+  const long long total = (long long)a.n_img * a.H * a.W * a.Cout;
+  const int Ccat = a.C0 + a.C1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % a.Cout);
+    const int px = (int)((i / a.Cout) % a.W);
+    const int py = (int)((i / ((long long)a.Cout * a.W)) % a.H);
+    const int b = (int)(i / ((long long)a.Cout * a.W * a.H));
+    const __half* wr = a.w + (long long)o * a.K;
+    float acc = a.bias ? a.bias[o] : 0.f;
+    const int taps = a.mode == 0 ? 9 : (a.mode == 1 ? 1 : 4);
+    for (int t = 0; t < taps; ++t) {
+      int yy, xx, Hs = a.H, Ws = a.W;
+      if (a.mode == 0) { yy = py + t / 3 - 1; xx = px + t % 3 - 1; }
+      else if (a.mode == 1) { yy = py; xx = px; }
+      else { Hs = 2 * a.H; Ws = 2 * a.W; yy = 2 * py + t / 2; xx = 2 * px + t % 2; }
+      if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
+      const long long pix = ((long long)b * Hs + yy) * Ws + xx;
+      const __half* s0 = a.src0 + pix * a.C0;
+      const __half* wk = wr + t * Ccat;
+      for (int c = 0; c < a.C0; c += 2) {
+        const float2 x = __half22float2(*reinterpret_cast<const __half2*>(s0 + c));
+        const float2 y = __half22float2(*reinterpret_cast<const __half2*>(wk + c));
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+      }
+      if (a.src1) {
+        const __half* s1 = a.src1 + pix * a.C1;
+        for (int c = 0; c < a.C1; c += 2) {
+          const float2 x = __half22float2(*reinterpret_cast<const __half2*>(s1 + c));
+          const float2 y = __half22float2(*reinterpret_cast<const __half2*>(wk + a.C0 + c));
+          acc = fmaf(x.x, y.x, acc);
+          acc = fmaf(x.y, y.y, acc);
+        }
+      }
+    }
+    a.out[i] = __float2half_rn(acc);
+  }
+}
+
+// fp32 NCHW <-> fp16 NHWC helpers for the per-op test entry points
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y,
+                                            int n_img, int C, int hw) {
+  const long long total = (long long)n_img * C * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int p = (int)((i / C) % hw);
+    const int b = (int)(i / ((long long)C * hw));
+    y[i] = __float2half_rn(x[((long long)b * C + c) * hw + p]);
+  }
+}
+__global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y,
+                                            int n_img, int C, int hw) {
+  const long long total = (long long)n_img * C * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % hw);
+    const int c = (int)((i / hw) % C);
+    const int b = (int)(i / ((long long)C * hw));
+    y[i] = __half2float(x[((long long)b * hw + p) * C + c]);
+  }
+}
+
+inline int ew_grid(long long total, int threads = 256, int cap = 148 * 16) {
+  long long g = (total + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace nope

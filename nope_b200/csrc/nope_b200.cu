@@ -1,0 +1,972 @@
+// nope_b200 -- engine + C ABI (include/nope_b200.h).
+//
+// The engine owns the repacked UNet weights, a per-chunk activation workspace and the
+// layer schedule of UNet.forward (reference:
+// src/model/u_net/denoising_diffusion_pytorch/u_net.py:160-198), batched over all pose
+// hypotheses of a chunk.  Host code is plain C++; kernels live in conv_tc.cuh / kernels.cuh.
+#include "../../include/nope_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+using namespace nope;
+
+namespace {
+
+constexpr int kAbiVersion = 1;
+constexpr int kHeadsHidden = 128;  // 4 heads x 32 (model_utils.py:368,394)
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct ConvLayer {
+  int mode = 0;  // 0: 3x3 pad1, 1: 1x1, 2: unshuffle+1x1
+  int cin = 0, cout = 0, K = 0, bn = 0;
+  __half* w = nullptr;    // [cout][K] fp16
+  float* bias = nullptr;  // [cout] fp32 or nullptr
+  CUtensorMap wmap;
+  bool has_map = false;
+};
+
+struct NormLayer {
+  float* gamma = nullptr;
+  float* beta = nullptr;
+  int C = 0, G = 1;
+};
+
+struct Act {  // NHWC fp16 activation [n_img, S, S, C]
+  __half* p = nullptr;
+  int C = 0;
+  int S = 0;  // spatial side
+};
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+  NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return 0;
+}
+
+}  // namespace
+
+struct nope_unet {
+  int dim = 0, Cl = 0, S0 = 0, rot_dim = 6, cemb = 0, device = 0, num_sms = 148;
+  int dims[5] = {0, 0, 0, 0, 0};
+  bool finalized = false;
+  int conv_impl = 0;
+  int chunk = 256;
+  int64_t launches = 0;
+
+  std::map<std::string, HostTensor> host;
+  std::map<std::string, std::vector<int64_t>> expected;  // key -> shape
+
+  std::map<std::string, ConvLayer> convs;
+  std::map<std::string, NormLayer> norms;
+  std::map<std::string, int> pb_off;
+  int P = 0;  // total pose-projection width
+  ConvLayer poseproj;
+  float *pose_w = nullptr, *pose_b = nullptr, *init_w = nullptr, *init_b = nullptr,
+        *final_w = nullptr, *final_b = nullptr;
+  std::vector<void*> owned;  // every cudaMalloc'd pointer
+
+  // workspace
+  int cap = 0, cap_ref = 0;
+  Act sk[4][2];
+  __half *TA = nullptr, *TB = nullptr, *TC = nullptr, *TD = nullptr, *XA = nullptr, *XB = nullptr,
+         *RB = nullptr, *cs = nullptr, *pb = nullptr;
+  __half *x0 = nullptr, *g1 = nullptr, *pt = nullptr;  // per-reference pre-stage
+  float2* gn_partial = nullptr;
+  int* ref_of = nullptr;
+  float* score_partial = nullptr;
+  size_t score_partial_cap = 0;
+  float* sim_buf = nullptr;
+  size_t sim_buf_cap = 0;
+  std::vector<void*> ws_owned;
+
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;
+
+  // debug tap
+  std::string tap_name;
+  float* tap_out = nullptr;
+  int64_t tap_cap = 0;
+  int tap_C = 0, tap_S = 0;
+  bool tap_hit = false;
+
+  ~nope_unet() {
+    for (void* p : owned) cudaFree(p);
+    for (void* p : ws_owned) cudaFree(p);
+    if (score_partial) cudaFree(score_partial);
+    if (sim_buf) cudaFree(sim_buf);
+  }
+
+  // ------------------------------------------------------------------ schema
+  void expect(const std::string& k, std::vector<int64_t> s) { expected[k] = std::move(s); }
+  void expect_resblock(const std::string& p, int cin, int cout, bool mlp = true) {
+    if (mlp) {
+      expect(p + ".mlp.1.weight", {cout, cemb});
+      expect(p + ".mlp.1.bias", {cout});
+    }
+    expect(p + ".block1.proj.weight", {cout, cin, 3, 3});
+    expect(p + ".block1.proj.bias", {cout});
+    expect(p + ".block1.norm.weight", {cout});
+    expect(p + ".block1.norm.bias", {cout});
+    expect(p + ".block2.proj.weight", {cout, cout, 3, 3});
+    expect(p + ".block2.proj.bias", {cout});
+    expect(p + ".block2.norm.weight", {cout});
+    expect(p + ".block2.norm.bias", {cout});
+    if (cin != cout) {
+      expect(p + ".res_conv.weight", {cout, cin, 1, 1});
+      expect(p + ".res_conv.bias", {cout});
+    }
+  }
+  void expect_linattn(const std::string& p, int d) {
+    expect(p + ".fn.fn.to_qkv.weight", {3 * kHeadsHidden, d, 1, 1});
+    expect(p + ".fn.fn.to_out.0.weight", {d, kHeadsHidden, 1, 1});
+    expect(p + ".fn.fn.to_out.0.bias", {d});
+    expect(p + ".fn.fn.to_out.1.weight", {d});
+    expect(p + ".fn.fn.to_out.1.bias", {d});
+    expect(p + ".fn.norm.weight", {d});
+    expect(p + ".fn.norm.bias", {d});
+  }
+  // state_dict schema of the reference UNet (u_net.py:27-158), encoder excluded.
+  void build_schema() {
+    expect("pose_mlp.0.weight", {cemb, rot_dim});
+    expect("pose_mlp.0.bias", {cemb});
+    expect("init_conv.weight", {dim, Cl, 3, 3});
+    expect("init_conv.bias", {dim});
+    for (int i = 0; i < 4; ++i) {
+      const int din = dims[i], dout = dims[i + 1];
+      const std::string p = "downs." + std::to_string(i);
+      expect_resblock(p + ".0", din, din);
+      expect_resblock(p + ".1", din, din);
+      expect_linattn(p + ".2", din);
+      if (i < 3) {
+        expect(p + ".3.1.weight", {dout, din * 4, 1, 1});
+        expect(p + ".3.1.bias", {dout});
+      } else {
+        expect(p + ".3.weight", {dout, din, 3, 3});
+        expect(p + ".3.bias", {dout});
+      }
+    }
+    const int mid = dims[4];
+    expect("mid_attn.fn.fn.to_qkv.weight", {3 * kHeadsHidden, mid, 1, 1});
+    expect("mid_attn.fn.fn.to_out.weight", {mid, kHeadsHidden, 1, 1});
+    expect("mid_attn.fn.fn.to_out.bias", {mid});
+    expect("mid_attn.fn.norm.weight", {mid});
+    expect("mid_attn.fn.norm.bias", {mid});
+    expect_resblock("mid_block1", mid, mid);
+    expect_resblock("mid_block2", mid, mid);
+    for (int j = 0; j < 4; ++j) {
+      const int din = dims[3 - j], dout = dims[4 - j];
+      const std::string p = "ups." + std::to_string(j);
+      expect_resblock(p + ".0", dout + din, dout);
+      expect_resblock(p + ".1", dout + din, dout);
+      expect_linattn(p + ".2", dout);
+      if (j < 3) {
+        expect(p + ".3.1.weight", {din, dout, 3, 3});
+        expect(p + ".3.1.bias", {din});
+      } else {
+        expect(p + ".3.weight", {din, dout, 3, 3});
+        expect(p + ".3.bias", {din});
+      }
+    }
+    expect_resblock("final_res_block", 2 * dim, dim);
+    expect_resblock("final_conv.0", dim, dim);  // owns an unused mlp.1 (u_net.py:154-157)
+    expect("final_conv.1.weight", {Cl, dim, 1, 1});
+    expect("final_conv.1.bias", {Cl});
+  }
+
+  // ------------------------------------------------------------------ weights
+  int upload_f32(const std::string& key, float** out) {
+    auto it = host.find(key);
+    NOPE_CHECK(it != host.end(), "missing tensor " + key);
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(out), it->second.data.size() * sizeof(float)));
+    owned.push_back(*out);
+    NOPE_CUDA(cudaMemcpy(*out, it->second.data.data(), it->second.data.size() * sizeof(float),
+                         cudaMemcpyHostToDevice));
+    return 0;
+  }
+  // pack one conv weight (+ bias) into a ConvLayer
+  int make_conv(const std::string& name, const std::string& wkey, const std::string& bkey, int mode) {
+    auto it = host.find(wkey);
+    NOPE_CHECK(it != host.end(), "missing tensor " + wkey);
+    const auto& sh = it->second.shape;
+    ConvLayer L;
+    L.mode = mode;
+    L.cout = (int)sh[0];
+    const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
+    L.cin = mode == 2 ? (int)sh[1] / 4 : (int)sh[1];
+    L.K = L.cin * taps;
+    NOPE_CHECK(L.cin % 64 == 0, wkey + ": input channels must be a multiple of 64");
+    L.bn = pick_bn(L.cout);
+    NOPE_CHECK(L.bn != 0, wkey + ": output channels must be a multiple of 64");
+    float* tmp = nullptr;
+    const size_t n = it->second.data.size();
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), n * sizeof(float)));
+    NOPE_CUDA(cudaMemcpy(tmp, it->second.data.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w), n * sizeof(__half)));
+    owned.push_back(L.w);
+    pack_weight_kernel<<<ew_grid((long long)n), 256>>>(tmp, L.w, L.cout, L.cin, taps, L.K, 0);
+    NOPE_CUDA(cudaGetLastError());
+    NOPE_CUDA(cudaDeviceSynchronize());
+    NOPE_CUDA(cudaFree(tmp));
+    if (!bkey.empty()) {
+      if (upload_f32(bkey, &L.bias)) return -1;
+    }
+    if (make_weight_map(&L.wmap, L.w, L.cout, L.K, L.bn)) return -1;
+    L.has_map = true;
+    convs[name] = L;
+    return 0;
+  }
+  int make_norm(const std::string& name, const std::string& prefix, int G) {
+    NormLayer n;
+    auto it = host.find(prefix + ".weight");
+    NOPE_CHECK(it != host.end(), "missing tensor " + prefix + ".weight");
+    n.C = (int)it->second.shape[0];
+    n.G = G;
+    NOPE_CHECK(n.C % (8 * G) == 0, prefix + ": channels per group must be a multiple of 8");
+    if (upload_f32(prefix + ".weight", &n.gamma)) return -1;
+    if (upload_f32(prefix + ".bias", &n.beta)) return -1;
+    norms[name] = n;
+    return 0;
+  }
+  int make_resblock(const std::string& p) {
+    if (make_conv(p + ".block1", p + ".block1.proj.weight", p + ".block1.proj.bias", 0)) return -1;
+    if (make_conv(p + ".block2", p + ".block2.proj.weight", p + ".block2.proj.bias", 0)) return -1;
+    if (make_norm(p + ".norm1", p + ".block1.norm", 8)) return -1;
+    if (make_norm(p + ".norm2", p + ".block2.norm", 8)) return -1;
+    if (host.count(p + ".res_conv.weight"))
+      if (make_conv(p + ".res", p + ".res_conv.weight", p + ".res_conv.bias", 1)) return -1;
+    return 0;
+  }
+  int make_linattn(const std::string& p) {
+    if (make_norm(p + ".prenorm", p + ".fn.norm", 1)) return -1;
+    if (make_conv(p + ".qkv", p + ".fn.fn.to_qkv.weight", "", 1)) return -1;
+    if (make_conv(p + ".out", p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", 1)) return -1;
+    if (make_norm(p + ".outnorm", p + ".fn.fn.to_out.1", 1)) return -1;
+    return 0;
+  }
+  // concatenate the 19 pose projections (model_utils.py:261-263) into one [P, cemb] GEMM
+  int make_poseproj() {
+    std::vector<std::string> blocks;
+    for (int i = 0; i < 4; ++i)
+      for (int b = 0; b < 2; ++b) blocks.push_back("downs." + std::to_string(i) + "." + std::to_string(b));
+    blocks.push_back("mid_block1");
+    blocks.push_back("mid_block2");
+    for (int j = 0; j < 4; ++j)
+      for (int b = 0; b < 2; ++b) blocks.push_back("ups." + std::to_string(j) + "." + std::to_string(b));
+    blocks.push_back("final_res_block");
+    std::vector<float> w, bias;
+    P = 0;
+    for (const auto& b : blocks) {
+      const HostTensor& hw = host.at(b + ".mlp.1.weight");
+      const HostTensor& hb = host.at(b + ".mlp.1.bias");
+      pb_off[b] = P;
+      P += (int)hw.shape[0];
+      w.insert(w.end(), hw.data.begin(), hw.data.end());
+      bias.insert(bias.end(), hb.data.begin(), hb.data.end());
+    }
+    HostTensor tw;
+    tw.shape = {P, cemb, 1, 1};
+    tw.data = std::move(w);
+    HostTensor tb;
+    tb.shape = {P};
+    tb.data = std::move(bias);
+    host["__poseproj.weight"] = std::move(tw);
+    host["__poseproj.bias"] = std::move(tb);
+    if (make_conv("__poseproj", "__poseproj.weight", "__poseproj.bias", 1)) return -1;
+    poseproj = convs["__poseproj"];
+    return 0;
+  }
+
+  int finalize() {
+    NOPE_CHECK(!finalized, "already finalized");
+    for (const auto& kv : expected)
+      NOPE_CHECK(host.count(kv.first), "state_dict is missing " + kv.first);
+    NOPE_CUDA(cudaSetDevice(device));
+    if (upload_f32("pose_mlp.0.weight", &pose_w) || upload_f32("pose_mlp.0.bias", &pose_b) ||
+        upload_f32("init_conv.weight", &init_w) || upload_f32("init_conv.bias", &init_b) ||
+        upload_f32("final_conv.1.weight", &final_w) || upload_f32("final_conv.1.bias", &final_b))
+      return -1;
+    for (int i = 0; i < 4; ++i) {
+      const std::string p = "downs." + std::to_string(i);
+      if (make_resblock(p + ".0") || make_resblock(p + ".1") || make_linattn(p + ".2")) return -1;
+      if (i < 3) {
+        if (make_conv(p + ".3", p + ".3.1.weight", p + ".3.1.bias", 2)) return -1;
+      } else {
+        if (make_conv(p + ".3", p + ".3.weight", p + ".3.bias", 0)) return -1;
+      }
+    }
+    if (make_resblock("mid_block1") || make_resblock("mid_block2")) return -1;
+    if (make_norm("mid_attn.prenorm", "mid_attn.fn.norm", 1)) return -1;
+    if (make_conv("mid_attn.qkv", "mid_attn.fn.fn.to_qkv.weight", "", 1)) return -1;
+    if (make_conv("mid_attn.out", "mid_attn.fn.fn.to_out.weight", "mid_attn.fn.fn.to_out.bias", 1))
+      return -1;
+    for (int j = 0; j < 4; ++j) {
+      const std::string p = "ups." + std::to_string(j);
+      if (make_resblock(p + ".0") || make_resblock(p + ".1") || make_linattn(p + ".2")) return -1;
+      if (j < 3) {
+        if (make_conv(p + ".3", p + ".3.1.weight", p + ".3.1.bias", 0)) return -1;
+      } else {
+        if (make_conv(p + ".3", p + ".3.weight", p + ".3.bias", 0)) return -1;
+      }
+    }
+    if (make_resblock("final_res_block") || make_resblock("final_conv.0")) return -1;
+    if (make_poseproj()) return -1;
+    host.clear();
+    finalized = true;
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ workspace
+  int ws_alloc_half(__half** p, size_t n) {
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(__half)));
+    ws_owned.push_back(*p);
+    return 0;
+  }
+  int ensure_workspace(int need_cap, int need_ref) {
+    if (need_cap <= cap && need_ref <= cap_ref) return 0;
+    NOPE_CUDA(cudaDeviceSynchronize());
+    for (void* p : ws_owned) cudaFree(p);
+    ws_owned.clear();
+    tmaps.clear();
+    cap = std::max(cap, need_cap);
+    cap_ref = std::max(cap_ref, need_ref);
+    const size_t c = (size_t)cap;
+    const size_t big = (size_t)S0 * S0 * dim * 2;  // S0^2 x 2*dim halfs (qkv / upsampled input)
+    for (int i = 0; i < 4; ++i) {
+      const int s = S0 >> i;
+      for (int b = 0; b < 2; ++b) {
+        sk[i][b].C = dims[i];
+        sk[i][b].S = s;
+        if (ws_alloc_half(&sk[i][b].p, c * s * s * dims[i])) return -1;
+      }
+    }
+    if (ws_alloc_half(&TA, c * big) || ws_alloc_half(&TB, c * big) || ws_alloc_half(&TC, c * big) ||
+        ws_alloc_half(&TD, c * big) || ws_alloc_half(&XA, c * big / 2) ||
+        ws_alloc_half(&XB, c * big / 2) || ws_alloc_half(&RB, c * big / 2) ||
+        ws_alloc_half(&cs, c * cemb) || ws_alloc_half(&pb, c * P))
+      return -1;
+    const size_t r = (size_t)cap_ref;
+    if (ws_alloc_half(&x0, r * big / 2) || ws_alloc_half(&g1, r * big / 2) ||
+        ws_alloc_half(&pt, r * big / 2))
+      return -1;
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&gn_partial),
+                         (size_t)std::max(cap, cap_ref) * 8 * 8 * sizeof(float2)));
+    ws_owned.push_back(gn_partial);
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&ref_of), (size_t)std::max(cap, cap_ref) * sizeof(int)));
+    ws_owned.push_back(ref_of);
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ tensor maps
+  int get_map(const CUtensorMap** out, const void* base, int cap_img, int C, const TileGeom& g,
+              int kind /* -1: plain, 0..3: unshuffle (p1*2+p2) */) {
+    auto key = std::make_tuple(base, cap_img * 8 + (kind + 1), C, g.H, g.W);
+    auto it = tmaps.find(key);
+    if (it == tmaps.end()) {
+      CUtensorMap m;
+      int rc = kind < 0 ? make_act_map(&m, base, cap_img, C, g)
+                        : make_unshuffle_map(&m, base, cap_img, C, g, kind >> 1, kind & 1);
+      if (rc) return -1;
+      it = tmaps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ op launchers
+  // out[n_img, So, So, cout] = conv(L, in0 (++ in1))
+  int conv(const ConvLayer& L, const __half* in0, int c0, const __half* in1, int c1, __half* out,
+           int So, int n_img, int cap_img, cudaStream_t st) {
+    NOPE_CHECK(c0 + c1 == L.cin, "conv: channel mismatch");
+    ++launches;
+    if (conv_impl == 1) {
+      SimtConvArgs a;
+      a.src0 = in0; a.src1 = in1; a.C0 = c0; a.C1 = c1; a.w = L.w; a.bias = L.bias; a.out = out;
+      a.n_img = n_img; a.H = So; a.W = So; a.Cout = L.cout; a.K = L.K; a.mode = L.mode;
+      conv_simt_kernel<<<ew_grid((long long)n_img * So * So * L.cout, 256, 148 * 32), 256, 0, st>>>(a);
+      NOPE_CUDA(cudaGetLastError());
+      return 0;
+    }
+    TileGeom g;
+    if (make_geom(So, So, &g)) return -1;
+    ConvParams p;
+    memset(&p, 0, sizeof p);
+    const CUtensorMap* m = nullptr;
+    int nseg = 0, ksteps = 0;
+    if (L.mode == 2) {
+      NOPE_CHECK(in1 == nullptr, "unshuffle conv takes one source");
+      for (int t = 0; t < 4; ++t) {
+        if (get_map(&m, in0, cap_img, c0, g, t)) return -1;
+        p.amap[t] = *m;
+        p.seg[nseg++] = ConvSeg{(int16_t)t, 0, 0, (int16_t)(c0 / 64)};
+        ksteps += c0 / 64;
+      }
+    } else {
+      if (get_map(&m, in0, cap_img, c0, g, -1)) return -1;
+      p.amap[0] = *m;
+      if (in1) {
+        if (get_map(&m, in1, cap_img, c1, g, -1)) return -1;
+        p.amap[1] = *m;
+      } else {
+        p.amap[1] = p.amap[0];
+      }
+      p.amap[2] = p.amap[0];
+      p.amap[3] = p.amap[0];
+      const int taps = L.mode == 0 ? 9 : 1;
+      for (int t = 0; t < taps; ++t) {
+        const int dy = L.mode == 0 ? t / 3 - 1 : 0, dx = L.mode == 0 ? t % 3 - 1 : 0;
+        p.seg[nseg++] = ConvSeg{0, (int16_t)dy, (int16_t)dx, (int16_t)(c0 / 64)};
+        ksteps += c0 / 64;
+        if (in1) {
+          p.seg[nseg++] = ConvSeg{1, (int16_t)dy, (int16_t)dx, (int16_t)(c1 / 64)};
+          ksteps += c1 / 64;
+        }
+      }
+    }
+    p.bmap = L.wmap;
+    if (get_map(&m, out, cap_img, L.cout, g, -1)) return -1;
+    p.omap = *m;
+    p.bias = L.bias;
+    p.nseg = nseg;
+    p.ksteps = ksteps;
+    p.m_tiles = geom_m_tiles(g, n_img);
+    p.n_tiles = L.cout / L.bn;
+    p.tiles_per_img = g.tiles_per_img;
+    p.h_cnt = g.h_cnt;
+    p.b_cnt = g.b_cnt;
+    NOPE_CHECK(ksteps * 64 == L.K, "conv: K mismatch");
+    return launch_conv_tc(p, L.bn, num_sms, st);
+  }
+
+  static int gn_nslab(int hw) { return hw >= 1024 ? 8 : (hw >= 256 ? 2 : 1); }
+
+  // y = [silu](GN(x)) + pb[:, off:off+C] + res
+  int gn(const NormLayer* N, const __half* x, __half* y, int S, int C, int n_img, bool silu,
+         int pb_offset, const __half* res, const int* res_map, cudaStream_t st) {
+    const int hw = S * S;
+    const int nslab = gn_nslab(hw);
+    const int threads = (C / 8) * gn_rows(C);
+    NOPE_CHECK(threads <= 1024 && C % 8 == 0, "gn: unsupported channel count");
+    if (N) {
+      NOPE_CHECK(N->C == C, "gn: channel mismatch");
+      gn_stats_kernel<<<dim3(nslab, n_img), threads, threads * sizeof(float2), st>>>(
+          x, gn_partial, hw, C, N->G, nslab);
+      NOPE_CUDA(cudaGetLastError());
+      ++launches;
+    }
+    GnApplyArgs a;
+    a.x = x; a.y = y; a.partial = N ? gn_partial : nullptr;
+    a.gamma = N ? N->gamma : nullptr; a.beta = N ? N->beta : nullptr;
+    a.pb = pb_offset >= 0 ? pb : nullptr; a.pb_stride = P; a.pb_off = pb_offset >= 0 ? pb_offset : 0;
+    a.res = res; a.res_of = res_map;
+    a.hw = hw; a.C = C; a.G = N ? N->G : 1; a.nslab_stats = nslab; a.nslab = nslab;
+    a.silu = silu ? 1 : 0; a.eps = 1e-5f;
+    gn_apply_kernel<<<dim3(nslab, n_img), threads, 0, st>>>(a);
+    NOPE_CUDA(cudaGetLastError());
+    ++launches;
+    return 0;
+  }
+
+  int tap(const char* name, const __half* buf, int C, int S, int n, cudaStream_t st) {
+    if (tap_out == nullptr || tap_name != name || tap_hit) return 0;
+    NOPE_CHECK((int64_t)n * C * S * S <= tap_cap, "debug tap: output buffer too small");
+    nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * C * S * S), 256, 0, st>>>(buf, tap_out, n, C, S * S);
+    NOPE_CUDA(cudaGetLastError());
+    tap_C = C; tap_S = S; tap_hit = true;
+    return 0;
+  }
+
+  // ResnetBlock.forward (model_utils.py:271-279) on NHWC fp16
+  int resblock(const std::string& p, const __half* in0, int c0, const __half* in1, int c1,
+               __half* out, int S, int n, bool pose, cudaStream_t st) {
+    const ConvLayer& b1 = convs.at(p + ".block1");
+    const ConvLayer& b2 = convs.at(p + ".block2");
+    const int co = b1.cout;
+    if (conv(b1, in0, c0, in1, c1, TA, S, n, cap, st)) return -1;
+    if (gn(&norms.at(p + ".norm1"), TA, TB, S, co, n, true, pose ? pb_off.at(p) : -1, nullptr, nullptr, st))
+      return -1;
+    if (conv(b2, TB, co, nullptr, 0, TA, S, n, cap, st)) return -1;
+    const __half* res = in0;
+    auto it = convs.find(p + ".res");
+    if (it != convs.end()) {
+      if (conv(it->second, in0, c0, in1, c1, TC, S, n, cap, st)) return -1;
+      res = TC;
+    } else {
+      NOPE_CHECK(in1 == nullptr && c0 == co, "resblock: identity residual needs Cin == Cout");
+    }
+    return gn(&norms.at(p + ".norm2"), TA, out, S, co, n, true, -1, res, nullptr, st);
+  }
+
+  // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418)
+  int linattn(const std::string& p, const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
+    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st)) return -1;
+    if (conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
+    linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD, TC, S * S);
+    NOPE_CUDA(cudaGetLastError());
+    ++launches;
+    if (conv(convs.at(p + ".out"), TC, kHeadsHidden, nullptr, 0, TA, S, n, cap, st)) return -1;
+    return gn(&norms.at(p + ".outnorm"), TA, out, S, C, n, false, -1, x, nullptr, st);
+  }
+
+  // Residual(PreNorm(Attention)) (model_utils.py:367-390)
+  int midattn(const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
+    NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
+    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st)) return -1;
+    if (conv(convs.at("mid_attn.qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
+    midattn_kernel<<<n, 128, 0, st>>>(TD, TC, S * S);
+    NOPE_CUDA(cudaGetLastError());
+    ++launches;
+    if (conv(convs.at("mid_attn.out"), TC, kHeadsHidden, nullptr, 0, TA, S, n, cap, st)) return -1;
+    return gn(nullptr, TA, out, S, C, n, false, -1, x, nullptr, st);
+  }
+
+  // pose-independent prefix, once per reference image: x0 = init_conv(ref),
+  // g1 = SiLU(GN(downs.0.0.block1.proj(x0)))   (u_net.py:161; model_utils.py:272)
+  int prestage(const float* ref_feat, int B, cudaStream_t st) {
+    init_conv_kernel<<<ew_grid((long long)B * S0 * S0 * dim), 256, 0, st>>>(ref_feat, init_w, init_b, x0,
+                                                                            B, Cl, S0, S0, dim);
+    NOPE_CUDA(cudaGetLastError());
+    ++launches;
+    if (conv(convs.at("downs.0.0.block1"), x0, dim, nullptr, 0, pt, S0, B, cap_ref, st)) return -1;
+    return gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st);
+  }
+
+  // UNet.forward for hypotheses [hyp0, hyp0 + n) of the flattened (b, pose) list
+  int forward_chunk(const float* poses, int hyp0, int n, int N, const float* query_feat,
+                    float* out_emb, float* score_part, cudaStream_t st) {
+    // hypothesis -> reference image
+    iota_div(ref_of, hyp0, N, n, st);
+    // pose embedding + all 19 pose projections in one GEMM
+    pose_embed_kernel<<<n, 256, rot_dim * sizeof(float), st>>>(poses + (size_t)hyp0 * rot_dim, pose_w,
+                                                               pose_b, cs, n, rot_dim, cemb);
+    NOPE_CUDA(cudaGetLastError());
+    ++launches;
+    if (conv_pose(n, st)) return -1;
+
+    // r (= init_conv output) and the hoisted block1 output, broadcast per hypothesis
+    const int hw0 = S0 * S0;
+    bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
+        x0, ref_of, nullptr, 0, 0, RB, n, hw0, dim);
+    bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
+        g1, ref_of, pb, P, pb_off.at("downs.0.0"), TB, n, hw0, dim);
+    NOPE_CUDA(cudaGetLastError());
+    launches += 2;
+    if (tap("init_conv", RB, dim, S0, n, st)) return -1;
+
+    // ---- downs
+    __half* cur = nullptr;
+    int S = S0;
+    for (int i = 0; i < 4; ++i) {
+      const int C = dims[i];
+      const std::string p = "downs." + std::to_string(i);
+      if (i == 0) {
+        // block 0 with its block1 half hoisted: TB already holds SiLU(GN(conv(x0))) + pose bias
+        if (conv(convs.at(p + ".0.block2"), TB, C, nullptr, 0, TA, S, n, cap, st)) return -1;
+        if (gn(&norms.at(p + ".0.norm2"), TA, sk[0][0].p, S, C, n, true, -1, x0, ref_of, st)) return -1;
+      } else {
+        if (resblock(p + ".0", cur, C, nullptr, 0, sk[i][0].p, S, n, true, st)) return -1;
+      }
+      if (tap((p + ".0").c_str(), sk[i][0].p, C, S, n, st)) return -1;
+      if (resblock(p + ".1", sk[i][0].p, C, nullptr, 0, XA, S, n, true, st)) return -1;
+      if (tap((p + ".1").c_str(), XA, C, S, n, st)) return -1;
+      if (linattn(p + ".2", XA, sk[i][1].p, C, S, n, st)) return -1;
+      if (tap((p + ".2").c_str(), sk[i][1].p, C, S, n, st)) return -1;
+      if (i < 3) S >>= 1;
+      if (conv(convs.at(p + ".3"), sk[i][1].p, C, nullptr, 0, XB, S, n, cap, st)) return -1;
+      if (tap((p + ".3").c_str(), XB, dims[i + 1], S, n, st)) return -1;
+      cur = XB;
+    }
+    // ---- mid, twice with shared weights (u_net.py:177-183)
+    const int Cm = dims[4];
+    for (int rep = 0; rep < 2; ++rep) {
+      if (resblock("mid_block1", XB, Cm, nullptr, 0, XA, S, n, true, st)) return -1;
+      if (midattn(XA, XB, Cm, S, n, st)) return -1;
+      if (resblock("mid_block2", XB, Cm, nullptr, 0, XA, S, n, true, st)) return -1;
+      if (tap(rep == 0 ? "mid.0" : "mid.1", XA, Cm, S, n, st)) return -1;
+      std::swap(XA, XB);
+    }
+    cur = XB;
+    __half* oth = XA;
+    // ---- ups
+    for (int j = 0; j < 4; ++j) {
+      const int din = dims[3 - j], dout = dims[4 - j];
+      const std::string p = "ups." + std::to_string(j);
+      if (resblock(p + ".0", cur, dout, sk[3 - j][1].p, din, oth, S, n, true, st)) return -1;
+      std::swap(cur, oth);
+      if (tap((p + ".0").c_str(), cur, dout, S, n, st)) return -1;
+      if (resblock(p + ".1", cur, dout, sk[3 - j][0].p, din, oth, S, n, true, st)) return -1;
+      std::swap(cur, oth);
+      if (linattn(p + ".2", cur, oth, dout, S, n, st)) return -1;
+      std::swap(cur, oth);
+      if (tap((p + ".2").c_str(), cur, dout, S, n, st)) return -1;
+      if (j < 3) {
+        upsample2x_kernel<<<ew_grid((long long)n * 4 * S * S * dout / 8), 256, 0, st>>>(cur, TD, n, S, S, dout);
+        NOPE_CUDA(cudaGetLastError());
+        ++launches;
+        S <<= 1;
+        if (conv(convs.at(p + ".3"), TD, dout, nullptr, 0, oth, S, n, cap, st)) return -1;
+      } else {
+        if (conv(convs.at(p + ".3"), cur, dout, nullptr, 0, oth, S, n, cap, st)) return -1;
+      }
+      std::swap(cur, oth);
+      if (tap((p + ".3").c_str(), cur, din, S, n, st)) return -1;
+    }
+    // ---- head
+    if (resblock("final_res_block", cur, dim, RB, dim, oth, S, n, true, st)) return -1;
+    std::swap(cur, oth);
+    if (tap("final_res_block", cur, dim, S, n, st)) return -1;
+    if (resblock("final_conv.0", cur, dim, nullptr, 0, oth, S, n, false, st)) return -1;
+    std::swap(cur, oth);
+    if (tap("final_conv.0", cur, dim, S, n, st)) return -1;
+    XA = cur;  // keep the ping-pong pair consistent for the next chunk
+    XB = oth;
+    const int hw = S * S;
+    const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
+    final_conv_score_kernel<<<dim3(nslab, n), kFinalThreads, (size_t)Cl * dim * sizeof(float), st>>>(
+        cur, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat, ref_of,
+        score_part ? score_part + (size_t)hyp0 * nslab : nullptr, hw, dim, Cl);
+    NOPE_CUDA(cudaGetLastError());
+    ++launches;
+    return 0;
+  }
+
+  int iota_div(int* r, int h0, int N, int n, cudaStream_t st);
+  int conv_pose(int n, cudaStream_t st) {
+    // pb[n, P] = cs[n, cemb] @ Wp^T + bp : the 1x1 "image" geometry of the conv kernel
+    return conv(poseproj, cs, cemb, nullptr, 0, pb, 1, n, cap, st);
+  }
+};
+
+namespace {
+__global__ void iota_div_kernel(int* r, int h0, int N, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) r[i] = (h0 + i) / N;
+}
+}  // namespace
+
+int nope_unet::iota_div(int* r, int h0, int N, int n, cudaStream_t st) {
+  iota_div_kernel<<<(n + 255) / 256, 256, 0, st>>>(r, h0, N, n);
+  ++launches;
+  return 0;
+}
+
+namespace {
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  template <typename T> int get(T** out, size_t n) {
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(out), std::max<size_t>(n, 1) * sizeof(T)));
+    p.push_back(*out);
+    return 0;
+  }
+};
+int to_nhwc(const float* x, __half** out, Scratch& s, int n, int C, int hw, cudaStream_t st) {
+  if (s.get(out, (size_t)n * C * hw)) return -1;
+  nchw_f32_to_nhwc_f16_kernel<<<ew_grid((long long)n * C * hw), 256, 0, st>>>(x, *out, n, C, hw);
+  NOPE_CUDA(cudaGetLastError());
+  return 0;
+}
+int to_nchw(const __half* x, float* out, int n, int C, int hw, cudaStream_t st) {
+  nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * C * hw), 256, 0, st>>>(x, out, n, C, hw);
+  NOPE_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+const char* nope_last_error(void) { return last_error().c_str(); }
+int nope_abi_version(void) { return kAbiVersion; }
+const char* nope_build_arch(void) { return "sm_100a"; }
+
+int nope_unet_create(nope_unet_t** out, int u_net_dim, int latent_ch, int latent_hw, int device) {
+  NOPE_CHECK(out != nullptr, "null out pointer");
+  NOPE_CHECK(u_net_dim > 0 && u_net_dim % 64 == 0, "u_net_dim must be a positive multiple of 64");
+  NOPE_CHECK(latent_ch >= 1 && latent_ch <= kMaxLatent, "latent_ch must be in [1, 8]");
+  NOPE_CHECK(latent_hw == 32, "latent_hw must be 32 (256x256 images) in this build");
+  int ndev = 0;
+  NOPE_CUDA(cudaGetDeviceCount(&ndev));
+  NOPE_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+  cudaDeviceProp prop;
+  NOPE_CUDA(cudaGetDeviceProperties(&prop, device));
+  NOPE_CHECK(prop.major == 10, "nope_b200 kernels are built for sm_100a only");
+  auto u = std::make_unique<nope_unet>();
+  u->dim = u_net_dim;
+  u->Cl = latent_ch;
+  u->S0 = latent_hw;
+  u->cemb = 4 * u_net_dim;
+  u->device = device;
+  u->num_sms = prop.multiProcessorCount;
+  const int mults[4] = {1, 2, 4, 8};
+  u->dims[0] = u_net_dim;
+  for (int i = 0; i < 4; ++i) u->dims[i + 1] = u_net_dim * mults[i];
+  u->build_schema();
+  *out = u.release();
+  return 0;
+}
+
+void nope_unet_destroy(nope_unet_t* u) { delete u; }
+
+int nope_unet_load_tensor(nope_unet_t* u, const char* key, const float* data, const int64_t* shape,
+                          int ndim) {
+  NOPE_CHECK(u && key && data && shape, "null argument");
+  NOPE_CHECK(!u->finalized, "engine already finalized");
+  auto it = u->expected.find(key);
+  NOPE_CHECK(it != u->expected.end(), std::string("unexpected state_dict key: ") + key);
+  NOPE_CHECK((int)it->second.size() == ndim, std::string("rank mismatch for ") + key);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    NOPE_CHECK(it->second[i] == shape[i], std::string("shape mismatch for ") + key);
+    n *= (size_t)shape[i];
+  }
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.assign(data, data + n);
+  u->host[key] = std::move(t);
+  return 0;
+}
+
+int nope_unet_finalize(nope_unet_t* u) {
+  NOPE_CHECK(u, "null engine");
+  return u->finalize();
+}
+
+int nope_unet_set_chunk(nope_unet_t* u, int hyps) {
+  NOPE_CHECK(u && hyps >= 1 && hyps <= 4096, "chunk must be in [1, 4096]");
+  u->chunk = hyps;
+  return 0;
+}
+int nope_unet_set_conv_impl(nope_unet_t* u, int impl) {
+  NOPE_CHECK(u && (impl == 0 || impl == 1), "impl must be 0 (tcgen05) or 1 (simt)");
+  u->conv_impl = impl;
+  return 0;
+}
+int64_t nope_unet_last_launch_count(const nope_unet_t* u) { return u ? u->launches : 0; }
+
+int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, int B, int N,
+                    const float* query_feat, float* out_emb, float* out_sim, int k, float* out_topv,
+                    int64_t* out_topi, int64_t idx_base, void* stream) {
+  NOPE_CHECK(u && u->finalized, "engine not finalized");
+  NOPE_CHECK(ref_feat && poses && B >= 1 && N >= 1, "bad arguments");
+  NOPE_CHECK(!(out_sim || k > 0) || query_feat, "scores / top-k need query_feat");
+  NOPE_CHECK(k >= 0 && k <= N && k <= 64, "k must be in [0, min(N, 64)]");
+  NOPE_CHECK(k == 0 || (out_topv && out_topi), "top-k outputs missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NOPE_CUDA(cudaSetDevice(u->device));
+  u->launches = 0;
+  const int total = B * N;
+  const int cap = std::min(u->chunk, total);
+  if (u->ensure_workspace(cap, B)) return -1;
+  const int hw = u->S0 * u->S0;
+  const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
+  float* part = nullptr;
+  if (query_feat) {
+    const size_t need = (size_t)total * nslab;
+    if (need > u->score_partial_cap) {
+      NOPE_CUDA(cudaStreamSynchronize(st));
+      if (u->score_partial) cudaFree(u->score_partial);
+      NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->score_partial), need * sizeof(float)));
+      u->score_partial_cap = need;
+    }
+    part = u->score_partial;
+  }
+  if (u->prestage(ref_feat, B, st)) return -1;
+  for (int h0 = 0; h0 < total; h0 += cap) {
+    const int n = std::min(cap, total - h0);
+    if (u->forward_chunk(poses, h0, n, N, query_feat, out_emb, part, st)) return -1;
+  }
+  if (query_feat && (out_sim || k > 0)) {
+    float* sim = out_sim;
+    if (!sim) {
+      if ((size_t)total > u->sim_buf_cap) {
+        NOPE_CUDA(cudaStreamSynchronize(st));
+        if (u->sim_buf) cudaFree(u->sim_buf);
+        NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->sim_buf), (size_t)total * sizeof(float)));
+        u->sim_buf_cap = total;
+      }
+      sim = u->sim_buf;
+    }
+    sim_topk_kernel<<<B, 256, 0, st>>>(part, nslab, sim, N, k, out_topv,
+                                       reinterpret_cast<long long*>(out_topi), (long long)idx_base);
+    NOPE_CUDA(cudaGetLastError());
+    ++u->launches;
+  }
+  return 0;
+}
+
+int nope_score_topk(const float* query_feat, const float* emb, int B, int N, int C, int HW, int metric,
+                    int k, float* out_sim, float* out_topv, int64_t* out_topi, int64_t idx_base,
+                    void* stream) {
+  NOPE_CHECK(query_feat && emb && out_sim, "null argument");
+  NOPE_CHECK(metric == NOPE_METRIC_L2 || metric == NOPE_METRIC_COSINE,
+             "unknown similarity metric (only l2 and cosine exist)");
+  NOPE_CHECK(k >= 0 && k <= N && k <= 64, "k must be in [0, min(N, 64)]");
+  NOPE_CHECK(k == 0 || (out_topv && out_topi), "top-k outputs missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  score_kernel<<<dim3(N, B), 256, 0, st>>>(query_feat, emb, out_sim, N, C, HW, metric);
+  NOPE_CUDA(cudaGetLastError());
+  if (k > 0) {
+    sim_topk_kernel<<<B, 256, 0, st>>>(nullptr, 0, out_sim, N, k, out_topv,
+                                       reinterpret_cast<long long*>(out_topi), (long long)idx_base);
+    NOPE_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_topi, int64_t idx_base,
+              void* stream) {
+  NOPE_CHECK(sim && out_topv && out_topi, "null argument");
+  NOPE_CHECK(k >= 1 && k <= N && k <= 64, "k must be in [1, min(N, 64)]");
+  sim_topk_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      nullptr, 0, sim, N, k, out_topv, reinterpret_cast<long long*>(out_topi), (long long)idx_base);
+  NOPE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// per-op entry points
+// ---------------------------------------------------------------------------------
+
+int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, int C1,
+                 const float* weight, const float* bias, float* out, int n_img, int H, int W,
+                 int Cout, void* stream) {
+  NOPE_CHECK(x0 && weight && out, "null argument");
+  NOPE_CHECK(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  NOPE_CHECK(H == W, "square images only");
+  NOPE_CHECK(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0, "channels must be multiples of 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Scratch s;
+  const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
+  const int cin = C0 + (x1 ? C1 : 0);
+  const int Hin = mode == 2 ? 2 * H : H;
+  __half *a0 = nullptr, *a1 = nullptr, *wp = nullptr, *o = nullptr;
+  if (to_nhwc(x0, &a0, s, n_img, C0, Hin * Hin, st)) return -1;
+  if (x1 && to_nhwc(x1, &a1, s, n_img, C1, Hin * Hin, st)) return -1;
+  if (s.get(&wp, (size_t)Cout * cin * taps) || s.get(&o, (size_t)n_img * H * W * Cout)) return -1;
+  pack_weight_kernel<<<ew_grid((long long)Cout * cin * taps), 256, 0, st>>>(weight, wp, Cout, cin, taps,
+                                                                            cin * taps, 0);
+  NOPE_CUDA(cudaGetLastError());
+  nope_unet eng;  // only used for its conv launcher / map cache
+  eng.conv_impl = impl;
+  cudaDeviceProp prop;
+  int dev = 0;
+  NOPE_CUDA(cudaGetDevice(&dev));
+  NOPE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  eng.num_sms = prop.multiProcessorCount;
+  ConvLayer L;
+  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = cin * taps; L.bn = pick_bn(Cout); L.w = wp;
+  float* dbias = nullptr;
+  if (bias) {
+    if (s.get(&dbias, Cout)) return -1;
+    NOPE_CUDA(cudaMemcpyAsync(dbias, bias, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  L.bias = dbias;
+  if (impl == 0 && make_weight_map(&L.wmap, wp, Cout, L.K, L.bn)) return -1;
+  if (eng.conv(L, a0, C0, a1, x1 ? C1 : 0, o, H, n_img, n_img, st)) return -1;
+  if (to_nchw(o, out, n_img, Cout, H * W, st)) return -1;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nope_op_groupnorm(const float* x, const float* gamma, const float* beta, int G, int silu,
+                      const float* chan_bias, const float* residual, float* out, int n_img, int C,
+                      int H, int W, void* stream) {
+  NOPE_CHECK(x && gamma && beta && out && H == W, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Scratch s;
+  const int hw = H * W;
+  __half *a = nullptr, *r = nullptr, *o = nullptr, *pbh = nullptr;
+  if (to_nhwc(x, &a, s, n_img, C, hw, st)) return -1;
+  if (residual && to_nhwc(residual, &r, s, n_img, C, hw, st)) return -1;
+  if (chan_bias && to_nhwc(chan_bias, &pbh, s, n_img, C, 1, st)) return -1;
+  if (s.get(&o, (size_t)n_img * C * hw)) return -1;
+  nope_unet eng;
+  if (s.get(&eng.gn_partial, (size_t)n_img * 64)) return -1;
+  NormLayer N;
+  N.C = C; N.G = G;
+  N.gamma = const_cast<float*>(gamma);
+  N.beta = const_cast<float*>(beta);
+  eng.pb = pbh;
+  eng.P = C;
+  if (eng.gn(&N, a, o, H, C, n_img, silu != 0, chan_bias ? 0 : -1, r, nullptr, st)) return -1;
+  if (to_nchw(o, out, n_img, C, hw, st)) return -1;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nope_op_linear_attention(const float* qkv, float* out, int n_img, int H, int W, void* stream) {
+  NOPE_CHECK(qkv && out, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Scratch s;
+  __half *a = nullptr, *o = nullptr;
+  if (to_nhwc(qkv, &a, s, n_img, 384, H * W, st) || s.get(&o, (size_t)n_img * 128 * H * W)) return -1;
+  linattn_kernel<<<dim3(4, n_img), kLinAttnThreads, 0, st>>>(a, o, H * W);
+  NOPE_CUDA(cudaGetLastError());
+  if (to_nchw(o, out, n_img, 128, H * W, st)) return -1;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nope_op_attention(const float* qkv, float* out, int n_img, int H, int W, void* stream) {
+  NOPE_CHECK(qkv && out && H * W <= 32, "bad argument (H*W must be <= 32)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Scratch s;
+  __half *a = nullptr, *o = nullptr;
+  if (to_nhwc(qkv, &a, s, n_img, 384, H * W, st) || s.get(&o, (size_t)n_img * 128 * H * W)) return -1;
+  midattn_kernel<<<n_img, 128, 0, st>>>(a, o, H * W);
+  NOPE_CUDA(cudaGetLastError());
+  if (to_nchw(o, out, n_img, 128, H * W, st)) return -1;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nope_op_upsample2x(const float* x, float* out, int n_img, int C, int H, int W, void* stream) {
+  NOPE_CHECK(x && out && C % 8 == 0 && H == W, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Scratch s;
+  __half *a = nullptr, *o = nullptr;
+  if (to_nhwc(x, &a, s, n_img, C, H * W, st) || s.get(&o, (size_t)n_img * C * H * W * 4)) return -1;
+  upsample2x_kernel<<<ew_grid((long long)n_img * 4 * H * W * C / 8), 256, 0, st>>>(a, o, n_img, H, W, C);
+  NOPE_CUDA(cudaGetLastError());
+  if (to_nchw(o, out, n_img, C, 4 * H * W, st)) return -1;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nope_unet_debug_tap(nope_unet_t* u, const float* ref_feat, const float* poses, int N, const char* tap,
+                        float* out, int64_t out_capacity_floats, int* out_C, int* out_H, void* stream) {
+  NOPE_CHECK(u && u->finalized && ref_feat && poses && tap && out, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NOPE_CHECK(N <= u->chunk, "debug tap: N must fit one chunk");
+  if (u->ensure_workspace(N, 1)) return -1;
+  u->tap_name = tap;
+  u->tap_out = out;
+  u->tap_cap = out_capacity_floats;
+  u->tap_hit = false;
+  int rc = u->prestage(ref_feat, 1, st);
+  if (!rc) rc = u->forward_chunk(poses, 0, N, N, nullptr, nullptr, nullptr, st);
+  u->tap_out = nullptr;
+  if (rc) return rc;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  NOPE_CHECK(u->tap_hit, std::string("unknown tap name: ") + tap);
+  if (out_C) *out_C = u->tap_C;
+  if (out_H) *out_H = u->tap_S;
+  return 0;
+}
+
+}  // extern "C"

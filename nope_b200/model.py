@@ -1,0 +1,176 @@
+"""Host-side mirror of the reference task module `PoseConditional`
+(src/model/model.py:32-565), inference surface only: forward (loss), sample,
+generate_templates, retrieval, plus predict_pose (= eval_geodesic lines 313-357 without
+logging).  Training, VSD evaluation, wandb/video logging are out of scope
+(SURVEY.md section 8).
+
+Differences that are deliberate and documented:
+  * generate_templates batches the whole pose grid through one engine sweep instead of a
+    Python loop that re-encodes the reference per pose (model.py:212-222, 115).
+  * retrieval raises ValueError for an unknown metric instead of returning None
+    (model.py:256 falls through); "cosine" is an extension.
+  * ranking is deterministic: descending score, ties -> lowest index.
+"""
+import ctypes as C
+import types
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+_METRICS = {"l2": 0, "cosine": 1}
+
+
+def _ns(d):
+    return d if not isinstance(d, dict) else types.SimpleNamespace(**d)
+
+
+class PoseConditional:
+    def __init__(self, u_net, optim_config=None, testing_config=None, save_dir=None, **kwargs):
+        self.u_net = u_net
+        self.save_dir = save_dir
+        self.optim_config = _ns(optim_config) if optim_config is not None else \
+            types.SimpleNamespace(loss_type="l1")
+        self.testing_config = _ns(testing_config) if testing_config is not None else \
+            types.SimpleNamespace(similarity_metric="l2")
+        loss_type = getattr(self.optim_config, "loss_type", "l1")
+        self.loss = F.l1_loss if loss_type == "l1" else F.mse_loss
+        self.dist = None     # optional nope_b200.dist.ShardedSweep for multi-GPU
+
+    @property
+    def device(self):
+        return self.u_net.device
+
+    def eval(self):
+        self.u_net.eval()
+        return self
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Accepts a Lightning checkpoint's `state_dict` (keys prefixed `u_net.`) or a bare
+        UNet state_dict."""
+        if any(k.startswith("u_net.") for k in state_dict):
+            state_dict = {k[len("u_net."):]: v for k, v in state_dict.items()
+                          if k.startswith("u_net.")}
+        self.u_net.load_state_dict(state_dict, strict=strict)
+        return self
+
+    # ------------------------------------------------------------------ model.py:96-111
+    def compute_loss(self, pred, gt):
+        loss = self.loss(pred, gt, reduction="none")
+        return loss.flatten(1).mean(dim=1).mean()
+
+    @torch.no_grad()
+    def forward(self, query, reference, relativeR):
+        query_feat = self.u_net.encoder.encode_image(query)
+        reference_feat = self.u_net.encoder.encode_image(reference, mode="mode")
+        pred = self.u_net(reference_feat, relativeR)
+        return self.compute_loss(pred, query_feat)
+
+    __call__ = forward
+
+    # ------------------------------------------------------------------ model.py:113-124
+    @torch.no_grad()
+    def sample(self, reference, relativeR):
+        reference_feat = self.u_net.encoder.encode_image(reference, mode="mode")
+        return self.u_net(reference_feat, relativeR), None   # template encoder: no decoder
+
+    # ------------------------------------------------------------------ model.py:193-252
+    @torch.no_grad()
+    def generate_templates(self, reference, all_relativeR, gt_templates=None, visualize=False):
+        reference_feat = self.u_net.encoder.encode_image(reference, mode="mode")
+        emb = self.u_net.sweep(reference_feat, all_relativeR, want_emb=True)["emb"]
+        return emb, None, None
+
+    # ------------------------------------------------------------------ model.py:254-266
+    @torch.no_grad()
+    def retrieval(self, query, template_feat, k=5):
+        metric = getattr(self.testing_config, "similarity_metric", "l2")
+        if metric not in _METRICS:
+            raise ValueError(f"unknown similarity_metric {metric!r} (supported: l2, cosine)")
+        query_feat = self.u_net.encoder.encode_image(query, mode="mode")
+        return score_topk(query_feat, template_feat, k=k, metric=metric)
+
+    # ------------------------------------------------------------------ model.py:313-357
+    @torch.no_grad()
+    def predict_pose(self, query, reference, all_relativeR, template_poses=None, k=5,
+                     return_templates=False):
+        """-> (R [B,k,3,3] | None, nearest_idx [B,k] int64, similarity [B,N]).  The scores and
+        the ranking come out of the sweep's fused last layer; the [B,N,C,32,32] templates are
+        only materialised when asked for."""
+        metric = getattr(self.testing_config, "similarity_metric", "l2")
+        if metric not in _METRICS:
+            raise ValueError(f"unknown similarity_metric {metric!r} (supported: l2, cosine)")
+        enc = self.u_net.encoder
+        B = query.shape[0]
+        feats = enc.encode_image(torch.cat([query.to(self.device), reference.to(self.device)]))
+        query_feat, reference_feat = feats[:B], feats[B:]
+        N = all_relativeR.shape[1]
+        k = min(k, N)
+        if self.dist is not None:
+            sim, topi, emb = self.dist.sweep(self.u_net, reference_feat, all_relativeR, query_feat,
+                                             k=k, metric=metric, want_emb=return_templates)
+        elif metric == "l2":
+            out = self.u_net.sweep(reference_feat, all_relativeR, query_feat=query_feat,
+                                   want_emb=return_templates, k=k)
+            sim, topi, emb = out["sim"], out["topi"], out["emb"]
+        else:
+            emb = self.u_net.sweep(reference_feat, all_relativeR, want_emb=True)["emb"]
+            sim, topi = score_topk(query_feat, emb, k=k, metric=metric)
+        R = None
+        if template_poses is not None:
+            tp = template_poses[0] if template_poses.dim() == 4 else template_poses
+            R = tp.to(topi.device)[topi]          # model.py:352-354
+        if return_templates:
+            return R, topi, sim, emb
+        return R, topi, sim
+
+
+def score_topk(query_feat, template_feat, k=5, metric="l2", idx_base=0):
+    """similarity [B,N] and nearest_idx [B,k] of materialised templates
+    (the arithmetic of model.py:260-265) on the GPU."""
+    if metric not in _METRICS:
+        raise ValueError(f"unknown similarity_metric {metric!r} (supported: l2, cosine)")
+    lib = _lib.load()
+    dev = template_feat.device
+    if dev.type != "cuda":
+        raise _lib.NopeError("score_topk needs CUDA tensors (no CPU fallback)")
+    q = query_feat.to(dev, torch.float32).contiguous()
+    t = template_feat.to(torch.float32).contiguous()
+    B, N, Cc = t.shape[0], t.shape[1], t.shape[2]
+    hw = t.shape[3] * t.shape[4]
+    if k > N:
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")  # torch.topk's error
+    sim = torch.empty((B, N), device=dev, dtype=torch.float32)
+    topv = torch.empty((B, k), device=dev, dtype=torch.float32)
+    topi = torch.empty((B, k), device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nope_score_topk(_lib.ptr(q), _lib.ptr(t), B, N, Cc, hw, _METRICS[metric], k,
+                                       _lib.ptr(sim), _lib.ptr(topv), _lib.ptr(topi), idx_base,
+                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return sim, topi
+
+
+def topk(sim, k, idx_base=0):
+    """Deterministic top-k of sim [B,N] on the GPU (descending, ties -> lowest index)."""
+    lib = _lib.load()
+    sim = sim.contiguous()
+    B, N = sim.shape
+    topv = torch.empty((B, k), device=sim.device, dtype=torch.float32)
+    topi = torch.empty((B, k), device=sim.device, dtype=torch.int64)
+    with torch.cuda.device(sim.device):
+        _lib.check(lib.nope_topk(_lib.ptr(sim), B, N, k, _lib.ptr(topv), _lib.ptr(topi), idx_base,
+                                 C.c_void_p(torch.cuda.current_stream(sim.device).cuda_stream)))
+    return topv, topi
+
+
+def build_model(u_net_dim=192, descriptor_size=8, device="cuda:0", chunk=256,
+                similarity_metric="l2"):
+    """The one configuration the reference resolves: configs/model/template_base.yaml."""
+    from .encoder import FeatureExtractor
+    from .unet import UNet
+    enc = FeatureExtractor(descriptor_size=descriptor_size, threshold=0.2, normalize=False)
+    unet = UNet(u_net_dim=u_net_dim, rot_representation_dim=6, encoder=enc,
+                pose_mlp_name="single_layer", device=device, chunk=chunk)
+    return PoseConditional(unet, optim_config={"loss_type": "l1"},
+                           testing_config={"similarity_metric": similarity_metric}, save_dir=None)

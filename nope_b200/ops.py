@@ -1,0 +1,81 @@
+"""Per-op entry points of the C ABI (include/nope_b200.h, "per-op entry points"), bound
+for the parity tests: each runs ONE layer type of the reference UNet on fp32 NCHW CUDA
+tensors through the same kernels the sweep uses."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_IMPL = {"tcgen05": 0, "simt": 1}
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _f32(t):
+    return None if t is None else t.to(torch.float32).contiguous()
+
+
+def conv(x0, weight, bias=None, x1=None, mode="3x3", impl="tcgen05"):
+    """mode '3x3' (pad 1), '1x1', or 'unshuffle' (pixel-unshuffle(2) + 1x1; weight
+    [Cout, 4*Cin, 1, 1]).  x1 is concatenated after x0 along channels."""
+    lib = _lib.load()
+    m = {"3x3": 0, "1x1": 1, "unshuffle": 2}[mode]
+    x0, x1, weight, bias = _f32(x0), _f32(x1), _f32(weight), _f32(bias)
+    n, c0, hin, win = x0.shape
+    h, w = (hin // 2, win // 2) if m == 2 else (hin, win)
+    cout = weight.shape[0]
+    out = torch.empty((n, cout, h, w), device=x0.device, dtype=torch.float32)
+    with torch.cuda.device(x0.device):
+        _lib.check(lib.nope_op_conv(_IMPL[impl], m, _lib.ptr(x0), c0, _lib.ptr(x1),
+                                    0 if x1 is None else x1.shape[1], _lib.ptr(weight),
+                                    _lib.ptr(bias), _lib.ptr(out), n, h, w, cout, _stream(x0.device)))
+    return out
+
+
+def groupnorm(x, gamma, beta, groups, silu=False, chan_bias=None, residual=None):
+    lib = _lib.load()
+    x, gamma, beta = _f32(x), _f32(gamma), _f32(beta)
+    chan_bias, residual = _f32(chan_bias), _f32(residual)
+    n, c, h, w = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nope_op_groupnorm(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), groups,
+                                         1 if silu else 0, _lib.ptr(chan_bias), _lib.ptr(residual),
+                                         _lib.ptr(out), n, c, h, w, _stream(x.device)))
+    return out
+
+
+def linear_attention(qkv):
+    lib = _lib.load()
+    qkv = _f32(qkv)
+    n, c, h, w = qkv.shape
+    assert c == 384
+    out = torch.empty((n, 128, h, w), device=qkv.device, dtype=torch.float32)
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.nope_op_linear_attention(_lib.ptr(qkv), _lib.ptr(out), n, h, w,
+                                                _stream(qkv.device)))
+    return out
+
+
+def attention(qkv):
+    lib = _lib.load()
+    qkv = _f32(qkv)
+    n, c, h, w = qkv.shape
+    assert c == 384
+    out = torch.empty((n, 128, h, w), device=qkv.device, dtype=torch.float32)
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.nope_op_attention(_lib.ptr(qkv), _lib.ptr(out), n, h, w, _stream(qkv.device)))
+    return out
+
+
+def upsample2x(x):
+    lib = _lib.load()
+    x = _f32(x)
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nope_op_upsample2x(_lib.ptr(x), _lib.ptr(out), n, c, h, w, _stream(x.device)))
+    return out

@@ -1,0 +1,165 @@
+"""Host-side mirror of the reference `UNet` (src/model/u_net/denoising_diffusion_pytorch/
+u_net.py:27-198) on top of the C ABI in include/nope_b200.h.
+
+Same constructor arguments and the attributes the task module reads (`.encoder`,
+`.channels`, `.name`, `__call__(x, pose)`); `load_state_dict` takes the reference's keys
+unchanged.  All arithmetic runs in libnope_b200.so; this file only moves pointers.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class UNet:
+    def __init__(self, u_net_dim, rot_representation_dim, encoder, pose_mlp_name="single_layer",
+                 init_dim=None, out_dim=None, use_hard_up_down=True, dim_mults=(1, 2, 4, 8),
+                 resnet_block_groups=8, device="cuda:0", chunk=256, **kwargs):
+        # only the configuration the reference actually ships resolves to a valid model
+        # (configs/model/template_base.yaml)
+        if pose_mlp_name != "single_layer":
+            raise ValueError("only pose_mlp_name='single_layer' is implemented")
+        if rot_representation_dim != 6 or tuple(dim_mults) != (1, 2, 4, 8) or \
+                resnet_block_groups != 8 or not use_hard_up_down or \
+                (init_dim not in (None, u_net_dim)) or \
+                (out_dim not in (None, encoder.latent_dim)):
+            raise ValueError("unsupported UNet configuration (template_base.yaml values only)")
+        self.encoder = encoder
+        self.channels = encoder.latent_dim
+        self.name = encoder.name
+        self.u_net_dim = u_net_dim
+        self.rot_representation_dim = rot_representation_dim
+        self.device = torch.device(device)
+        self._chunk = chunk
+        self._h = None
+        self._finalized = False
+
+    # ------------------------------------------------------------------ lifetime
+    def _handle(self):
+        if self._h is None:
+            lib = _lib.load()
+            if self.device.type != "cuda":
+                raise _lib.NopeError("nope_b200.UNet needs a CUDA device (no CPU fallback)")
+            h = C.c_void_p()
+            _lib.check(lib.nope_unet_create(C.byref(h), self.u_net_dim, self.channels, 32,
+                                            self.device.index or 0))
+            self._h = h
+            _lib.check(lib.nope_unet_set_chunk(h, self._chunk))
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.load().nope_unet_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def to(self, device):
+        if self._h is not None and torch.device(device) != self.device:
+            raise _lib.NopeError("cannot move a finalized engine; construct it on the target device")
+        self.device = torch.device(device)
+        self.encoder.to(self.device)
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", 0 if device is None else device))
+
+    def eval(self):
+        self.encoder.eval()
+        return self
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, strict=True):
+        """Accepts the reference UNet state_dict: 301 UNet tensors plus `encoder.*`
+        entries.  Shapes are checked by the engine."""
+        lib = _lib.load()
+        h = self._handle()
+        enc_sd = {}
+        for k, v in state_dict.items():
+            if k.startswith("encoder."):
+                kk = k[len("encoder."):]
+                if kk.startswith("backbone.") or kk.startswith("projector."):
+                    enc_sd[kk] = v
+                continue
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(lib.nope_unet_load_tensor(h, k.encode(), C.c_void_p(t.data_ptr()),
+                                                 shape, t.dim()))
+        if enc_sd:
+            self.encoder.load_state_dict(enc_sd, strict=strict)
+        _lib.check(lib.nope_unet_finalize(h))
+        self._finalized = True
+        self.encoder.to(self.device)
+        return self
+
+    def set_chunk(self, hyps):
+        self._chunk = hyps
+        if self._h is not None:
+            _lib.check(_lib.load().nope_unet_set_chunk(self._h, hyps))
+
+    def set_conv_impl(self, impl):
+        """'tcgen05' (default) or 'simt' (debug twin on CUDA cores)."""
+        _lib.check(_lib.load().nope_unet_set_conv_impl(self._handle(),
+                                                       {"tcgen05": 0, "simt": 1}[impl]))
+
+    @property
+    def last_launch_count(self):
+        return int(_lib.load().nope_unet_last_launch_count(self._handle()))
+
+    # ------------------------------------------------------------------ hot path
+    def sweep(self, ref_feat, poses, query_feat=None, want_emb=True, want_sim=None, k=0,
+              idx_base=0):
+        """ref_feat [B,C,32,32], poses [B,N,6] (+ query_feat [B,C,32,32]) ->
+        dict(emb [B,N,C,32,32] | None, sim [B,N] | None, topv/topi [B,k] | None)."""
+        if not self._finalized:
+            raise _lib.NopeError("load_state_dict() must be called before the sweep")
+        lib = _lib.load()
+        dev = self.device
+        ref_feat = ref_feat.to(dev, torch.float32).contiguous()
+        poses = poses.to(dev, torch.float32).contiguous()
+        B, N = poses.shape[0], poses.shape[1]
+        assert ref_feat.shape == (B, self.channels, 32, 32), ref_feat.shape
+        assert poses.shape[2] == self.rot_representation_dim
+        if want_sim is None:
+            want_sim = query_feat is not None
+        if query_feat is not None:
+            query_feat = query_feat.to(dev, torch.float32).contiguous()
+            assert query_feat.shape == ref_feat.shape
+        emb = torch.empty((B, N, self.channels, 32, 32), device=dev, dtype=torch.float32) \
+            if want_emb else None
+        sim = torch.empty((B, N), device=dev, dtype=torch.float32) if want_sim else None
+        topv = torch.empty((B, k), device=dev, dtype=torch.float32) if k > 0 else None
+        topi = torch.empty((B, k), device=dev, dtype=torch.int64) if k > 0 else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nope_unet_sweep(self._handle(), _lib.ptr(ref_feat), _lib.ptr(poses), B, N,
+                                           _lib.ptr(query_feat), _lib.ptr(emb), _lib.ptr(sim), k,
+                                           _lib.ptr(topv), _lib.ptr(topi), idx_base,
+                                           C.c_void_p(stream)))
+        return {"emb": emb, "sim": sim, "topv": topv, "topi": topi}
+
+    def __call__(self, x, pose):
+        """UNet.forward(x [B,C,32,32], pose [B,6]) -> [B,C,32,32] (u_net.py:160-198)."""
+        out = self.sweep(x, pose[:, None, :], want_emb=True)["emb"]
+        return out[:, 0]
+
+    forward = __call__
+
+    def debug_tap(self, ref_feat, poses, tap):
+        """Activation named `tap` (oracle tap names) for poses [N,6] of ONE reference."""
+        lib = _lib.load()
+        dev = self.device
+        ref_feat = ref_feat.to(dev, torch.float32).contiguous()
+        poses = poses.to(dev, torch.float32).contiguous()
+        N = poses.shape[0]
+        cap = N * 32 * 32 * 8 * self.u_net_dim
+        out = torch.empty(cap, device=dev, dtype=torch.float32)
+        c, s = C.c_int(), C.c_int()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nope_unet_debug_tap(self._handle(), _lib.ptr(ref_feat), _lib.ptr(poses), N,
+                                               tap.encode(), _lib.ptr(out), cap, C.byref(c),
+                                               C.byref(s), C.c_void_p(stream)))
+        return out[: N * c.value * s.value * s.value].view(N, c.value, s.value, s.value)
