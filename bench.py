@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- pose-hypotheses/s of the NOPE hot path on B200.
+
+A "step" = one pass of the hot path for one query: the pose-conditioned UNet over the
+whole pose grid + l2 scoring + top-5 (BASELINE.json configs[1]: 256x256, 642-pose
+icosphere grid, batch = 1 query, fp16 UNet).  With N GPUs the grid is sharded
+(weak scaling: 642 poses per GPU, global grid = 642 N) and the only collective is the
+all-gather of per-shard (score, index) top-k.
+
+  value  hypotheses/s with the encoder latents and poses already resident in HBM
+  e2e    the same metric through the public API (PoseConditional.predict_pose): pinned HOST
+         images + poses -> H2D -> encoder x2 -> sweep -> fused score/top-k -> D2H result
+  roofline  tensor-core convolution kernel: algorithmic FLOPs / CUDA-event launch time
+  cpu_baseline  the oracle (CPU port of the reference) on the host cores, bounded sample
+
+`--impl reference` times the reference's own CPU implementation of the path (the real
+reference modules when /root/reference is mounted, else the oracle port of them).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_POSES = 642
+GFLOP_PER_HYP = 35.05       # SURVEY.md 8d / BASELINE.md section 3
+METRIC = "pose-hypotheses/sec @256x256 (UNet sweep + l2 score + top-5)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--poses", type=int, default=N_POSES, help="poses per GPU")
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("NOPE_CHUNK", "256")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured"
+    return 1400.0, 6650.0, "fallback"     # B200_PROFILING.md fallback (sustained)
+
+
+# ---------------------------------------------------------------------------------------
+def cpu_baseline(seconds=12.0, chunk=16):
+    """Oracle (CPU port of the reference path) on all host cores: UNet sweep in chunks of
+    16 hypotheses + scoring, until ~`seconds` of work.  hyp/s."""
+    import torch
+    from oracle import inputs, unet_oracle as orc, weights
+    torch.set_num_threads(os.cpu_count())
+    sd = weights.make_unet_state_dict(seed=0)
+    g = torch.Generator().manual_seed(0)
+    rf = torch.randn(1, 8, 32, 32, generator=g) * 1.5
+    qf = torch.randn(1, 8, 32, 32, generator=g) * 1.5
+    from nope_b200.poses import synthetic_pose_batch
+    poses, _ = synthetic_pose_batch(N_POSES, 1)
+    done, t0 = 0, time.time()
+    with torch.no_grad():
+        orc.generate_templates(sd, rf, poses[:, :2], chunk=2)          # warm-up
+        t0 = time.time()
+        while time.time() - t0 < seconds and done + chunk <= N_POSES:
+            emb = orc.generate_templates(sd, rf, poses[:, done:done + chunk], chunk=chunk)
+            orc.l2_similarity(qf, emb)
+            done += chunk
+    dt = time.time() - t0
+    return {"value": done / dt, "unit": "hyp/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"first {done} of the {N_POSES}-pose grid, batched {chunk}/forward, "
+                      f"fp32 torch-CPU oracle, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path, bounded sample per step."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    sample = 16
+    from oracle import ref_import, unet_oracle as orc, weights
+    from nope_b200.poses import synthetic_pose_batch
+    poses, _ = synthetic_pose_batch(N_POSES, 1)
+    g = torch.Generator().manual_seed(0)
+    q = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    r = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    sd = weights.make_full_state_dict(seed=0)
+    if ref_import.reference_available():
+        kind = "reference"
+        model = ref_import.build_reference_model()
+        model.u_net.load_state_dict(sd, strict=True)
+
+        def step():
+            # the reference's retrieval path with the grid batched along dim 0 (its own
+            # modules, best-effort CPU: one encoder call per image, UNet at batch `sample`)
+            with torch.no_grad():
+                qf = model.u_net.encoder.encode_image(q)
+                rf = model.u_net.encoder.encode_image(r)
+                emb = model.u_net(rf.expand(sample, -1, -1, -1), poses[0, :sample])[None]
+                d = (qf.unsqueeze(1) - emb) ** 2
+                sim = -torch.norm(d, dim=2).sum(3).sum(2)
+                sim.topk(k=5, dim=1)
+    else:
+        kind = "port"
+        unet_sd = {k: v for k, v in sd.items() if not k.startswith("encoder.")}
+        enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+
+        def step():
+            with torch.no_grad():
+                qf = orc.encode_image(enc_sd, q)
+                rf = orc.encode_image(enc_sd, r)
+                emb = orc.generate_templates(unet_sd, rf, poses[:, :sample], chunk=sample)
+                orc.topk_lowest_index(orc.l2_similarity(qf, emb), 5)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = (time.time() - t0) / args.steps
+    v = sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "hyp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"256x256, {N_POSES}-pose icosphere grid, batch=1 query; each step a "
+                               f"{sample}-pose sample of the grid (+2 encoder calls) on host CPU",
+                   "poses_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": "hyp/s", "cores": os.cpu_count(), "kind": kind,
+                         "sample": f"{sample} poses + 2 encoder calls per step"},
+        "e2e": {"value": v, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    from oracle import weights                      # seeded synthetic weights (random init)
+    from nope_b200.model import build_model
+    from nope_b200.dist import ShardedSweep
+    from nope_b200.poses import synthetic_pose_batch
+
+    n_local = args.poses
+    n_global = n_local * world
+    model = build_model(device=str(dev), chunk=args.chunk)
+    model.load_state_dict(weights.make_full_state_dict(seed=0)).eval()
+    unet = model.u_net
+    if world > 1:
+        model.dist = ShardedSweep()
+
+    # global grid: one icosphere-642 grid per GPU shard (pose VALUES do not affect timing)
+    poses_g, tposes = synthetic_pose_batch(n_local, 1)
+    poses_g = poses_g.repeat(1, world, 1)           # [1, n_global, 6]
+    g = torch.Generator().manual_seed(0)
+    q_img = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    r_img = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    poses_host = poses_g.clone().pin_memory()
+    h2d = q_img.numel() * 4 + r_img.numel() * 4 + poses_host.numel() * 4
+    d2h = 5 * 8 + n_global * 4                      # top-5 indices (int64) + similarity row
+
+    # ---- resident inputs for `value`
+    q_feat = unet.encoder.encode_image(q_img.to(dev))
+    r_feat = unet.encoder.encode_image(r_img.to(dev))
+    poses_dev = poses_g.to(dev)
+
+    def step_resident():
+        if world > 1:
+            return model.dist.sweep(unet, r_feat, poses_dev, q_feat, k=5, want_emb=False)
+        out = unet.sweep(r_feat, poses_dev, query_feat=q_feat, want_emb=False, k=5)
+        return out["sim"], out["topi"], None
+
+    def step_e2e():
+        q = q_img.to(dev, non_blocking=True)
+        r = r_img.to(dev, non_blocking=True)
+        p = poses_host.to(dev, non_blocking=True)
+        _, idx, sim = model.predict_pose(q, r, p, None, k=5)
+        return idx.cpu(), sim.cpu()                 # D2H of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches_per_step = unet.last_launch_count
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    # ---- roofline of the dominant kernel (tcgen05 convolution), CUDA events per launch
+    unet.profile(True)
+    step_resident()
+    prof = unet.profile_read()
+    unet.profile(False)
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    conv_tf = prof["conv_flops"] / (prof["conv_ms"] * 1e-3) / 1e12 if prof["conv_ms"] > 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()
+    value = n_global / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": {
+            "workload": f"configs[1]: 256x256, {n_local}-pose icosphere grid per GPU, batch=1 query, "
+                        "fp16 UNet (fp32 accumulate / statistics), l2 score + top-5",
+            "poses_per_gpu": n_local, "global_poses": n_global, "queries": 1, "chunk": args.chunk,
+            "weights": "seeded random init, reference state_dict schema (305.8 M params)",
+            "l2": "not flushed: each step streams 0.61 GB of fp16 weights and ~1.4 GB of "
+                  "activations per chunk, >> 126 MB L2",
+            "parallelism": f"pose grid sharded {world}-way, all-gather of top-k" if world > 1 else "1 GPU",
+        },
+        "clocks": clocks,
+        "e2e": {"value": n_global / (ms_e2e * 1e-3), "unit": "hyp/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "PoseConditional.predict_pose (pinned host images -> encoder x2 -> sweep -> top-5 -> host)"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": {
+            "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)",
+            "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": conv_tf / peak_tf if peak_tf else None, "peak_source": f"{peak_src} (sustained bf16 cuBLAS)",
+            "traffic": None, "launches_per_step": prof["conv_launches"],
+            "conv_ms_per_step": prof["conv_ms"], "conv_share_of_step": prof["conv_ms"] / ms if ms else None,
+            "algorithmic_tflop_per_step": prof["conv_flops"] / 1e12,
+            "best_single_launch_tflops": prof["max_launch_tflops"],
+            "whole_step_tflops": value * GFLOP_PER_HYP / 1e3,
+        },
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,15 @@ int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, i
 /* Number of kernels the last nope_unet_sweep call enqueued (for bench.py's gpu_launches). */
 int64_t nope_unet_last_launch_count(const nope_unet_t* u);
 
+/* Profiling hook for bench.py's roofline: when enabled, every tensor-core convolution
+ * launch of subsequent sweeps is bracketed by CUDA events on the launching stream.
+ * nope_unet_profile_read synchronises the device and returns the summed launch time
+ * (ms), the summed algorithmic FLOPs (2*M*N*K per launch), the launch count and the best
+ * single-launch TFLOP/s.  Enabling/disabling clears the recorded events. */
+int nope_unet_profile(nope_unet_t* u, int enable);
+int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops,
+                           int64_t* conv_launches, double* max_launch_tflops);
+
 /* Score materialised templates against a query and rank them: the arithmetic of
  * PoseConditional.retrieval (model.py:254-266) after encode_image.
  *   query_feat [B, C, HW] fp32, emb [B, N, C, HW] fp32 -> sim [B, N], topv/topi [B, k]. */

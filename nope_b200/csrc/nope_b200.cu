@@ -95,6 +95,11 @@ struct nope_unet {
 
   std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;
 
+  // per-launch CUDA-event profile of the convolution kernel (bench.py roofline)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;      // pairs
+  std::vector<double> prof_flops;
+
   // debug tap
   std::string tap_name;
   float* tap_out = nullptr;
@@ -107,6 +112,7 @@ struct nope_unet {
     for (void* p : ws_owned) cudaFree(p);
     if (score_partial) cudaFree(score_partial);
     if (sim_buf) cudaFree(sim_buf);
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   }
 
   // ------------------------------------------------------------------ schema
@@ -447,7 +453,17 @@ struct nope_unet {
     p.h_cnt = g.h_cnt;
     p.b_cnt = g.b_cnt;
     NOPE_CHECK(ksteps * 64 == L.K, "conv: K mismatch");
-    return launch_conv_tc(p, L.bn, num_sms, st);
+    if (!profile) return launch_conv_tc(p, L.bn, num_sms, st);
+    cudaEvent_t e0, e1;
+    NOPE_CUDA(cudaEventCreate(&e0));
+    NOPE_CUDA(cudaEventCreate(&e1));
+    NOPE_CUDA(cudaEventRecord(e0, st));
+    const int rc = launch_conv_tc(p, L.bn, num_sms, st);
+    NOPE_CUDA(cudaEventRecord(e1, st));
+    prof_ev.push_back(e0);
+    prof_ev.push_back(e1);
+    prof_flops.push_back(2.0 * (double)n_img * So * So * (double)L.cout * (double)L.K);
+    return rc;
   }
 
   static int gn_nslab(int hw) { return hw >= 1024 ? 8 : (hw >= 256 ? 2 : 1); }
@@ -757,6 +773,34 @@ int nope_unet_set_conv_impl(nope_unet_t* u, int impl) {
   return 0;
 }
 int64_t nope_unet_last_launch_count(const nope_unet_t* u) { return u ? u->launches : 0; }
+
+int nope_unet_profile(nope_unet_t* u, int enable) {
+  NOPE_CHECK(u, "null engine");
+  for (cudaEvent_t e : u->prof_ev) cudaEventDestroy(e);
+  u->prof_ev.clear();
+  u->prof_flops.clear();
+  u->profile = enable != 0;
+  return 0;
+}
+
+int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops, int64_t* conv_launches,
+                           double* max_launch_tflops) {
+  NOPE_CHECK(u && conv_ms && conv_flops && conv_launches, "null argument");
+  NOPE_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0, fl = 0.0, best = 0.0;
+  for (size_t i = 0; i < u->prof_flops.size(); ++i) {
+    float t = 0.f;
+    NOPE_CUDA(cudaEventElapsedTime(&t, u->prof_ev[2 * i], u->prof_ev[2 * i + 1]));
+    ms += t;
+    fl += u->prof_flops[i];
+    if (t > 0.f) best = std::max(best, u->prof_flops[i] / (t * 1e-3) / 1e12);
+  }
+  *conv_ms = ms;
+  *conv_flops = fl;
+  *conv_launches = (int64_t)u->prof_flops.size();
+  if (max_launch_tflops) *max_launch_tflops = best;
+  return 0;
+}
 
 int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, int B, int N,
                     const float* query_feat, float* out_emb, float* out_sim, int k, float* out_topv,

@@ -108,6 +108,17 @@ class UNet:
     def last_launch_count(self):
         return int(_lib.load().nope_unet_last_launch_count(self._handle()))
 
+    def profile(self, enable):
+        _lib.check(_lib.load().nope_unet_profile(self._handle(), 1 if enable else 0))
+
+    def profile_read(self):
+        """-> dict(conv_ms, conv_flops, conv_launches, max_launch_tflops) since profile(True)."""
+        ms, fl, n, best = C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+        _lib.check(_lib.load().nope_unet_profile_read(self._handle(), C.byref(ms), C.byref(fl),
+                                                      C.byref(n), C.byref(best)))
+        return {"conv_ms": ms.value, "conv_flops": fl.value, "conv_launches": n.value,
+                "max_launch_tflops": best.value}
+
     # ------------------------------------------------------------------ hot path
     def sweep(self, ref_feat, poses, query_feat=None, want_emb=True, want_sim=None, k=0,
               idx_base=0):

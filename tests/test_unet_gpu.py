@@ -1,0 +1,132 @@
+"""GPU: the whole hot path through the public Python surface (which calls the C ABI)
+against (a) the golden fixtures generated from the unmodified reference and (b) the
+oracle run live on the host CPU.
+
+Tolerances (fp16 storage, fp32 accumulation/statistics; SURVEY.md section 7 measured
+1.1e-3 / 1.7e-4 for fp16 autocast of the reference itself):
+  embeddings  rel-L2 <= EMB_TOL, similarity rel <= SIM_TOL, top-1 index identical,
+  top-5 set identical where the reference's own adjacent score gaps exceed 2*SIM_TOL."""
+import numpy as np
+import pytest
+import torch
+
+from _util import log, max_rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+EMB_TOL = 3e-3
+SIM_TOL = 1e-3
+
+
+def _cmp_ranking(sim_ref, idx_ref, idx, tol):
+    """top-1 must match; later ranks must match unless the reference scores of the two
+    candidates are closer than tol (relative)."""
+    sim_ref = torch.as_tensor(sim_ref)
+    idx_ref = torch.as_tensor(idx_ref)
+    assert torch.equal(idx[:, 0].cpu(), idx_ref[:, 0]), (idx, idx_ref)
+    for b in range(idx_ref.shape[0]):
+        for r in range(idx_ref.shape[1]):
+            i, j = int(idx[b, r]), int(idx_ref[b, r])
+            if i != j:
+                gap = abs(float(sim_ref[b, i] - sim_ref[b, j])) / abs(float(sim_ref[b, j]))
+                assert gap < 2 * tol, (b, r, i, j, gap)
+
+
+def test_cfg1_golden(gpu_model, golden_dir):
+    g = np.load(f"{golden_dir}/cfg1_b1_n6.npz")
+    rf = torch.from_numpy(g["ref_feat"])
+    qf = torch.from_numpy(g["query_feat"])
+    poses = torch.from_numpy(g["all_relativeR"])
+    out = gpu_model.u_net.sweep(rf, poses, query_feat=qf, want_emb=True, k=5)
+    e_emb = rel_l2(out["emb"], torch.from_numpy(g["emb"]))
+    e_sim = max_rel(out["sim"], torch.from_numpy(g["similarity"]))
+    log("cfg1_golden", emb_rel_l2=e_emb, sim_max_rel=e_sim, topi=out["topi"].tolist(),
+        ref_topi=g["nearest_idx"].tolist(), launches=gpu_model.u_net.last_launch_count)
+    assert e_emb < EMB_TOL and e_sim < SIM_TOL
+    _cmp_ranking(g["similarity"], g["nearest_idx"], out["topi"], SIM_TOL)
+
+
+def test_cfg1_end_to_end_from_images(gpu_model, golden_dir):
+    """images -> encoder (torch/cuDNN fp32) -> sweep -> fused score/top-k, via predict_pose"""
+    from oracle import inputs
+    g = np.load(f"{golden_dir}/cfg1_b1_n6.npz")
+    q, r = inputs.make_images(seed=0, batch=1)
+    poses = torch.from_numpy(g["all_relativeR"])
+    tposes = torch.from_numpy(g["template_poses"])
+    R, idx, sim, emb = gpu_model.predict_pose(q, r, poses, tposes, k=5, return_templates=True)
+    e_q = rel_l2(gpu_model.u_net.encoder.encode_image(q), torch.from_numpy(g["query_feat"]))
+    e_emb = rel_l2(emb, torch.from_numpy(g["emb"]))
+    e_sim = max_rel(sim, torch.from_numpy(g["similarity"]))
+    log("cfg1_e2e", enc_rel_l2=e_q, emb_rel_l2=e_emb, sim_max_rel=e_sim)
+    assert e_q < 1e-4 and e_emb < EMB_TOL and e_sim < SIM_TOL
+    assert R.shape == (1, 5, 3, 3)
+    assert torch.equal(R[0, 0].cpu(), tposes[int(g["nearest_idx"][0, 0])])
+    # the reference's own surface: generate_templates + retrieval
+    emb2, _, _ = gpu_model.generate_templates(r, poses, None)
+    sim2, idx2 = gpu_model.retrieval(q, emb2)
+    assert torch.equal(idx2, idx) and rel_l2(sim2, sim) < 1e-6
+    assert torch.equal(emb2, emb)                      # deterministic kernels, same inputs
+
+
+def test_grid26_b2_golden(gpu_model, golden_dir):
+    g = np.load(f"{golden_dir}/grid26_b2.npz")
+    rf, qf = torch.from_numpy(g["ref_feat"]), torch.from_numpy(g["query_feat"])
+    poses = torch.from_numpy(g["all_relativeR"])
+    out = gpu_model.u_net.sweep(rf, poses, query_feat=qf, want_emb=True, k=5)
+    emb = out["emb"].cpu()
+    e0 = rel_l2(emb[0, 0], torch.from_numpy(g["emb_b0_n0"]))
+    e1 = rel_l2(emb[1, 25], torch.from_numpy(g["emb_b1_n25"]))
+    e_l2 = max_rel(emb.flatten(2).norm(dim=2), torch.from_numpy(g["emb_l2"]))
+    e_sim = max_rel(out["sim"], torch.from_numpy(g["similarity"]))
+    log("grid26_golden", emb00=e0, emb125=e1, emb_l2=e_l2, sim_max_rel=e_sim,
+        topi=out["topi"].tolist(), ref=g["nearest_idx"].tolist())
+    assert max(e0, e1) < EMB_TOL and e_sim < SIM_TOL
+    _cmp_ranking(g["similarity"], g["nearest_idx"], out["topi"], SIM_TOL)
+    # chunking must not change anything: 7 hypotheses per chunk vs one chunk
+    gpu_model.u_net.set_chunk(7)
+    out2 = gpu_model.u_net.sweep(rf, poses, query_feat=qf, want_emb=True, k=5)
+    gpu_model.u_net.set_chunk(256)
+    assert torch.equal(out2["emb"], out["emb"]) and torch.equal(out2["topi"], out["topi"])
+    assert torch.equal(out2["sim"], out["sim"])
+
+
+def test_layer_taps_vs_live_oracle(gpu_model, seeded_state_dict, golden_dir):
+    """per-layer activations of one sweep against the oracle (CPU, run here)."""
+    from oracle import unet_oracle as orc
+    g = np.load(f"{golden_dir}/cfg1_b1_n6.npz")
+    unet_sd = {k: v for k, v in seeded_state_dict.items() if not k.startswith("encoder.")}
+    rf = torch.from_numpy(g["ref_feat"])
+    poses = torch.from_numpy(g["all_relativeR"])[0, :3]
+    taps = {}
+    with torch.no_grad():
+        orc.unet_forward(unet_sd, rf.expand(3, -1, -1, -1), poses, taps=taps)
+    worst = 0.0
+    for name in ["init_conv", "downs.0.0", "downs.0.1", "downs.0.2", "downs.0.3", "downs.1.2",
+                 "downs.2.3", "downs.3.3", "mid.0", "mid.1", "ups.0.0", "ups.0.3", "ups.1.3",
+                 "ups.2.3", "ups.3.3", "final_res_block", "final_conv.0"]:
+        got = gpu_model.u_net.debug_tap(rf, poses, name)
+        e = rel_l2(got, taps[name])
+        worst = max(worst, e)
+        log("tap", name=name, rel_l2=e)
+    assert worst < EMB_TOL
+
+
+def test_forward_call_and_loss(gpu_model, golden_dir):
+    """UNet.__call__(x, pose) and PoseConditional.forward (loss) keep the reference surface."""
+    from oracle import inputs
+    g = np.load(f"{golden_dir}/cfg1_b1_n6.npz")
+    rf = torch.from_numpy(g["ref_feat"])
+    y = gpu_model.u_net(rf, torch.from_numpy(g["all_relativeR"][:, 2]))
+    assert y.shape == (1, 8, 32, 32)
+    assert rel_l2(y, torch.from_numpy(g["emb"][:, 2])) < EMB_TOL
+    q, r = inputs.make_images(seed=0, batch=1)
+    loss = gpu_model.forward(q, r, torch.from_numpy(g["all_relativeR"][:, 2]))
+    ref_loss = (torch.from_numpy(g["emb"][:, 2]) - torch.from_numpy(g["query_feat"])).abs().mean()
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * float(ref_loss)
+
+
+def test_bad_arguments_raise(gpu_model):
+    from nope_b200 import NopeError
+    rf = torch.zeros(1, 8, 32, 32)
+    with pytest.raises(NopeError):
+        gpu_model.u_net.sweep(rf, torch.zeros(1, 3, 6), query_feat=rf, k=5)   # k > N
