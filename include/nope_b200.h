@@ -108,11 +108,18 @@ int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_top
  * happens inside.  These calls synchronise the stream before returning.
  * conv: mode 0 = 3x3 pad 1 (model_utils.py:240), 1 = 1x1 (model_utils.py:269),
  *       2 = pixel-unshuffle(2)+1x1 (HardDownsample, model_utils.py:168-172; input is
- *       [n, C0, 2H, 2W], weight [Cout, 4*C0]).  x1 (optional) is concatenated after x0
- *       along channels (u_net.py:186).  impl as in nope_unet_set_conv_impl. */
+ *       [n, C0, 2H, 2W], weight [Cout, 4*C0]), 3 = nearest-x2 upsample + 3x3 (HardUpsample,
+ *       model_utils.py:161-165; input is [n, C0, H/2, W/2], weight [Cout, C0, 3, 3], folded
+ *       inside into four 2x2 parity kernels).  x1 (optional) is concatenated after x0 along
+ *       channels (u_net.py:186).  impl as in nope_unet_set_conv_impl. */
 int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, int C1,
                  const float* weight, const float* bias, float* out, int n_img, int H, int W,
                  int Cout, void* stream);
+/* Block.forward (model_utils.py:248-252): [SiLU](GroupNorm_G(conv(x) + bias)) with the
+ * GroupNorm statistics taken from the convolution epilogue -- the fused path the sweep uses. */
+int nope_op_conv_gn(int impl, int mode, const float* x0, int C0, const float* x1, int C1,
+                    const float* weight, const float* bias, const float* gamma, const float* beta,
+                    int G, int silu, float* out, int n_img, int H, int W, int Cout, void* stream);
 /* y = [SiLU](GroupNorm_G(x)) + chan_bias[n, c] + residual   (model_utils.py:237-253,271-279) */
 int nope_op_groupnorm(const float* x, const float* gamma, const float* beta, int G, int silu,
                       const float* chan_bias, const float* residual, float* out, int n_img,

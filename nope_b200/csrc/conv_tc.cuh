@@ -43,8 +43,21 @@ struct ConvSeg {
 struct ConvParams {
   CUtensorMap amap[4];
   CUtensorMap bmap;
-  CUtensorMap omap;
+  CUtensorMap omap[4];  // one per output parity class when n_par == 4, else omap[0]
   const float* bias;  // [n_total] or nullptr
+  // Sub-pixel ("parity") decomposition of nearest-x2-upsample + conv3x3 (HardUpsample,
+  // model_utils.py:161-165): n_par == 4 makes n_tile enumerate (parity, channel tile); parity
+  // (py, px) shifts every tap by (+py, +px), reads weight rows parity * n_per_par + ..., and
+  // stores through omap[parity] (the stride-2 sub-lattice of the 2H x 2W output).
+  int n_par;          // 1 or 4
+  int n_tiles_par;    // channel tiles per parity (== n_tiles when n_par == 1)
+  // optional GroupNorm partial statistics of the fp32 outputs (bias included), written
+  // deterministically as stats[(img * parts + part) * n_oct + octet] = (sum, sum of squares)
+  // over 32-pixel row segments x 8-channel octets; parts = max(1, H*W/32).
+  float2* stats;
+  int stats_hw;       // H*W of one output image
+  int stats_noct;     // n_total / 8
+  int m_valid;        // n_img * H * W (rows beyond it are padding)
   int nseg;
   int ksteps;         // sum of nchunks
   int m_tiles, n_tiles;
@@ -98,7 +111,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&p.amap[i]);
     prefetch_tmap(&p.bmap);
-    prefetch_tmap(&p.omap);
+    for (int i = 0; i < p.n_par; ++i) prefetch_tmap(&p.omap[i]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -124,6 +137,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
+      const int par = n_tile / p.n_tiles_par;          // 0 unless n_par == 4
+      const int py = par >> 1, px = par & 1;
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
       int kcol = 0;
@@ -134,7 +149,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_4d(sa, am, &full_bar[stage], ch * kBK, sg.dx, y0 + sg.dy, b0);
+          tma_load_4d(sa, am, &full_bar[stage], ch * kBK, sg.dx + px, y0 + sg.dy + py, b0);
           tma_load_2d(sa + S::kABytes, &p.bmap, &full_bar[stage], kcol, n_tile * BN);
           kcol += kBK;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -180,6 +195,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
+      const int par = n_tile / p.n_tiles_par;
+      const int n_chan0 = (n_tile - par * p.n_tiles_par) * BN;   // first output channel of the tile
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
       // staging buffer must have been fully read by the previous TMA store
@@ -196,21 +213,52 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         tmem_ld_32x32(t_row + cc * 64, v0);
         tmem_ld_32x32(t_row + cc * 64 + 32, v1);
         tmem_ld_wait();
-        const float* bptr = p.bias ? p.bias + n_tile * BN + cc * 64 : nullptr;
+        const float* bptr = p.bias ? p.bias + n_chan0 + cc * 64 : nullptr;
         uint8_t* srow = out_stage + cc * (kBM * 128) + row * 128;
+        float st_s[8], st_q[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {   // 8 x 16-byte chunks of 8 channels
           uint32_t w[4];
+          float s = 0.f, q2 = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int c = j * 8 + q * 2;
             float a = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
             float b = __uint_as_float(c + 1 < 32 ? v0[c + 1] : v1[c + 1 - 32]);
             if (bptr) { a += __ldg(bptr + c); b += __ldg(bptr + c + 1); }
+            s += a + b;
+            q2 = fmaf(a, a, q2);
+            q2 = fmaf(b, b, q2);
             w[q] = pack_half2(a, b);
           }
+          st_s[j] = s;
+          st_q[j] = q2;
           const int phys = j ^ (row & 7);   // SWIZZLE_128B: 16-B chunk index XOR (row mod 8)
           *reinterpret_cast<uint4*>(srow + phys * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (p.stats) {
+          // fixed-order butterfly over the rows of one image segment (<= 32 rows)
+          const int seg = p.stats_hw < 32 ? p.stats_hw : 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float s = st_s[j], q2 = st_q[j];
+            for (int off = seg >> 1; off > 0; off >>= 1) {
+              s += __shfl_xor_sync(0xffffffffu, s, off);
+              q2 += __shfl_xor_sync(0xffffffffu, q2, off);
+            }
+            st_s[j] = s;
+            st_q[j] = q2;
+          }
+          const int gp = m_tile * kBM + row;
+          if ((lane & (seg - 1)) == 0 && gp < p.m_valid) {
+            const int img = gp / p.stats_hw;
+            const int parts = p.stats_hw < 32 ? 1 : p.stats_hw >> 5;
+            const int part = (gp - img * p.stats_hw) >> 5;
+            float2* dst = p.stats + ((size_t)img * parts + part) * p.stats_noct +
+                          (n_chan0 + cc * 64) / 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float2(st_s[j], st_q[j]);
+          }
         }
       }
       // accumulator fully read: hand it back to the MMA warp
@@ -223,7 +271,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
       if (ew == 0 && lane == 0) {
 #pragma unroll 1
         for (int cc = 0; cc < BN / 64; ++cc)
-          tma_store_4d(&p.omap, out_stage + cc * (kBM * 128), n_tile * BN + cc * 64, 0, y0, b0);
+          tma_store_4d(&p.omap[par], out_stage + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
         tma_store_commit();
       }
       store_pending = true;
@@ -233,6 +281,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     if (ew == 0 && lane == 0) tma_store_wait_all();
   }
 
+  __syncwarp();   // lanes 1..31 of the producer / MMA warps wait here for lane 0
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);

@@ -29,6 +29,35 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __half* __rest
   }
 }
 
+// HardUpsample = nearest x2 then conv3x3 (model_utils.py:161-165).  Output pixel
+// (2y+py, 2x+px) only ever sees the 2x2 source neighbourhood {y+py-1, y+py} x {x+px-1, x+px},
+// so the 3x3 kernel folds, per output parity, into a 2x2 kernel on the SOURCE resolution:
+//   rows:  py=0: dy=-1 <- ky0,        dy=0 <- ky1+ky2;   py=1: dy=0 <- ky0+ky1, dy=+1 <- ky2
+// (same for columns): 2.25x fewer MACs and no upsampled tensor.  Sums are taken in fp32.
+// src fp32 [Cout][Cin][3][3] -> dst fp32 [4*Cout][Cin][2][2] (row = parity * Cout + o).
+__global__ void fold_upconv_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout,
+                                   int cin) {
+  const long long total = (long long)4 * cout * cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int o = (int)((i / cin) % cout);
+    const int par = (int)(i / ((long long)cin * cout));
+    const int py = par >> 1, px = par & 1;
+    const float* w = src + ((long long)o * cin + c) * 9;
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky) {
+      const int a = py == 0 ? (ky == 0 ? 0 : 1) : (ky == 2 ? 1 : 0);
+      for (int kx = 0; kx < 3; ++kx) {
+        const int b = px == 0 ? (kx == 0 ? 0 : 1) : (kx == 2 ? 1 : 0);
+        f[a * 2 + b] += w[ky * 3 + kx];
+      }
+    }
+    float* d = dst + i * 4;
+    d[0] = f[0]; d[1] = f[1]; d[2] = f[2]; d[3] = f[3];
+  }
+}
+
 // ----------------------------------------------------------------------------
 // pose embedding: cs[h, :] = SiLU(W6 pose[h] + b)   (u_net.py:63-66 pose_mlp, then the
 // SiLU that opens every ResnetBlock.mlp, model_utils.py:261-263)
@@ -161,39 +190,90 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float2* __restrict
   }
 }
 
+// Statistics of an NHWC fp16 tensor in the conv-epilogue format (parts of 32 pixels x
+// 8-channel octets); used only behind the SIMT debug convolution.  grid (parts, img).
+__global__ void stats_ref_kernel(const __half* __restrict__ x, float2* __restrict__ stats, int hw,
+                                 int C) {
+  const int part = blockIdx.x, img = blockIdx.y, parts = gridDim.x;
+  const int noct = C / 8;
+  const int npx = hw < 32 ? hw : 32;
+  for (int o = threadIdx.x; o < noct; o += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int p = 0; p < npx; ++p) {
+      const __half* px = x + ((size_t)img * hw + part * 32 + p) * C + o * 8;
+      for (int i = 0; i < 8; ++i) {
+        const float f = __half2float(px[i]);
+        s += f;
+        ss = fmaf(f, f, ss);
+      }
+    }
+    stats[((size_t)img * parts + part) * noct + o] = make_float2(s, ss);
+  }
+}
+
 struct GnApplyArgs {
   const __half* x;
   __half* y;
-  const float2* partial;  // nullptr => no normalisation (y = x + ...)
+  // Partial statistics [img][parts][noct] of (sum, sum of squares); the channels of group g
+  // are covered by entries g*opg .. g*opg+opg-1 of each part (opg = noct / G).  Producers:
+  // the conv epilogue (parts = max(1, hw/32), noct = C/8), gn_stats_kernel (parts = nslab,
+  // noct = G) or a previous gn_apply with `emit` (parts = nslab, noct = 1, G = 1).
+  // nullptr => no normalisation (y = x + ...).
+  const float2* stats;
+  int st_parts, st_noct;
   const float* gamma;
   const float* beta;
   const __half* pb;       // per-hypothesis channel bias (added after the activation) or nullptr
   const __half* res;      // residual or nullptr
   const int* res_of;      // hypothesis -> residual image index, nullptr => identity
+  float2* emit;           // optional: per (img, slab) sum / sum of squares of the outputs y
   int pb_stride, pb_off;
-  int hw, C, G, nslab_stats, nslab;
+  int hw, C, G, nslab;
   int silu;
   float eps;
 };
 
 __global__ void gn_apply_kernel(const GnApplyArgs a) {
+  __shared__ float2 s_red[256];
+  __shared__ float2 s_grp[8];
   const int octs = a.C / 8;
   const int rows = blockDim.x / octs;
   const int o = threadIdx.x % octs;
   const int r = threadIdx.x / octs;
   const int slab = blockIdx.x, h = blockIdx.y;
   float scale[8], shift[8], pbv[8];
-  if (a.partial) {
-    const int g = o / (octs / a.G);
-    float s = 0.f, ss = 0.f;
-    for (int i = 0; i < a.nslab_stats; ++i) {
-      const float2 t = a.partial[((long long)h * a.nslab_stats + i) * a.G + g];
-      s += t.x;
-      ss += t.y;
+  if (a.stats) {
+    // cooperative, fixed-order reduction of this image's partials: tpg threads per group
+    const int opg = a.st_noct / a.G;
+    const int E = a.st_parts * opg;
+    int tpg = 256 / a.G;
+    if (tpg > E) tpg = E;
+    if ((int)threadIdx.x < a.G * tpg) {
+      const int g = threadIdx.x / tpg, li = threadIdx.x - g * tpg;
+      float s = 0.f, ss = 0.f;
+      for (int e = li; e < E; e += tpg) {
+        const int part = e / opg, oo = e - part * opg;
+        const float2 t = a.stats[((size_t)h * a.st_parts + part) * a.st_noct + g * opg + oo];
+        s += t.x;
+        ss += t.y;
+      }
+      s_red[threadIdx.x] = make_float2(s, ss);
     }
+    __syncthreads();
+    if ((int)threadIdx.x < a.G) {
+      float s = 0.f, ss = 0.f;
+      for (int i = 0; i < tpg; ++i) {
+        const float2 t = s_red[threadIdx.x * tpg + i];
+        s += t.x;
+        ss += t.y;
+      }
+      s_grp[threadIdx.x] = make_float2(s, ss);
+    }
+    __syncthreads();
+    const float2 tot = s_grp[o / (octs / a.G)];
     const float cnt = (float)a.hw * (float)(a.C / a.G);
-    const float mean = s / cnt;
-    const float var = fmaxf(ss / cnt - mean * mean, 0.f);
+    const float mean = tot.x / cnt;
+    const float var = fmaxf(tot.y / cnt - mean * mean, 0.f);
     const float rstd = rsqrtf(var + a.eps);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -212,6 +292,7 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
   const long long roff =
       a.res ? ((long long)(a.res_of ? a.res_of[h] : h) * a.hw + (long long)slab * pps) * a.C + o * 8
             : 0;
+  float es = 0.f, ess = 0.f;
   for (int p = r; p < pps; p += rows) {
     const uint4 v = *reinterpret_cast<const uint4*>(a.x + off + (long long)p * a.C);
     const __half2* hv = reinterpret_cast<const __half2*>(&v);
@@ -244,6 +325,35 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
     w.z = pack_half2(f[4], f[5]);
     w.w = pack_half2(f[6], f[7]);
     *reinterpret_cast<uint4*>(a.y + off + (long long)p * a.C) = w;
+    if (a.emit) {
+      // statistics of the values as stored (fp16-rounded), what the consumer will read
+      const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 t = __half22float2(hw2[q]);
+        es += t.x + t.y;
+        ess = fmaf(t.x, t.x, ess);
+        ess = fmaf(t.y, t.y, ess);
+      }
+    }
+  }
+  if (a.emit) {
+    __syncthreads();   // s_red reuse
+#pragma unroll
+    for (int off2 = 16; off2 > 0; off2 >>= 1) {
+      es += __shfl_xor_sync(0xffffffffu, es, off2);
+      ess += __shfl_xor_sync(0xffffffffu, ess, off2);
+    }
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = make_float2(es, ess);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f, ss = 0.f;
+      for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) {
+        s += s_red[i].x;
+        ss += s_red[i].y;
+      }
+      a.emit[(size_t)h * a.nslab + slab] = make_float2(s, ss);
+    }
   }
 }
 
@@ -665,7 +775,8 @@ sim_topk_kernel(const float* __restrict__ partial, int nslab, float* __restrict_
 // SIMT implicit-GEMM convolution: a slow, obviously-correct CUDA-core twin of the
 // tcgen05 kernel (same packed weights, same segment semantics).  Debug / bring-up
 // only (NOPE_CONV_IMPL=simt); never the default path.
-// mode 0: 3x3 pad 1; mode 1: 1x1; mode 2: pixel-unshuffle(2) + 1x1 (input is 2H x 2W).
+// mode 0: 3x3 pad 1; mode 1: 1x1; mode 2: pixel-unshuffle(2) + 1x1 (input is 2H x 2W);
+// mode 3: parity-folded nearest-x2 upsample + 3x3 (input is H/2 x W/2, weights [4*Cout][4*Cin]).
 // ----------------------------------------------------------------------------
 struct SimtConvArgs {
   const __half* src0;
@@ -686,14 +797,16 @@ __global__ void conv_simt_kernel(const SimtConvArgs a) {
     const int px = (int)((i / a.Cout) % a.W);
     const int py = (int)((i / ((long long)a.Cout * a.W)) % a.H);
     const int b = (int)(i / ((long long)a.Cout * a.W * a.H));
-    const __half* wr = a.w + (long long)o * a.K;
+    const int par = a.mode == 3 ? ((py & 1) * 2 + (px & 1)) : 0;
+    const __half* wr = a.w + ((long long)par * a.Cout + o) * a.K;
     float acc = a.bias ? a.bias[o] : 0.f;
     const int taps = a.mode == 0 ? 9 : (a.mode == 1 ? 1 : 4);
     for (int t = 0; t < taps; ++t) {
       int yy, xx, Hs = a.H, Ws = a.W;
       if (a.mode == 0) { yy = py + t / 3 - 1; xx = px + t % 3 - 1; }
       else if (a.mode == 1) { yy = py; xx = px; }
-      else { Hs = 2 * a.H; Ws = 2 * a.W; yy = 2 * py + t / 2; xx = 2 * px + t % 2; }
+      else if (a.mode == 2) { Hs = 2 * a.H; Ws = 2 * a.W; yy = 2 * py + t / 2; xx = 2 * px + t % 2; }
+      else { Hs = a.H / 2; Ws = a.W / 2; yy = (py >> 1) + t / 2 - 1 + (py & 1); xx = (px >> 1) + t % 2 - 1 + (px & 1); }
       if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
       const long long pix = ((long long)b * Hs + yy) * Ws + xx;
       const __half* s0 = a.src0 + pix * a.C0;

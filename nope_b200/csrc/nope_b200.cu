@@ -31,7 +31,7 @@ struct HostTensor {
 };
 
 struct ConvLayer {
-  int mode = 0;  // 0: 3x3 pad1, 1: 1x1, 2: unshuffle+1x1
+  int mode = 0;  // 0: 3x3 pad1, 1: 1x1, 2: unshuffle+1x1, 3: nearest-x2 upsample + 3x3 (folded)
   int cin = 0, cout = 0, K = 0, bn = 0;
   __half* w = nullptr;    // [cout][K] fp16
   float* bias = nullptr;  // [cout] fp32 or nullptr
@@ -85,7 +85,8 @@ struct nope_unet {
   __half *TA = nullptr, *TB = nullptr, *TC = nullptr, *TD = nullptr, *XA = nullptr, *XB = nullptr,
          *RB = nullptr, *cs = nullptr, *pb = nullptr;
   __half *x0 = nullptr, *g1 = nullptr, *pt = nullptr;  // per-reference pre-stage
-  float2* gn_partial = nullptr;
+  float2* gn_partial = nullptr;   // gn_stats_kernel output (per-op test path only)
+  float2 *SA = nullptr, *SB = nullptr;   // fused statistics: conv epilogue / gn_apply emit
   int* ref_of = nullptr;
   float* score_partial = nullptr;
   size_t score_partial_cap = 0;
@@ -202,7 +203,8 @@ struct nope_unet {
                          cudaMemcpyHostToDevice));
     return 0;
   }
-  // pack one conv weight (+ bias) into a ConvLayer
+  // pack one conv weight (+ bias) into a ConvLayer.  mode 3 (nearest-x2 upsample + conv3x3,
+  // HardUpsample) first folds the 3x3 kernel into four 2x2 parity kernels (fold_upconv_kernel).
   int make_conv(const std::string& name, const std::string& wkey, const std::string& bkey, int mode) {
     auto it = host.find(wkey);
     NOPE_CHECK(it != host.end(), "missing tensor " + wkey);
@@ -210,26 +212,37 @@ struct nope_unet {
     ConvLayer L;
     L.mode = mode;
     L.cout = (int)sh[0];
+    const int rows = mode == 3 ? 4 * L.cout : L.cout;   // weight-matrix rows
     const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
     L.cin = mode == 2 ? (int)sh[1] / 4 : (int)sh[1];
     L.K = L.cin * taps;
     NOPE_CHECK(L.cin % 64 == 0, wkey + ": input channels must be a multiple of 64");
     L.bn = pick_bn(L.cout);
     NOPE_CHECK(L.bn != 0, wkey + ": output channels must be a multiple of 64");
-    float* tmp = nullptr;
+    float *tmp = nullptr, *folded = nullptr;
     const size_t n = it->second.data.size();
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), n * sizeof(float)));
     NOPE_CUDA(cudaMemcpy(tmp, it->second.data.data(), n * sizeof(float), cudaMemcpyHostToDevice));
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w), n * sizeof(__half)));
+    const size_t npack = (size_t)rows * L.K;
+    const float* src = tmp;
+    if (mode == 3) {
+      NOPE_CHECK(sh.size() == 4 && sh[2] == 3 && sh[3] == 3, wkey + ": expected a 3x3 kernel");
+      NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&folded), npack * sizeof(float)));
+      fold_upconv_kernel<<<ew_grid((long long)4 * L.cout * L.cin), 256>>>(tmp, folded, L.cout, L.cin);
+      NOPE_CUDA(cudaGetLastError());
+      src = folded;
+    }
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w), npack * sizeof(__half)));
     owned.push_back(L.w);
-    pack_weight_kernel<<<ew_grid((long long)n), 256>>>(tmp, L.w, L.cout, L.cin, taps, L.K, 0);
+    pack_weight_kernel<<<ew_grid((long long)npack), 256>>>(src, L.w, rows, L.cin, taps, L.K, 0);
     NOPE_CUDA(cudaGetLastError());
     NOPE_CUDA(cudaDeviceSynchronize());
     NOPE_CUDA(cudaFree(tmp));
+    if (folded) NOPE_CUDA(cudaFree(folded));
     if (!bkey.empty()) {
       if (upload_f32(bkey, &L.bias)) return -1;
     }
-    if (make_weight_map(&L.wmap, L.w, L.cout, L.K, L.bn)) return -1;
+    if (make_weight_map(&L.wmap, L.w, rows, L.K, L.bn)) return -1;
     L.has_map = true;
     convs[name] = L;
     return 0;
@@ -322,7 +335,7 @@ struct nope_unet {
       const std::string p = "ups." + std::to_string(j);
       if (make_resblock(p + ".0") || make_resblock(p + ".1") || make_linattn(p + ".2")) return -1;
       if (j < 3) {
-        if (make_conv(p + ".3", p + ".3.1.weight", p + ".3.1.bias", 0)) return -1;
+        if (make_conv(p + ".3", p + ".3.1.weight", p + ".3.1.bias", 3)) return -1;
       } else {
         if (make_conv(p + ".3", p + ".3.weight", p + ".3.bias", 0)) return -1;
       }
@@ -372,6 +385,11 @@ struct nope_unet {
     ws_owned.push_back(gn_partial);
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&ref_of), (size_t)std::max(cap, cap_ref) * sizeof(int)));
     ws_owned.push_back(ref_of);
+    const size_t st_per_img = (size_t)S0 * S0 * dim / 256;   // (hw/32) x (C/8) at the top level
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&SA), (size_t)std::max(cap, cap_ref) * st_per_img * sizeof(float2)));
+    ws_owned.push_back(SA);
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&SB), (size_t)std::max(cap, cap_ref) * 8 * sizeof(float2)));
+    ws_owned.push_back(SB);
     return 0;
   }
 
@@ -394,7 +412,7 @@ struct nope_unet {
   // ------------------------------------------------------------------ op launchers
   // out[n_img, So, So, cout] = conv(L, in0 (++ in1))
   int conv(const ConvLayer& L, const __half* in0, int c0, const __half* in1, int c1, __half* out,
-           int So, int n_img, int cap_img, cudaStream_t st) {
+           int So, int n_img, int cap_img, cudaStream_t st, float2* stats = nullptr) {
     NOPE_CHECK(c0 + c1 == L.cin, "conv: channel mismatch");
     ++launches;
     if (conv_impl == 1) {
@@ -403,6 +421,13 @@ struct nope_unet {
       a.n_img = n_img; a.H = So; a.W = So; a.Cout = L.cout; a.K = L.K; a.mode = L.mode;
       conv_simt_kernel<<<ew_grid((long long)n_img * So * So * L.cout, 256, 148 * 32), 256, 0, st>>>(a);
       NOPE_CUDA(cudaGetLastError());
+      if (stats) {
+        // the SIMT twin has no fused statistics: produce them in the conv-epilogue format
+        // (parts = max(1, hw/32), noct = C/8) with a plain reduction kernel
+        const int hw = So * So;
+        stats_ref_kernel<<<dim3(hw < 32 ? 1 : hw / 32, n_img), 256, 0, st>>>(out, stats, hw, L.cout);
+        NOPE_CUDA(cudaGetLastError());
+      }
       return 0;
     }
     TileGeom g;
@@ -411,7 +436,20 @@ struct nope_unet {
     memset(&p, 0, sizeof p);
     const CUtensorMap* m = nullptr;
     int nseg = 0, ksteps = 0;
-    if (L.mode == 2) {
+    p.n_par = 1;
+    if (L.mode == 3) {
+      // So is the OUTPUT side (2x the source side); tiles and input maps use the source geometry
+      NOPE_CHECK(in1 == nullptr && So % 2 == 0, "upsample conv takes one source");
+      if (make_geom(So / 2, So / 2, &g)) return -1;
+      if (get_map(&m, in0, cap_img, c0, g, -1)) return -1;
+      for (int t = 0; t < 4; ++t) p.amap[t] = *m;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          p.seg[nseg++] = ConvSeg{0, (int16_t)(a - 1), (int16_t)(b - 1), (int16_t)(c0 / 64)};
+          ksteps += c0 / 64;
+        }
+      p.n_par = 4;
+    } else if (L.mode == 2) {
       NOPE_CHECK(in1 == nullptr, "unshuffle conv takes one source");
       for (int t = 0; t < 4; ++t) {
         if (get_map(&m, in0, cap_img, c0, g, t)) return -1;
@@ -442,17 +480,30 @@ struct nope_unet {
       }
     }
     p.bmap = L.wmap;
-    if (get_map(&m, out, cap_img, L.cout, g, -1)) return -1;
-    p.omap = *m;
+    if (L.mode == 3) {
+      for (int t = 0; t < 4; ++t) {
+        if (get_map(&m, out, cap_img, L.cout, g, t)) return -1;   // stride-2 sub-lattice (py, px)
+        p.omap[t] = *m;
+      }
+    } else {
+      if (get_map(&m, out, cap_img, L.cout, g, -1)) return -1;
+      for (int t = 0; t < 4; ++t) p.omap[t] = *m;
+    }
     p.bias = L.bias;
+    p.stats = stats;
+    p.stats_hw = So * So;
+    p.stats_noct = L.cout / 8;
+    p.m_valid = n_img * So * So;
     p.nseg = nseg;
     p.ksteps = ksteps;
     p.m_tiles = geom_m_tiles(g, n_img);
-    p.n_tiles = L.cout / L.bn;
+    p.n_tiles_par = L.cout / L.bn;
+    p.n_tiles = p.n_tiles_par * p.n_par;
     p.tiles_per_img = g.tiles_per_img;
     p.h_cnt = g.h_cnt;
     p.b_cnt = g.b_cnt;
     NOPE_CHECK(ksteps * 64 == L.K, "conv: K mismatch");
+    NOPE_CHECK(!(stats && L.mode == 3), "fused statistics are not available on the upsample conv");
     if (!profile) return launch_conv_tc(p, L.bn, num_sms, st);
     cudaEvent_t e0, e1;
     NOPE_CUDA(cudaEventCreate(&e0));
@@ -462,38 +513,51 @@ struct nope_unet {
     NOPE_CUDA(cudaEventRecord(e1, st));
     prof_ev.push_back(e0);
     prof_ev.push_back(e1);
+    // executed FLOPs: mode 3 runs 4 parity GEMMs of K = 4 Cin over the source-resolution pixels
     prof_flops.push_back(2.0 * (double)n_img * So * So * (double)L.cout * (double)L.K);
     return rc;
   }
 
   static int gn_nslab(int hw) { return hw >= 1024 ? 8 : (hw >= 256 ? 2 : 1); }
 
-  // y = [silu](GN(x)) + pb[:, off:off+C] + res
+  // y = [silu](GN(x)) + pb[:, off:off+C] + res.  Statistics come from `stats`
+  // ([img][st_parts][st_noct], see GnApplyArgs); stats == nullptr with N != nullptr runs the
+  // stand-alone gn_stats_kernel first (per-op test path).  `emit` (optional) receives the
+  // per-(img, slab) sums of y for a following GroupNorm(1, C).
   int gn(const NormLayer* N, const __half* x, __half* y, int S, int C, int n_img, bool silu,
-         int pb_offset, const __half* res, const int* res_map, cudaStream_t st) {
+         int pb_offset, const __half* res, const int* res_map, cudaStream_t st,
+         const float2* stats = nullptr, int st_parts = 0, int st_noct = 0, float2* emit = nullptr) {
     const int hw = S * S;
     const int nslab = gn_nslab(hw);
     const int threads = (C / 8) * gn_rows(C);
-    NOPE_CHECK(threads <= 1024 && C % 8 == 0, "gn: unsupported channel count");
+    NOPE_CHECK(threads <= 1024 && threads % 32 == 0 && threads >= 256 && C % 8 == 0,
+               "gn: unsupported channel count");
     if (N) {
       NOPE_CHECK(N->C == C, "gn: channel mismatch");
-      gn_stats_kernel<<<dim3(nslab, n_img), threads, threads * sizeof(float2), st>>>(
-          x, gn_partial, hw, C, N->G, nslab);
-      NOPE_CUDA(cudaGetLastError());
-      ++launches;
+      if (!stats) {
+        gn_stats_kernel<<<dim3(nslab, n_img), threads, threads * sizeof(float2), st>>>(
+            x, gn_partial, hw, C, N->G, nslab);
+        NOPE_CUDA(cudaGetLastError());
+        ++launches;
+        stats = gn_partial;
+        st_parts = nslab;
+        st_noct = N->G;
+      }
+      NOPE_CHECK(st_noct % N->G == 0, "gn: statistics granularity does not match the groups");
     }
     GnApplyArgs a;
-    a.x = x; a.y = y; a.partial = N ? gn_partial : nullptr;
+    a.x = x; a.y = y; a.stats = N ? stats : nullptr; a.st_parts = st_parts; a.st_noct = st_noct;
     a.gamma = N ? N->gamma : nullptr; a.beta = N ? N->beta : nullptr;
     a.pb = pb_offset >= 0 ? pb : nullptr; a.pb_stride = P; a.pb_off = pb_offset >= 0 ? pb_offset : 0;
-    a.res = res; a.res_of = res_map;
-    a.hw = hw; a.C = C; a.G = N ? N->G : 1; a.nslab_stats = nslab; a.nslab = nslab;
+    a.res = res; a.res_of = res_map; a.emit = emit;
+    a.hw = hw; a.C = C; a.G = N ? N->G : 1; a.nslab = nslab;
     a.silu = silu ? 1 : 0; a.eps = 1e-5f;
     gn_apply_kernel<<<dim3(nslab, n_img), threads, 0, st>>>(a);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     return 0;
   }
+  static int st_parts_of(int S) { return S * S < 32 ? 1 : S * S / 32; }
 
   int tap(const char* name, const __half* buf, int C, int S, int n, cudaStream_t st) {
     if (tap_out == nullptr || tap_name != name || tap_hit) return 0;
@@ -504,16 +568,20 @@ struct nope_unet {
     return 0;
   }
 
-  // ResnetBlock.forward (model_utils.py:271-279) on NHWC fp16
+  // ResnetBlock.forward (model_utils.py:271-279) on NHWC fp16.  GroupNorm statistics ride on
+  // the conv epilogues (SA); `emit_g1` makes the last apply also emit the GroupNorm(1, C)
+  // statistics of the block output into SB for a following attention pre-norm.
   int resblock(const std::string& p, const __half* in0, int c0, const __half* in1, int c1,
-               __half* out, int S, int n, bool pose, cudaStream_t st) {
+               __half* out, int S, int n, bool pose, cudaStream_t st, bool emit_g1 = false) {
     const ConvLayer& b1 = convs.at(p + ".block1");
     const ConvLayer& b2 = convs.at(p + ".block2");
     const int co = b1.cout;
-    if (conv(b1, in0, c0, in1, c1, TA, S, n, cap, st)) return -1;
-    if (gn(&norms.at(p + ".norm1"), TA, TB, S, co, n, true, pose ? pb_off.at(p) : -1, nullptr, nullptr, st))
+    const int parts = st_parts_of(S);
+    if (conv(b1, in0, c0, in1, c1, TA, S, n, cap, st, SA)) return -1;
+    if (gn(&norms.at(p + ".norm1"), TA, TB, S, co, n, true, pose ? pb_off.at(p) : -1, nullptr, nullptr, st,
+           SA, parts, co / 8))
       return -1;
-    if (conv(b2, TB, co, nullptr, 0, TA, S, n, cap, st)) return -1;
+    if (conv(b2, TB, co, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
     const __half* res = in0;
     auto it = convs.find(p + ".res");
     if (it != convs.end()) {
@@ -522,24 +590,31 @@ struct nope_unet {
     } else {
       NOPE_CHECK(in1 == nullptr && c0 == co, "resblock: identity residual needs Cin == Cout");
     }
-    return gn(&norms.at(p + ".norm2"), TA, out, S, co, n, true, -1, res, nullptr, st);
+    return gn(&norms.at(p + ".norm2"), TA, out, S, co, n, true, -1, res, nullptr, st, SA, parts, co / 8,
+              emit_g1 ? SB : nullptr);
   }
 
-  // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418)
+  // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418).  x's GroupNorm(1) statistics
+  // were emitted into SB by the producer of x; to_out[1]'s come from the to_out conv epilogue.
   int linattn(const std::string& p, const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
-    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st)) return -1;
+    const int nslab = gn_nslab(S * S);
+    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB, nslab, 1))
+      return -1;
     if (conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
     linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD, TC, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
-    if (conv(convs.at(p + ".out"), TC, kHeadsHidden, nullptr, 0, TA, S, n, cap, st)) return -1;
-    return gn(&norms.at(p + ".outnorm"), TA, out, S, C, n, false, -1, x, nullptr, st);
+    if (conv(convs.at(p + ".out"), TC, kHeadsHidden, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
+    return gn(&norms.at(p + ".outnorm"), TA, out, S, C, n, false, -1, x, nullptr, st, SA, st_parts_of(S),
+              C / 8);
   }
 
   // Residual(PreNorm(Attention)) (model_utils.py:367-390)
   int midattn(const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
     NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
-    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st)) return -1;
+    const int nslab = gn_nslab(S * S);
+    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB, nslab, 1))
+      return -1;
     if (conv(convs.at("mid_attn.qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
     midattn_kernel<<<n, 128, 0, st>>>(TD, TC, S * S);
     NOPE_CUDA(cudaGetLastError());
@@ -555,8 +630,9 @@ struct nope_unet {
                                                                             B, Cl, S0, S0, dim);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
-    if (conv(convs.at("downs.0.0.block1"), x0, dim, nullptr, 0, pt, S0, B, cap_ref, st)) return -1;
-    return gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st);
+    if (conv(convs.at("downs.0.0.block1"), x0, dim, nullptr, 0, pt, S0, B, cap_ref, st, SA)) return -1;
+    return gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st, SA,
+              st_parts_of(S0), dim / 8);
   }
 
   // UNet.forward for hypotheses [hyp0, hyp0 + n) of the flattened (b, pose) list
@@ -589,13 +665,15 @@ struct nope_unet {
       const std::string p = "downs." + std::to_string(i);
       if (i == 0) {
         // block 0 with its block1 half hoisted: TB already holds SiLU(GN(conv(x0))) + pose bias
-        if (conv(convs.at(p + ".0.block2"), TB, C, nullptr, 0, TA, S, n, cap, st)) return -1;
-        if (gn(&norms.at(p + ".0.norm2"), TA, sk[0][0].p, S, C, n, true, -1, x0, ref_of, st)) return -1;
+        if (conv(convs.at(p + ".0.block2"), TB, C, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
+        if (gn(&norms.at(p + ".0.norm2"), TA, sk[0][0].p, S, C, n, true, -1, x0, ref_of, st, SA,
+               st_parts_of(S), C / 8))
+          return -1;
       } else {
         if (resblock(p + ".0", cur, C, nullptr, 0, sk[i][0].p, S, n, true, st)) return -1;
       }
       if (tap((p + ".0").c_str(), sk[i][0].p, C, S, n, st)) return -1;
-      if (resblock(p + ".1", sk[i][0].p, C, nullptr, 0, XA, S, n, true, st)) return -1;
+      if (resblock(p + ".1", sk[i][0].p, C, nullptr, 0, XA, S, n, true, st, true)) return -1;
       if (tap((p + ".1").c_str(), XA, C, S, n, st)) return -1;
       if (linattn(p + ".2", XA, sk[i][1].p, C, S, n, st)) return -1;
       if (tap((p + ".2").c_str(), sk[i][1].p, C, S, n, st)) return -1;
@@ -607,7 +685,7 @@ struct nope_unet {
     // ---- mid, twice with shared weights (u_net.py:177-183)
     const int Cm = dims[4];
     for (int rep = 0; rep < 2; ++rep) {
-      if (resblock("mid_block1", XB, Cm, nullptr, 0, XA, S, n, true, st)) return -1;
+      if (resblock("mid_block1", XB, Cm, nullptr, 0, XA, S, n, true, st, true)) return -1;
       if (midattn(XA, XB, Cm, S, n, st)) return -1;
       if (resblock("mid_block2", XB, Cm, nullptr, 0, XA, S, n, true, st)) return -1;
       if (tap(rep == 0 ? "mid.0" : "mid.1", XA, Cm, S, n, st)) return -1;
@@ -622,17 +700,14 @@ struct nope_unet {
       if (resblock(p + ".0", cur, dout, sk[3 - j][1].p, din, oth, S, n, true, st)) return -1;
       std::swap(cur, oth);
       if (tap((p + ".0").c_str(), cur, dout, S, n, st)) return -1;
-      if (resblock(p + ".1", cur, dout, sk[3 - j][0].p, din, oth, S, n, true, st)) return -1;
+      if (resblock(p + ".1", cur, dout, sk[3 - j][0].p, din, oth, S, n, true, st, true)) return -1;
       std::swap(cur, oth);
       if (linattn(p + ".2", cur, oth, dout, S, n, st)) return -1;
       std::swap(cur, oth);
       if (tap((p + ".2").c_str(), cur, dout, S, n, st)) return -1;
       if (j < 3) {
-        upsample2x_kernel<<<ew_grid((long long)n * 4 * S * S * dout / 8), 256, 0, st>>>(cur, TD, n, S, S, dout);
-        NOPE_CUDA(cudaGetLastError());
-        ++launches;
-        S <<= 1;
-        if (conv(convs.at(p + ".3"), TD, dout, nullptr, 0, oth, S, n, cap, st)) return -1;
+        S <<= 1;   // folded nearest-x2 + conv3x3: reads `cur` at S/2, writes `oth` at S
+        if (conv(convs.at(p + ".3"), cur, dout, nullptr, 0, oth, S, n, cap, st)) return -1;
       } else {
         if (conv(convs.at(p + ".3"), cur, dout, nullptr, 0, oth, S, n, cap, st)) return -1;
       }
@@ -890,20 +965,29 @@ int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, i
                  const float* weight, const float* bias, float* out, int n_img, int H, int W,
                  int Cout, void* stream) {
   NOPE_CHECK(x0 && weight && out, "null argument");
-  NOPE_CHECK(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  NOPE_CHECK(mode >= 0 && mode <= 3, "mode must be 0..3");
   NOPE_CHECK(H == W, "square images only");
   NOPE_CHECK(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0, "channels must be multiples of 64");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Scratch s;
   const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
   const int cin = C0 + (x1 ? C1 : 0);
-  const int Hin = mode == 2 ? 2 * H : H;
+  const int Hin = mode == 2 ? 2 * H : (mode == 3 ? H / 2 : H);
+  const int rows = mode == 3 ? 4 * Cout : Cout;
   __half *a0 = nullptr, *a1 = nullptr, *wp = nullptr, *o = nullptr;
   if (to_nhwc(x0, &a0, s, n_img, C0, Hin * Hin, st)) return -1;
   if (x1 && to_nhwc(x1, &a1, s, n_img, C1, Hin * Hin, st)) return -1;
-  if (s.get(&wp, (size_t)Cout * cin * taps) || s.get(&o, (size_t)n_img * H * W * Cout)) return -1;
-  pack_weight_kernel<<<ew_grid((long long)Cout * cin * taps), 256, 0, st>>>(weight, wp, Cout, cin, taps,
-                                                                            cin * taps, 0);
+  if (s.get(&wp, (size_t)rows * cin * taps) || s.get(&o, (size_t)n_img * H * W * Cout)) return -1;
+  const float* wsrc = weight;
+  if (mode == 3) {
+    float* folded = nullptr;
+    if (s.get(&folded, (size_t)rows * cin * taps)) return -1;
+    fold_upconv_kernel<<<ew_grid((long long)4 * Cout * cin), 256, 0, st>>>(weight, folded, Cout, cin);
+    NOPE_CUDA(cudaGetLastError());
+    wsrc = folded;
+  }
+  pack_weight_kernel<<<ew_grid((long long)rows * cin * taps), 256, 0, st>>>(wsrc, wp, rows, cin, taps,
+                                                                           cin * taps, 0);
   NOPE_CUDA(cudaGetLastError());
   nope_unet eng;  // only used for its conv launcher / map cache
   eng.conv_impl = impl;
@@ -920,9 +1004,55 @@ int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, i
     NOPE_CUDA(cudaMemcpyAsync(dbias, bias, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   L.bias = dbias;
-  if (impl == 0 && make_weight_map(&L.wmap, wp, Cout, L.K, L.bn)) return -1;
+  if (impl == 0 && make_weight_map(&L.wmap, wp, rows, L.K, L.bn)) return -1;
   if (eng.conv(L, a0, C0, a1, x1 ? C1 : 0, o, H, n_img, n_img, st)) return -1;
   if (to_nchw(o, out, n_img, Cout, H * W, st)) return -1;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nope_op_conv_gn(int impl, int mode, const float* x0, int C0, const float* x1, int C1,
+                    const float* weight, const float* bias, const float* gamma, const float* beta,
+                    int G, int silu, float* out, int n_img, int H, int W, int Cout, void* stream) {
+  NOPE_CHECK(x0 && weight && gamma && beta && out, "null argument");
+  NOPE_CHECK(mode >= 0 && mode <= 2 && H == W, "bad mode / non-square image");
+  NOPE_CHECK(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0, "channels must be multiples of 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Scratch s;
+  const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
+  const int cin = C0 + (x1 ? C1 : 0);
+  const int Hin = mode == 2 ? 2 * H : H;
+  __half *a0 = nullptr, *a1 = nullptr, *wp = nullptr, *o = nullptr, *y = nullptr;
+  if (to_nhwc(x0, &a0, s, n_img, C0, Hin * Hin, st)) return -1;
+  if (x1 && to_nhwc(x1, &a1, s, n_img, C1, Hin * Hin, st)) return -1;
+  if (s.get(&wp, (size_t)Cout * cin * taps) || s.get(&o, (size_t)n_img * H * W * Cout) ||
+      s.get(&y, (size_t)n_img * H * W * Cout))
+    return -1;
+  pack_weight_kernel<<<ew_grid((long long)Cout * cin * taps), 256, 0, st>>>(weight, wp, Cout, cin, taps,
+                                                                            cin * taps, 0);
+  NOPE_CUDA(cudaGetLastError());
+  nope_unet eng;
+  eng.conv_impl = impl;
+  cudaDeviceProp prop;
+  int dev = 0;
+  NOPE_CUDA(cudaGetDevice(&dev));
+  NOPE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  eng.num_sms = prop.multiProcessorCount;
+  ConvLayer L;
+  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = cin * taps; L.bn = pick_bn(Cout); L.w = wp;
+  L.bias = const_cast<float*>(bias);
+  if (impl == 0 && make_weight_map(&L.wmap, wp, Cout, L.K, L.bn)) return -1;
+  const int parts = nope_unet::st_parts_of(H);
+  float2* stats = nullptr;
+  if (s.get(&stats, (size_t)n_img * parts * (Cout / 8))) return -1;
+  if (eng.conv(L, a0, C0, a1, x1 ? C1 : 0, o, H, n_img, n_img, st, stats)) return -1;
+  NormLayer N;
+  N.C = Cout; N.G = G;
+  N.gamma = const_cast<float*>(gamma);
+  N.beta = const_cast<float*>(beta);
+  if (eng.gn(&N, o, y, H, Cout, n_img, silu != 0, -1, nullptr, nullptr, st, stats, parts, Cout / 8))
+    return -1;
+  if (to_nchw(y, out, n_img, Cout, H * W, st)) return -1;
   NOPE_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

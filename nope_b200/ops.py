@@ -19,19 +19,38 @@ def _f32(t):
 
 
 def conv(x0, weight, bias=None, x1=None, mode="3x3", impl="tcgen05"):
-    """mode '3x3' (pad 1), '1x1', or 'unshuffle' (pixel-unshuffle(2) + 1x1; weight
-    [Cout, 4*Cin, 1, 1]).  x1 is concatenated after x0 along channels."""
+    """mode '3x3' (pad 1), '1x1', 'unshuffle' (pixel-unshuffle(2) + 1x1; weight
+    [Cout, 4*Cin, 1, 1]) or 'upsample3x3' (nearest x2 + conv3x3, folded into four 2x2 parity
+    kernels; x0 is the low-resolution input).  x1 is concatenated after x0 along channels."""
     lib = _lib.load()
-    m = {"3x3": 0, "1x1": 1, "unshuffle": 2}[mode]
+    m = {"3x3": 0, "1x1": 1, "unshuffle": 2, "upsample3x3": 3}[mode]
     x0, x1, weight, bias = _f32(x0), _f32(x1), _f32(weight), _f32(bias)
     n, c0, hin, win = x0.shape
-    h, w = (hin // 2, win // 2) if m == 2 else (hin, win)
+    h, w = (hin // 2, win // 2) if m == 2 else ((2 * hin, 2 * win) if m == 3 else (hin, win))
     cout = weight.shape[0]
     out = torch.empty((n, cout, h, w), device=x0.device, dtype=torch.float32)
     with torch.cuda.device(x0.device):
         _lib.check(lib.nope_op_conv(_IMPL[impl], m, _lib.ptr(x0), c0, _lib.ptr(x1),
                                     0 if x1 is None else x1.shape[1], _lib.ptr(weight),
                                     _lib.ptr(bias), _lib.ptr(out), n, h, w, cout, _stream(x0.device)))
+    return out
+
+
+def conv_gn(x0, weight, bias, gamma, beta, groups, silu=True, x1=None, mode="3x3", impl="tcgen05"):
+    """[SiLU](GroupNorm(conv(x))) with statistics from the conv epilogue (the sweep's path)."""
+    lib = _lib.load()
+    m = {"3x3": 0, "1x1": 1, "unshuffle": 2}[mode]
+    x0, x1, weight, bias, gamma, beta = map(_f32, (x0, x1, weight, bias, gamma, beta))
+    n, c0, hin, win = x0.shape
+    h, w = (hin // 2, win // 2) if m == 2 else (hin, win)
+    cout = weight.shape[0]
+    out = torch.empty((n, cout, h, w), device=x0.device, dtype=torch.float32)
+    with torch.cuda.device(x0.device):
+        _lib.check(lib.nope_op_conv_gn(_IMPL[impl], m, _lib.ptr(x0), c0, _lib.ptr(x1),
+                                       0 if x1 is None else x1.shape[1], _lib.ptr(weight),
+                                       _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), groups,
+                                       1 if silu else 0, _lib.ptr(out), n, h, w, cout,
+                                       _stream(x0.device)))
     return out
 
 

@@ -14,7 +14,7 @@ from _util import log, max_rel, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-EMB_TOL = 3e-3
+EMB_TOL = 2.5e-3   # measured 1.4-1.8e-3; fp16 weight rounding alone is 0.9e-3 (tools/precision_budget.py)
 SIM_TOL = 1e-3
 
 
