@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--poses", type=int, default=N_POSES, help="poses per GPU")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("NOPE_CHUNK", "256")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-impl", default=os.environ.get("NOPE_CONV_IMPL", "tcgen05"),
+                    choices=["tcgen05", "tcgen05_2cta"])
     return ap.parse_args()
 
 
@@ -252,6 +254,7 @@ def main():
     model = build_model(device=str(dev), chunk=args.chunk)
     model.load_state_dict(weights.make_full_state_dict(seed=0)).eval()
     unet = model.u_net
+    unet.set_conv_impl(args.conv_impl)
     if world > 1:
         model.dist = ShardedSweep()
 
@@ -337,6 +340,7 @@ def main():
             "workload": f"configs[1]: 256x256, {n_local}-pose icosphere grid per GPU, batch=1 query, "
                         "fp16 UNet (fp32 accumulate / statistics), l2 score + top-5",
             "poses_per_gpu": n_local, "global_poses": n_global, "queries": 1, "chunk": args.chunk,
+            "conv_impl": args.conv_impl,
             "weights": "seeded random init, reference state_dict schema (305.8 M params)",
             "l2": "not flushed: each step streams 0.61 GB of fp16 weights and ~1.4 GB of "
                   "activations per chunk, >> 126 MB L2",

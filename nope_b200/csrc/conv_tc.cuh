@@ -18,11 +18,12 @@
 // connections, u_net.py:186-194) is two source tensor maps walked by the same K
 // loop; pixel-unshuffle + 1x1 (HardDownsample) is four stride-2 tensor maps.
 //
-// CTA = 8 warps, persistent over (m_tile, n_tile) work items:
-//   warp 0 lane 0 : TMA producer      (smem ring, full/empty mbarriers)
-//   warp 1 lane 0 : tcgen05.mma issuer (accumulator in TMEM, double buffered)
+// CTA = 12 warps, persistent over (m_tile, n_tile) work items:
+//   warp 0        : TMA producer      (smem ring, full/empty mbarriers; one elected lane issues)
+//   warp 1        : tcgen05.mma issuer (accumulator in TMEM, double buffered)
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue: tcgen05.ld -> +bias -> fp16 -> swizzled smem -> TMA store
+//   warps 4..11   : epilogue: tcgen05.ld -> +bias -> GroupNorm partial sums -> fp16 ->
+//                   swizzled smem -> TMA store (two warps per TMEM lane quarter)
 #pragma once
 #include "common.cuh"
 #include <cudaTypedefs.h>
@@ -32,7 +33,8 @@ namespace nope {
 constexpr int kBM = 128;         // pixels per tile (UMMA M)
 constexpr int kBK = 64;          // channels per K-step (one 128-byte swizzle row)
 constexpr int kMaxSeg = 18;      // 9 taps x 2 sources
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 
 struct ConvSeg {
   int16_t map;      // index into amap[]
@@ -43,6 +45,7 @@ struct ConvSeg {
 struct ConvParams {
   CUtensorMap amap[4];
   CUtensorMap bmap;
+  CUtensorMap bmap_half;  // box of BN/2 weight rows: the 2-CTA kernel (conv_tc2.cuh)
   CUtensorMap omap[4];  // one per output parity class when n_par == 4, else omap[0]
   const float* bias;  // [n_total] or nullptr
   // Sub-pixel ("parity") decomposition of nearest-x2-upsample + conv3x3 (HardUpsample,
@@ -73,7 +76,8 @@ struct ConvSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = (BN / 64) * kBM * 128;
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
+  static constexpr int kBiasOffset = kBarOffset + 256;
+  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int m_tile, int& b0,
@@ -84,6 +88,108 @@ __device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int m_tile
   } else {
     b0 = m_tile * p.b_cnt;
     y0 = 0;
+  }
+}
+
+// constant bits of the K-major SWIZZLE_128B operand descriptor (see make_sw128_kmajor_desc)
+constexpr uint64_t kDescHi = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                             (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+
+// Transposing butterfly: every lane holds 8 partial values; afterwards v[0] of lane l is the
+// total over the kSeg lanes of its segment of value number `idx` (returned).  8+4+2(+1)
+// shuffles instead of 8 x log2(kSeg); fixed combination order, so results are deterministic.
+template <int kSeg>
+__device__ __forceinline__ int butterfly8(float (&v)[8], int lane) {
+  static_assert(kSeg == 16 || kSeg == 32, "segment must be 16 or 32 lanes");
+  constexpr int m0 = kSeg / 2, m1 = kSeg / 4, m2 = kSeg / 8;
+  {
+    const bool up = (lane & m0) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m0);
+    }
+  }
+  {
+    const bool up = (lane & m1) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m1);
+    }
+  }
+  {
+    const bool up = (lane & m2) != 0;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, m2);
+  }
+#pragma unroll
+  for (int m = m2 / 2; m > 0; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+  return ((lane & m0) ? 4 : 0) + ((lane & m1) ? 2 : 0) + ((lane & m2) ? 1 : 0);
+}
+
+// Epilogue of one 128 x BN accumulator tile, executed by the 8 epilogue warps of a CTA.
+// Warp e reads TMEM lanes 32*(e&3).. (its pixel rows) and the 32-column half (e>>2) of every
+// 64-column sub-tile: +bias (from smem) -> GroupNorm partial sums -> fp16 -> swizzled staging.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t* out_stage,
+                                                   const float* s_bias, uint32_t t_acc, int m_tile,
+                                                   int n_chan0, int e, int lane) {
+  const int q = e & 3, hh = e >> 2;
+  const int row = q * 32 + lane;
+  const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
+  uint32_t va[32], vb[32];
+  tmem_ld_32x32(t_row, va);
+#pragma unroll
+  for (int cc = 0; cc < BN / 64; ++cc) {
+    tmem_ld_wait();
+    uint32_t(&v)[32] = (cc & 1) ? vb : va;
+    if (cc + 1 < BN / 64) tmem_ld_32x32(t_row + (cc + 1) * 64, (cc & 1) ? va : vb);
+    const float* bs = s_bias + cc * 64 + hh * 32;
+    uint8_t* srow = out_stage + cc * (kBM * 128) + row * 128;
+    float st[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // 4 x 16-byte chunks of 8 channels
+      const float4 b0 = *reinterpret_cast<const float4*>(bs + j * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bs + j * 8 + 4);
+      float f[8];
+      f[0] = __uint_as_float(v[j * 8 + 0]) + b0.x;
+      f[1] = __uint_as_float(v[j * 8 + 1]) + b0.y;
+      f[2] = __uint_as_float(v[j * 8 + 2]) + b0.z;
+      f[3] = __uint_as_float(v[j * 8 + 3]) + b0.w;
+      f[4] = __uint_as_float(v[j * 8 + 4]) + b1.x;
+      f[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
+      f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z;
+      f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
+      float s = (f[0] + f[1]) + (f[2] + f[3]) + ((f[4] + f[5]) + (f[6] + f[7]));
+      float q2 = f[0] * f[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) q2 = fmaf(f[i], f[i], q2);
+      st[2 * j] = s;
+      st[2 * j + 1] = q2;
+      const int phys = (hh * 4 + j) ^ (row & 7);   // SWIZZLE_128B: chunk index XOR (row mod 8)
+      *reinterpret_cast<uint4*>(srow + phys * 16) =
+          make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]),
+                     pack_half2(f[6], f[7]));
+    }
+    if (p.stats) {
+      const bool small = p.stats_hw < 32;            // 4x4 images: two per warp
+      const int idx = small ? butterfly8<16>(st, lane) : butterfly8<32>(st, lane);
+      const int seg = small ? 16 : 32;
+      const int gp = m_tile * kBM + (row & ~(seg - 1));
+      const bool writer = small ? ((lane & 1) == 0) : ((lane & 3) == 0);
+      if (writer && gp < p.m_valid) {
+        const int img = gp / p.stats_hw;
+        const int parts = small ? 1 : p.stats_hw >> 5;
+        const int part = small ? 0 : (gp - img * p.stats_hw) >> 5;
+        float* dst = reinterpret_cast<float*>(p.stats + ((size_t)img * parts + part) * p.stats_noct +
+                                              (n_chan0 + cc * 64 + hh * 32) / 8);
+        dst[idx] = st[0];                            // idx = octet * 2 + {sum, sum of squares}
+      }
+    }
   }
 }
 
@@ -103,6 +209,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -130,7 +237,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // The producer and MMA warps run their loops warp-converged and elect one lane only around
+  // the instruction issue: control flow and address arithmetic stay on the uniform datapath
+  // (a `lane == 0` branch around the whole loop cost ~120 SASS instructions per K-step).
+  if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -147,18 +257,21 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         const CUtensorMap* am = &p.amap[sg.map];
         for (int ch = 0; ch < sg.nchunks; ++ch) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_4d(sa, am, &full_bar[stage], ch * kBK, sg.dx + px, y0 + sg.dy + py, b0);
-          tma_load_2d(sa + S::kABytes, &p.bmap, &full_bar[stage], kcol, n_tile * BN);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * S::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_4d(sa, am, &full_bar[stage], ch * kBK, sg.dx + px, y0 + sg.dy + py, b0);
+            tma_load_2d(sa + S::kABytes, &p.bmap, &full_bar[stage], kcol, n_tile * BN);
+          }
           kcol += kBK;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_f16(kBM, BN, false);
+    const uint32_t smem_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -170,28 +283,29 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
       for (int ks = 0; ks < p.ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-        const uint64_t adesc = make_sw128_kmajor_desc(sa);
-        const uint64_t bdesc = make_sw128_kmajor_desc(sa + S::kABytes);
+        if (elect_one()) {
+          const uint32_t a_lo = (smem_base + stage * S::kStageBytes) >> 4;
+          const uint64_t adesc = kDescHi | a_lo;
+          const uint64_t bdesc = kDescHi | (a_lo + (S::kABytes >> 4));
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 field
-          umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 field
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ks == p.ksteps - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&empty_bar[stage]);
-        if (ks == p.ksteps - 1) umma_commit(&tfull_bar[acc]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;            // == warp % 4: TMEM lane quarter this warp may read
-    const int row = ew * 32 + lane;     // pixel row inside the tile
+    // ===================== epilogue (8 warps) =====================
+    const int e = warp - 4;
+    const int etid = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
-    bool store_pending = false;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
@@ -199,89 +313,32 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
       const int n_chan0 = (n_tile - par * p.n_tiles_par) * BN;   // first output channel of the tile
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
-      // staging buffer must have been fully read by the previous TMA store
-      if (store_pending) {
-        if (ew == 0 && lane == 0) tma_store_wait_read0();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
+      if (etid < BN) s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
+      // staging buffer must have been fully read by the previous TMA store; bias visible
+      if (etid == 0) tma_store_wait_read0();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(t_row + cc * 64, v0);
-        tmem_ld_32x32(t_row + cc * 64 + 32, v1);
-        tmem_ld_wait();
-        const float* bptr = p.bias ? p.bias + n_chan0 + cc * 64 : nullptr;
-        uint8_t* srow = out_stage + cc * (kBM * 128) + row * 128;
-        float st_s[8], st_q[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {   // 8 x 16-byte chunks of 8 channels
-          uint32_t w[4];
-          float s = 0.f, q2 = 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = j * 8 + q * 2;
-            float a = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
-            float b = __uint_as_float(c + 1 < 32 ? v0[c + 1] : v1[c + 1 - 32]);
-            if (bptr) { a += __ldg(bptr + c); b += __ldg(bptr + c + 1); }
-            s += a + b;
-            q2 = fmaf(a, a, q2);
-            q2 = fmaf(b, b, q2);
-            w[q] = pack_half2(a, b);
-          }
-          st_s[j] = s;
-          st_q[j] = q2;
-          const int phys = j ^ (row & 7);   // SWIZZLE_128B: 16-B chunk index XOR (row mod 8)
-          *reinterpret_cast<uint4*>(srow + phys * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        if (p.stats) {
-          // fixed-order butterfly over the rows of one image segment (<= 32 rows)
-          const int seg = p.stats_hw < 32 ? p.stats_hw : 32;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float s = st_s[j], q2 = st_q[j];
-            for (int off = seg >> 1; off > 0; off >>= 1) {
-              s += __shfl_xor_sync(0xffffffffu, s, off);
-              q2 += __shfl_xor_sync(0xffffffffu, q2, off);
-            }
-            st_s[j] = s;
-            st_q[j] = q2;
-          }
-          const int gp = m_tile * kBM + row;
-          if ((lane & (seg - 1)) == 0 && gp < p.m_valid) {
-            const int img = gp / p.stats_hw;
-            const int parts = p.stats_hw < 32 ? 1 : p.stats_hw >> 5;
-            const int part = (gp - img * p.stats_hw) >> 5;
-            float2* dst = p.stats + ((size_t)img * parts + part) * p.stats_noct +
-                          (n_chan0 + cc * 64) / 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float2(st_s[j], st_q[j]);
-          }
-        }
-      }
+      conv_epilogue_tile<BN>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       // accumulator fully read: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       // make the generic-proxy smem writes visible to the TMA (async proxy), then store
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ew == 0 && lane == 0) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (etid == 0) {
 #pragma unroll 1
         for (int cc = 0; cc < BN / 64; ++cc)
           tma_store_4d(&p.omap[par], out_stage + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
         tma_store_commit();
       }
-      store_pending = true;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (ew == 0 && lane == 0) tma_store_wait_all();
+    if (etid == 0) tma_store_wait_all();
   }
 
-  __syncwarp();   // lanes 1..31 of the producer / MMA warps wait here for lane 0
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "kernels.cuh"
 
 using namespace nope;
@@ -36,6 +37,7 @@ struct ConvLayer {
   __half* w = nullptr;    // [cout][K] fp16
   float* bias = nullptr;  // [cout] fp32 or nullptr
   CUtensorMap wmap;
+  CUtensorMap wmap_half;  // BN/2-row box for the 2-CTA kernel
   bool has_map = false;
 };
 
@@ -243,6 +245,7 @@ struct nope_unet {
       if (upload_f32(bkey, &L.bias)) return -1;
     }
     if (make_weight_map(&L.wmap, L.w, rows, L.K, L.bn)) return -1;
+    if (make_weight_map(&L.wmap_half, L.w, rows, L.K, L.bn / 2)) return -1;
     L.has_map = true;
     convs[name] = L;
     return 0;
@@ -480,6 +483,7 @@ struct nope_unet {
       }
     }
     p.bmap = L.wmap;
+    p.bmap_half = L.wmap_half;
     if (L.mode == 3) {
       for (int t = 0; t < 4; ++t) {
         if (get_map(&m, out, cap_img, L.cout, g, t)) return -1;   // stride-2 sub-lattice (py, px)
@@ -504,12 +508,15 @@ struct nope_unet {
     p.b_cnt = g.b_cnt;
     NOPE_CHECK(ksteps * 64 == L.K, "conv: K mismatch");
     NOPE_CHECK(!(stats && L.mode == 3), "fused statistics are not available on the upsample conv");
-    if (!profile) return launch_conv_tc(p, L.bn, num_sms, st);
+    auto launch = [&]() {
+      return conv_impl == 2 ? launch_conv_tc2(p, L.bn, num_sms, st) : launch_conv_tc(p, L.bn, num_sms, st);
+    };
+    if (!profile) return launch();
     cudaEvent_t e0, e1;
     NOPE_CUDA(cudaEventCreate(&e0));
     NOPE_CUDA(cudaEventCreate(&e1));
     NOPE_CUDA(cudaEventRecord(e0, st));
-    const int rc = launch_conv_tc(p, L.bn, num_sms, st);
+    const int rc = launch();
     NOPE_CUDA(cudaEventRecord(e1, st));
     prof_ev.push_back(e0);
     prof_ev.push_back(e1);
@@ -843,7 +850,7 @@ int nope_unet_set_chunk(nope_unet_t* u, int hyps) {
   return 0;
 }
 int nope_unet_set_conv_impl(nope_unet_t* u, int impl) {
-  NOPE_CHECK(u && (impl == 0 || impl == 1), "impl must be 0 (tcgen05) or 1 (simt)");
+  NOPE_CHECK(u && impl >= 0 && impl <= 2, "impl must be 0 (tcgen05), 1 (simt) or 2 (tcgen05 2-CTA)");
   u->conv_impl = impl;
   return 0;
 }
@@ -1004,7 +1011,9 @@ int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, i
     NOPE_CUDA(cudaMemcpyAsync(dbias, bias, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   L.bias = dbias;
-  if (impl == 0 && make_weight_map(&L.wmap, wp, rows, L.K, L.bn)) return -1;
+  if (impl != 1 && (make_weight_map(&L.wmap, wp, rows, L.K, L.bn) ||
+                    make_weight_map(&L.wmap_half, wp, rows, L.K, L.bn / 2)))
+    return -1;
   if (eng.conv(L, a0, C0, a1, x1 ? C1 : 0, o, H, n_img, n_img, st)) return -1;
   if (to_nchw(o, out, n_img, Cout, H * W, st)) return -1;
   NOPE_CUDA(cudaStreamSynchronize(st));
@@ -1041,7 +1050,9 @@ int nope_op_conv_gn(int impl, int mode, const float* x0, int C0, const float* x1
   ConvLayer L;
   L.mode = mode; L.cin = cin; L.cout = Cout; L.K = cin * taps; L.bn = pick_bn(Cout); L.w = wp;
   L.bias = const_cast<float*>(bias);
-  if (impl == 0 && make_weight_map(&L.wmap, wp, Cout, L.K, L.bn)) return -1;
+  if (impl != 1 && (make_weight_map(&L.wmap, wp, Cout, L.K, L.bn) ||
+                    make_weight_map(&L.wmap_half, wp, Cout, L.K, L.bn / 2)))
+    return -1;
   const int parts = nope_unet::st_parts_of(H);
   float2* stats = nullptr;
   if (s.get(&stats, (size_t)n_img * parts * (Cout / 8))) return -1;

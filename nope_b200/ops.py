@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-_IMPL = {"tcgen05": 0, "simt": 1}
+_IMPL = {"tcgen05": 0, "simt": 1, "tcgen05_2cta": 2}
 
 
 def _stream(dev):

@@ -100,9 +100,9 @@ class UNet:
             _lib.check(_lib.load().nope_unet_set_chunk(self._h, hyps))
 
     def set_conv_impl(self, impl):
-        """'tcgen05' (default) or 'simt' (debug twin on CUDA cores)."""
-        _lib.check(_lib.load().nope_unet_set_conv_impl(self._handle(),
-                                                       {"tcgen05": 0, "simt": 1}[impl]))
+        """'tcgen05' (default), 'tcgen05_2cta' (CTA pairs) or 'simt' (debug twin on CUDA cores)."""
+        _lib.check(_lib.load().nope_unet_set_conv_impl(
+            self._handle(), {"tcgen05": 0, "simt": 1, "tcgen05_2cta": 2}[impl]))
 
     @property
     def last_launch_count(self):
