@@ -58,8 +58,8 @@ int nope_unet_load_tensor(nope_unet_t* u, const char* key, const float* data,
 int nope_unet_finalize(nope_unet_t* u);
 
 /* Tunables: hypotheses per chunk (workspace = ~5.5 MB per hypothesis), and the
- * convolution implementation: 0 = tcgen05 tensor cores, 128-pixel tiles (default),
- * 1 = SIMT debug twin, 2 = tcgen05 with CTA pairs (cta_group::2, 256-pixel tiles). */
+ * convolution implementation: 0 = tcgen05 tensor cores, 128-pixel tiles, 1 = SIMT debug
+ * twin, 2 = tcgen05 with CTA pairs (cta_group::2, 256-pixel tiles; default). */
 int nope_unet_set_chunk(nope_unet_t* u, int hyps_per_chunk);
 int nope_unet_set_conv_impl(nope_unet_t* u, int impl);
 

@@ -233,7 +233,18 @@ struct GnApplyArgs {
   float eps;
 };
 
-__global__ void gn_apply_kernel(const GnApplyArgs a) {
+__device__ __forceinline__ uint4 ld_stream16(const __half* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+constexpr int kGnUnroll = 4;   // independent 16-byte loads in flight per thread
+
+template <bool SILU, bool PB, bool RES>
+__global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float2 s_red[256];
   __shared__ float2 s_grp[8];
   const int octs = a.C / 8;
@@ -243,6 +254,11 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
   const int slab = blockIdx.x, h = blockIdx.y;
   float scale[8], shift[8], pbv[8];
   if (a.stats) {
+    // independent loads first (affine parameters), then the partial statistics
+    float4 g0 = *reinterpret_cast<const float4*>(a.gamma + o * 8);
+    float4 g1 = *reinterpret_cast<const float4*>(a.gamma + o * 8 + 4);
+    float4 be0 = *reinterpret_cast<const float4*>(a.beta + o * 8);
+    float4 be1 = *reinterpret_cast<const float4*>(a.beta + o * 8 + 4);
     // cooperative, fixed-order reduction of this image's partials: tpg threads per group
     const int opg = a.st_noct / a.G;
     const int E = a.st_parts * opg;
@@ -275,65 +291,88 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
     const float mean = tot.x / cnt;
     const float var = fmaxf(tot.y / cnt - mean * mean, 0.f);
     const float rstd = rsqrtf(var + a.eps);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bt[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      scale[i] = rstd * a.gamma[o * 8 + i];
-      shift[i] = a.beta[o * 8 + i] - mean * scale[i];
+      scale[i] = rstd * gm[i];
+      shift[i] = bt[i] - mean * scale[i];
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { scale[i] = 1.f; shift[i] = 0.f; }
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    pbv[i] = a.pb ? __half2float(a.pb[(long long)h * a.pb_stride + a.pb_off + o * 8 + i]) : 0.f;
-  const int pps = a.hw / a.nslab;
-  const long long off = ((long long)h * a.hw + (long long)slab * pps) * a.C + o * 8;
-  const long long roff =
-      a.res ? ((long long)(a.res_of ? a.res_of[h] : h) * a.hw + (long long)slab * pps) * a.C + o * 8
-            : 0;
-  float es = 0.f, ess = 0.f;
-  for (int p = r; p < pps; p += rows) {
-    const uint4 v = *reinterpret_cast<const uint4*>(a.x + off + (long long)p * a.C);
-    const __half2* hv = reinterpret_cast<const __half2*>(&v);
-    float f[8];
+  if (PB) {
+    const uint4 pv = *reinterpret_cast<const uint4*>(a.pb + (long long)h * a.pb_stride + a.pb_off + o * 8);
+    const __half2* hp = reinterpret_cast<const __half2*>(&pv);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 t = __half22float2(hv[q]);
-      f[2 * q] = t.x;
-      f[2 * q + 1] = t.y;
+      const float2 t = __half22float2(hp[q]);
+      pbv[2 * q] = t.x;
+      pbv[2 * q + 1] = t.y;
     }
+  }
+  const int pps = a.hw / a.nslab;
+  const __half* xp = a.x + ((long long)h * a.hw + (long long)slab * pps) * a.C + o * 8;
+  __half* yp = a.y + ((long long)h * a.hw + (long long)slab * pps) * a.C + o * 8;
+  const __half* rp = nullptr;
+  if (RES)
+    rp = a.res + ((long long)(a.res_of ? a.res_of[h] : h) * a.hw + (long long)slab * pps) * a.C + o * 8;
+  float es = 0.f, ess = 0.f;
+  for (int p0 = r; p0 < pps; p0 += rows * kGnUnroll) {
+    uint4 xv[kGnUnroll], rv[kGnUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = fmaf(f[i], scale[i], shift[i]);
-      if (a.silu) t = silu_f(t);
-      f[i] = t + pbv[i];
-    }
-    if (a.res) {
-      const uint4 rv = *reinterpret_cast<const uint4*>(a.res + roff + (long long)p * a.C);
-      const __half2* hr = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 t = __half22float2(hr[q]);
-        f[2 * q] += t.x;
-        f[2 * q + 1] += t.y;
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const int p = p0 + u * rows;
+      if (p < pps) {
+        xv[u] = ld_stream16(xp + (long long)p * a.C);
+        if (RES) rv[u] = ld_stream16(rp + (long long)p * a.C);
       }
     }
-    uint4 w;
-    w.x = pack_half2(f[0], f[1]);
-    w.y = pack_half2(f[2], f[3]);
-    w.z = pack_half2(f[4], f[5]);
-    w.w = pack_half2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(a.y + off + (long long)p * a.C) = w;
-    if (a.emit) {
-      // statistics of the values as stored (fp16-rounded), what the consumer will read
-      const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const int p = p0 + u * rows;
+      if (p >= pps) break;
+      const __half2* hv = reinterpret_cast<const __half2*>(&xv[u]);
+      float f[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 t = __half22float2(hw2[q]);
-        es += t.x + t.y;
-        ess = fmaf(t.x, t.x, ess);
-        ess = fmaf(t.y, t.y, ess);
+        const float2 t = __half22float2(hv[q]);
+        f[2 * q] = t.x;
+        f[2 * q + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = fmaf(f[i], scale[i], shift[i]);
+        if (SILU) t = silu_f(t);
+        if (PB) t += pbv[i];
+        f[i] = t;
+      }
+      if (RES) {
+        const __half2* hr = reinterpret_cast<const __half2*>(&rv[u]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 t = __half22float2(hr[q]);
+          f[2 * q] += t.x;
+          f[2 * q + 1] += t.y;
+        }
+      }
+      uint4 w;
+      w.x = pack_half2(f[0], f[1]);
+      w.y = pack_half2(f[2], f[3]);
+      w.z = pack_half2(f[4], f[5]);
+      w.w = pack_half2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(yp + (long long)p * a.C) = w;
+      if (a.emit) {
+        // statistics of the values as stored (fp16-rounded), what the consumer will read
+        const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 t = __half22float2(hw2[q]);
+          es += t.x + t.y;
+          ess = fmaf(t.x, t.x, ess);
+          ess = fmaf(t.y, t.y, ess);
+        }
       }
     }
   }
@@ -355,6 +394,21 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
       a.emit[(size_t)h * a.nslab + slab] = make_float2(s, ss);
     }
   }
+}
+
+inline cudaError_t launch_gn_apply(const GnApplyArgs& a, dim3 grid, int threads, cudaStream_t st) {
+  const int key = (a.silu ? 4 : 0) | (a.pb ? 2 : 0) | (a.res ? 1 : 0);
+  switch (key) {
+    case 0: gn_apply_kernel<false, false, false><<<grid, threads, 0, st>>>(a); break;
+    case 1: gn_apply_kernel<false, false, true><<<grid, threads, 0, st>>>(a); break;
+    case 2: gn_apply_kernel<false, true, false><<<grid, threads, 0, st>>>(a); break;
+    case 3: gn_apply_kernel<false, true, true><<<grid, threads, 0, st>>>(a); break;
+    case 4: gn_apply_kernel<true, false, false><<<grid, threads, 0, st>>>(a); break;
+    case 5: gn_apply_kernel<true, false, true><<<grid, threads, 0, st>>>(a); break;
+    case 6: gn_apply_kernel<true, true, false><<<grid, threads, 0, st>>>(a); break;
+    default: gn_apply_kernel<true, true, true><<<grid, threads, 0, st>>>(a); break;
+  }
+  return cudaGetLastError();
 }
 
 // ----------------------------------------------------------------------------

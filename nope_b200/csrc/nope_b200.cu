@@ -65,7 +65,7 @@ struct nope_unet {
   int dim = 0, Cl = 0, S0 = 0, rot_dim = 6, cemb = 0, device = 0, num_sms = 148;
   int dims[5] = {0, 0, 0, 0, 0};
   bool finalized = false;
-  int conv_impl = 0;
+  int conv_impl = 2;   // 0: tcgen05 1-CTA tiles, 1: SIMT debug twin, 2: tcgen05 CTA pairs (default)
   int chunk = 256;
   int64_t launches = 0;
 
@@ -525,7 +525,13 @@ struct nope_unet {
     return rc;
   }
 
-  static int gn_nslab(int hw) { return hw >= 1024 ? 8 : (hw >= 256 ? 2 : 1); }
+  // pixel slabs per image for the GroupNorm kernels: as few as keep >= ~4 CTAs per SM in
+  // flight (every CTA pays a fixed statistics prologue), at most 8, and >= 32 pixels each
+  static int gn_nslab(int hw, int n_img) {
+    int ns = 1;
+    while (ns < 8 && hw / (ns * 2) >= 32 && (long long)n_img * ns < 600) ns *= 2;
+    return ns;
+  }
 
   // y = [silu](GN(x)) + pb[:, off:off+C] + res.  Statistics come from `stats`
   // ([img][st_parts][st_noct], see GnApplyArgs); stats == nullptr with N != nullptr runs the
@@ -535,7 +541,7 @@ struct nope_unet {
          int pb_offset, const __half* res, const int* res_map, cudaStream_t st,
          const float2* stats = nullptr, int st_parts = 0, int st_noct = 0, float2* emit = nullptr) {
     const int hw = S * S;
-    const int nslab = gn_nslab(hw);
+    const int nslab = gn_nslab(hw, n_img);
     const int threads = (C / 8) * gn_rows(C);
     NOPE_CHECK(threads <= 1024 && threads % 32 == 0 && threads >= 256 && C % 8 == 0,
                "gn: unsupported channel count");
@@ -559,8 +565,7 @@ struct nope_unet {
     a.res = res; a.res_of = res_map; a.emit = emit;
     a.hw = hw; a.C = C; a.G = N ? N->G : 1; a.nslab = nslab;
     a.silu = silu ? 1 : 0; a.eps = 1e-5f;
-    gn_apply_kernel<<<dim3(nslab, n_img), threads, 0, st>>>(a);
-    NOPE_CUDA(cudaGetLastError());
+    NOPE_CUDA(launch_gn_apply(a, dim3(nslab, n_img), threads, st));
     ++launches;
     return 0;
   }
@@ -604,7 +609,7 @@ struct nope_unet {
   // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418).  x's GroupNorm(1) statistics
   // were emitted into SB by the producer of x; to_out[1]'s come from the to_out conv epilogue.
   int linattn(const std::string& p, const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
-    const int nslab = gn_nslab(S * S);
+    const int nslab = gn_nslab(S * S, n);
     if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB, nslab, 1))
       return -1;
     if (conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
@@ -619,7 +624,7 @@ struct nope_unet {
   // Residual(PreNorm(Attention)) (model_utils.py:367-390)
   int midattn(const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
     NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
-    const int nslab = gn_nslab(S * S);
+    const int nslab = gn_nslab(S * S, n);
     if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB, nslab, 1))
       return -1;
     if (conv(convs.at("mid_attn.qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;

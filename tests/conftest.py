@@ -33,6 +33,6 @@ def gpu_model(seeded_state_dict):
     from nope_b200.model import build_model
     m = build_model(device="cuda:0")
     m.load_state_dict(seeded_state_dict)
-    impl = os.environ.get("NOPE_CONV_IMPL", "tcgen05")   # "simt": bring-up twin on CUDA cores
+    impl = os.environ.get("NOPE_CONV_IMPL", "tcgen05_2cta")   # "simt": bring-up twin on CUDA cores
     m.u_net.set_conv_impl(impl)
     return m.eval()
