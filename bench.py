@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=N_POSES, help="poses per GPU")
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("NOPE_CHUNK", "256")))
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("NOPE_CHUNK", "642")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", default=os.environ.get("NOPE_CONV_IMPL", "tcgen05_2cta"),
                     choices=["tcgen05", "tcgen05_2cta"])

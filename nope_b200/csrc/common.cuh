@@ -209,7 +209,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool bf16) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with the fast divide (MUFU.RCP + FMUL, <= 2 ulp): the IEEE '/' expands to a
+// ~10-instruction Newton sequence, which made the GroupNorm+SiLU pass issue-bound.
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

@@ -475,10 +475,18 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
   }
   __syncthreads();
 
-  // ---- pass B: ctx = exp(k - max)^T v, ksum
-  const int cd = tid >> 3;         // ctx row d owned by this thread
-  const int ce = (tid & 7) * 4;    // 4 consecutive e
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, ks = 0.f;
+  // ---- pass B: ctx = exp(k - max)^T v, ksum.  Each thread owns a 4x4 block of ctx for one
+  // quarter of the tokens (2 x LDS.128 per 16 FMA); the four token quarters are combined in a
+  // fixed order afterwards.
+  const int tq = tid & 63, tp = tid >> 6;
+  const int cd = (tq >> 3) * 4;    // ctx rows d .. d+3
+  const int ce = (tq & 7) * 4;     // ctx cols e .. e+3
+  float c[4][4];
+  float ks[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
   for (int t0 = 0; t0 < n; t0 += kLinAttnTile) {
     const int tn = min(kLinAttnTile, n - t0);
     // stage: thread -> (token, 8-channel octet) for k and v
@@ -488,32 +496,55 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
       const uint4 vv = *reinterpret_cast<const uint4*>(vb + (long long)(t0 + t) * 384 + oc);
       const __half2* hk = reinterpret_cast<const __half2*>(&kv);
       const __half2* hv = reinterpret_cast<const __half2*>(&vv);
+      float ek[8], vf[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 a = __half22float2(hk[q]), b = __half22float2(hv[q]);
-        s_ek[t][oc + 2 * q] = __expf(a.x - s_kmax[oc + 2 * q]);
-        s_ek[t][oc + 2 * q + 1] = __expf(a.y - s_kmax[oc + 2 * q + 1]);
-        s_v[t][oc + 2 * q] = b.x;
-        s_v[t][oc + 2 * q + 1] = b.y;
+        ek[2 * q] = __expf(a.x - s_kmax[oc + 2 * q]);
+        ek[2 * q + 1] = __expf(a.y - s_kmax[oc + 2 * q + 1]);
+        vf[2 * q] = b.x;
+        vf[2 * q + 1] = b.y;
+      }
+      *reinterpret_cast<float4*>(&s_ek[t][oc]) = make_float4(ek[0], ek[1], ek[2], ek[3]);
+      *reinterpret_cast<float4*>(&s_ek[t][oc + 4]) = make_float4(ek[4], ek[5], ek[6], ek[7]);
+      *reinterpret_cast<float4*>(&s_v[t][oc]) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+      *reinterpret_cast<float4*>(&s_v[t][oc + 4]) = make_float4(vf[4], vf[5], vf[6], vf[7]);
+    }
+    __syncthreads();
+    for (int t = tp; t < tn; t += 4) {
+      const float4 e4 = *reinterpret_cast<const float4*>(&s_ek[t][cd]);
+      const float4 v4 = *reinterpret_cast<const float4*>(&s_v[t][ce]);
+      const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
+      const float vv4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ks[i] += ee[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] = fmaf(ee[i], vv4[j], c[i][j]);
       }
     }
     __syncthreads();
-    for (int t = 0; t < tn; ++t) {
-      const float e = s_ek[t][cd];
-      const float4 v4 = *reinterpret_cast<const float4*>(&s_v[t][ce]);
-      c0 = fmaf(e, v4.x, c0);
-      c1 = fmaf(e, v4.y, c1);
-      c2 = fmaf(e, v4.z, c2);
-      c3 = fmaf(e, v4.w, c3);
-      ks += e;
+  }
+  // combine the four token quarters (s_ek is free now: reuse it as [4][32][32] scratch)
+  {
+    float* part = &s_ek[0][0];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(part + (tp * 32 + cd + i) * 32 + ce) =
+          make_float4(c[i][0], c[i][1], c[i][2], c[i][3]);
+    float* pks = &s_v[0][0];                      // [4][32] partial column sums of exp(k)
+    if ((tq & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pks[tp * 32 + cd + i] = ks[i];
     }
     __syncthreads();
-  }
-  if ((tid & 7) == 0) s_ksum[cd] = ks;
-  __syncthreads();
-  {
-    const float inv = 1.0f / s_ksum[cd];
-    *reinterpret_cast<float4*>(&s_ctx[cd][ce]) = make_float4(c0 * inv, c1 * inv, c2 * inv, c3 * inv);
+    if (tid < 32) s_ksum[tid] = (pks[tid] + pks[32 + tid]) + (pks[64 + tid] + pks[96 + tid]);
+    __syncthreads();
+    for (int i = tid; i < 1024; i += kLinAttnThreads) {
+      const int d = i >> 5;
+      const float v = (part[i] + part[1024 + i]) + (part[2048 + i] + part[3072 + i]);
+      s_ctx[d][i & 31] = v / s_ksum[d];
+    }
   }
   __syncthreads();
 

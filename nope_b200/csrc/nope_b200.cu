@@ -66,7 +66,7 @@ struct nope_unet {
   int dims[5] = {0, 0, 0, 0, 0};
   bool finalized = false;
   int conv_impl = 2;   // 0: tcgen05 1-CTA tiles, 1: SIMT debug twin, 2: tcgen05 CTA pairs (default)
-  int chunk = 256;
+  int chunk = 642;
   int64_t launches = 0;
 
   std::map<std::string, HostTensor> host;

@@ -164,7 +164,7 @@ def topk(sim, k, idx_base=0):
     return topv, topi
 
 
-def build_model(u_net_dim=192, descriptor_size=8, device="cuda:0", chunk=256,
+def build_model(u_net_dim=192, descriptor_size=8, device="cuda:0", chunk=642,
                 similarity_metric="l2"):
     """The one configuration the reference resolves: configs/model/template_base.yaml."""
     from .encoder import FeatureExtractor

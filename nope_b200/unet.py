@@ -15,7 +15,7 @@ from . import _lib
 class UNet:
     def __init__(self, u_net_dim, rot_representation_dim, encoder, pose_mlp_name="single_layer",
                  init_dim=None, out_dim=None, use_hard_up_down=True, dim_mults=(1, 2, 4, 8),
-                 resnet_block_groups=8, device="cuda:0", chunk=256, **kwargs):
+                 resnet_block_groups=8, device="cuda:0", chunk=642, **kwargs):
         # only the configuration the reference actually ships resolves to a valid model
         # (configs/model/template_base.yaml)
         if pose_mlp_name != "single_layer":

@@ -11,7 +11,7 @@ from nope_b200.model import build_model
 from nope_b200.poses import synthetic_pose_batch
 
 n = int(os.environ.get("NOPE_POSES", "642"))
-model = build_model(device="cuda:0", chunk=int(os.environ.get("NOPE_CHUNK", "256")))
+model = build_model(device="cuda:0", chunk=int(os.environ.get("NOPE_CHUNK", "642")))
 model.load_state_dict(weights.make_full_state_dict(seed=0)).eval()
 poses, _ = synthetic_pose_batch(n, 1)
 g = torch.Generator().manual_seed(0)
