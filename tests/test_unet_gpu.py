@@ -135,3 +135,55 @@ def test_bad_arguments_raise(gpu_model):
     rf = torch.zeros(1, 8, 32, 32)
     with pytest.raises(NopeError):
         gpu_model.u_net.sweep(rf, torch.zeros(1, 3, 6), query_feat=rf, k=5)   # k > N
+
+
+def test_full_size_grid_properties(gpu_model):
+    """BASELINE configs[1] size (642-pose grid, one query): size-independent properties instead
+    of an oracle run (642 CPU forwards would take minutes):
+      * determinism: the same sweep twice is bit-identical;
+      * pose-permutation equivariance: permuting the grid permutes the scores, bit for bit
+        (every hypothesis is an independent forward, whatever tile / CTA pair it lands in);
+      * duplicated poses give identical scores and the top-k tie-break picks the lower index;
+      * chunk-size invariance at a size with ragged last tiles (642 = 5*128 + 2)."""
+    from nope_b200.poses import synthetic_pose_batch
+    g = torch.Generator().manual_seed(7)
+    rf = torch.randn(1, 8, 32, 32, generator=g) * 1.5
+    qf = torch.randn(1, 8, 32, 32, generator=g) * 1.5
+    poses, _ = synthetic_pose_batch(642, 1)
+    u = gpu_model.u_net
+    a = u.sweep(rf, poses, query_feat=qf, want_emb=False, k=5)
+    b = u.sweep(rf, poses, query_feat=qf, want_emb=False, k=5)
+    assert torch.equal(a["sim"], b["sim"]) and torch.equal(a["topi"], b["topi"])
+    perm = torch.randperm(642, generator=g)
+    c = u.sweep(rf, poses[:, perm], query_feat=qf, want_emb=False, k=5)
+    assert torch.equal(c["sim"].cpu(), a["sim"].cpu()[:, perm])
+    assert torch.equal(perm[c["topi"].cpu()[0]], a["topi"].cpu()[0])
+    dup = poses.clone()
+    best = int(a["topi"][0, 0])
+    other = 600 if best != 600 else 601
+    dup[0, other] = dup[0, best]
+    d = u.sweep(rf, dup, query_feat=qf, want_emb=False, k=5)
+    assert d["sim"][0, other] == d["sim"][0, best]
+    assert d["topi"][0, :2].tolist() == sorted([best, other])
+    u.set_chunk(100)
+    e = u.sweep(rf, poses, query_feat=qf, want_emb=False, k=5)
+    u.set_chunk(642)
+    assert torch.equal(e["sim"], a["sim"]) and torch.equal(e["topi"], a["topi"])
+    log("full_grid_642", top5=a["topi"].tolist(), launches=u.last_launch_count)
+
+
+def test_batch_of_queries_is_independent(gpu_model):
+    """configs[2] shape in miniature (B=3 queries x 162-pose grid): each batch row equals the
+    same query run alone (hypotheses of different references never interact)."""
+    from nope_b200.poses import synthetic_pose_batch
+    g = torch.Generator().manual_seed(9)
+    rf = torch.randn(3, 8, 32, 32, generator=g) * 1.5
+    qf = torch.randn(3, 8, 32, 32, generator=g) * 1.5
+    poses, _ = synthetic_pose_batch(162, 3)
+    u = gpu_model.u_net
+    full = u.sweep(rf, poses, query_feat=qf, want_emb=True, k=5)
+    for b in range(3):
+        one = u.sweep(rf[b:b + 1], poses[b:b + 1], query_feat=qf[b:b + 1], want_emb=True, k=5)
+        assert torch.equal(one["sim"][0], full["sim"][b])
+        assert torch.equal(one["topi"][0], full["topi"][b])
+        assert torch.equal(one["emb"][0], full["emb"][b])
