@@ -226,7 +226,8 @@ struct GnApplyArgs {
   const __half* pb;       // per-hypothesis channel bias (added after the activation) or nullptr
   const __half* res;      // residual or nullptr
   const int* res_of;      // hypothesis -> residual image index, nullptr => identity
-  float2* emit;           // optional: per (img, slab) sum / sum of squares of the outputs y
+  float2* emit;           // optional: per (img, fixed sub-slab) sum / sum of squares of y
+  int emit_parts;         // fixed sub-slabs per image (independent of nslab)
   int pb_stride, pb_off;
   int hw, C, G, nslab;
   int silu;
@@ -312,86 +313,95 @@ __global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
       pbv[2 * q + 1] = t.y;
     }
   }
+  // The CTA covers pixel slab `slab` of nslab; statistics are emitted per FIXED sub-slab
+  // (a.emit_parts per image, independent of nslab) and every sub-slab is reduced with the same
+  // thread->pixel assignment and the same tree, so the emitted sums -- and everything
+  // downstream -- do not depend on how many images share the launch.
   const int pps = a.hw / a.nslab;
+  const int nsub = a.emit ? a.emit_parts / a.nslab : 1;   // fixed sub-slabs handled by this CTA
+  const int spp = pps / nsub;                             // pixels per sub-slab
   const __half* xp = a.x + ((long long)h * a.hw + (long long)slab * pps) * a.C + o * 8;
   __half* yp = a.y + ((long long)h * a.hw + (long long)slab * pps) * a.C + o * 8;
   const __half* rp = nullptr;
   if (RES)
     rp = a.res + ((long long)(a.res_of ? a.res_of[h] : h) * a.hw + (long long)slab * pps) * a.C + o * 8;
-  float es = 0.f, ess = 0.f;
-  for (int p0 = r; p0 < pps; p0 += rows * kGnUnroll) {
-    uint4 xv[kGnUnroll], rv[kGnUnroll];
+  for (int sub = 0; sub < nsub; ++sub) {
+    float es = 0.f, ess = 0.f;
+    const int pbeg = sub * spp, pend = pbeg + spp;
+    for (int p0 = pbeg + r; p0 < pend; p0 += rows * kGnUnroll) {
+      uint4 xv[kGnUnroll], rv[kGnUnroll];
 #pragma unroll
-    for (int u = 0; u < kGnUnroll; ++u) {
-      const int p = p0 + u * rows;
-      if (p < pps) {
-        xv[u] = ld_stream16(xp + (long long)p * a.C);
-        if (RES) rv[u] = ld_stream16(rp + (long long)p * a.C);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kGnUnroll; ++u) {
-      const int p = p0 + u * rows;
-      if (p >= pps) break;
-      const __half2* hv = reinterpret_cast<const __half2*>(&xv[u]);
-      float f[8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 t = __half22float2(hv[q]);
-        f[2 * q] = t.x;
-        f[2 * q + 1] = t.y;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float t = fmaf(f[i], scale[i], shift[i]);
-        if (SILU) t = silu_f(t);
-        if (PB) t += pbv[i];
-        f[i] = t;
-      }
-      if (RES) {
-        const __half2* hr = reinterpret_cast<const __half2*>(&rv[u]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 t = __half22float2(hr[q]);
-          f[2 * q] += t.x;
-          f[2 * q + 1] += t.y;
+      for (int u = 0; u < kGnUnroll; ++u) {
+        const int p = p0 + u * rows;
+        if (p < pend) {
+          xv[u] = ld_stream16(xp + (long long)p * a.C);
+          if (RES) rv[u] = ld_stream16(rp + (long long)p * a.C);
         }
       }
-      uint4 w;
-      w.x = pack_half2(f[0], f[1]);
-      w.y = pack_half2(f[2], f[3]);
-      w.z = pack_half2(f[4], f[5]);
-      w.w = pack_half2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(yp + (long long)p * a.C) = w;
-      if (a.emit) {
-        // statistics of the values as stored (fp16-rounded), what the consumer will read
-        const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+      for (int u = 0; u < kGnUnroll; ++u) {
+        const int p = p0 + u * rows;
+        if (p >= pend) break;
+        const __half2* hv = reinterpret_cast<const __half2*>(&xv[u]);
+        float f[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 t = __half22float2(hw2[q]);
-          es += t.x + t.y;
-          ess = fmaf(t.x, t.x, ess);
-          ess = fmaf(t.y, t.y, ess);
+          const float2 t = __half22float2(hv[q]);
+          f[2 * q] = t.x;
+          f[2 * q + 1] = t.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = fmaf(f[i], scale[i], shift[i]);
+          if (SILU) t = silu_f(t);
+          if (PB) t += pbv[i];
+          f[i] = t;
+        }
+        if (RES) {
+          const __half2* hr = reinterpret_cast<const __half2*>(&rv[u]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 t = __half22float2(hr[q]);
+            f[2 * q] += t.x;
+            f[2 * q + 1] += t.y;
+          }
+        }
+        uint4 w;
+        w.x = pack_half2(f[0], f[1]);
+        w.y = pack_half2(f[2], f[3]);
+        w.z = pack_half2(f[4], f[5]);
+        w.w = pack_half2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(yp + (long long)p * a.C) = w;
+        if (a.emit) {
+          // statistics of the values as stored (fp16-rounded), what the consumer will read
+          const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 t = __half22float2(hw2[q]);
+            es += t.x + t.y;
+            ess = fmaf(t.x, t.x, ess);
+            ess = fmaf(t.y, t.y, ess);
+          }
         }
       }
     }
-  }
-  if (a.emit) {
-    __syncthreads();   // s_red reuse
+    if (a.emit) {
+      __syncthreads();   // s_red reuse
 #pragma unroll
-    for (int off2 = 16; off2 > 0; off2 >>= 1) {
-      es += __shfl_xor_sync(0xffffffffu, es, off2);
-      ess += __shfl_xor_sync(0xffffffffu, ess, off2);
-    }
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = make_float2(es, ess);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float s = 0.f, ss = 0.f;
-      for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) {
-        s += s_red[i].x;
-        ss += s_red[i].y;
+      for (int off2 = 16; off2 > 0; off2 >>= 1) {
+        es += __shfl_xor_sync(0xffffffffu, es, off2);
+        ess += __shfl_xor_sync(0xffffffffu, ess, off2);
       }
-      a.emit[(size_t)h * a.nslab + slab] = make_float2(s, ss);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = make_float2(es, ess);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float s = 0.f, ss = 0.f;
+        for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) {
+          s += s_red[i].x;
+          ss += s_red[i].y;
+        }
+        a.emit[(size_t)h * a.emit_parts + slab * nsub + sub] = make_float2(s, ss);
+      }
     }
   }
 }

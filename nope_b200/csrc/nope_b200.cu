@@ -562,7 +562,7 @@ struct nope_unet {
     a.x = x; a.y = y; a.stats = N ? stats : nullptr; a.st_parts = st_parts; a.st_noct = st_noct;
     a.gamma = N ? N->gamma : nullptr; a.beta = N ? N->beta : nullptr;
     a.pb = pb_offset >= 0 ? pb : nullptr; a.pb_stride = P; a.pb_off = pb_offset >= 0 ? pb_offset : 0;
-    a.res = res; a.res_of = res_map; a.emit = emit;
+    a.res = res; a.res_of = res_map; a.emit = emit; a.emit_parts = emit_parts_of(hw);
     a.hw = hw; a.C = C; a.G = N ? N->G : 1; a.nslab = nslab;
     a.silu = silu ? 1 : 0; a.eps = 1e-5f;
     NOPE_CUDA(launch_gn_apply(a, dim3(nslab, n_img), threads, st));
@@ -570,6 +570,9 @@ struct nope_unet {
     return 0;
   }
   static int st_parts_of(int S) { return S * S < 32 ? 1 : S * S / 32; }
+  // fixed number of sub-slabs per image for statistics emitted by gn_apply (<= 8, >= 32 pixels
+  // each): independent of the number of images, so results do not depend on chunk / shard size
+  static int emit_parts_of(int hw) { return hw >= 256 ? 8 : (hw >= 32 ? hw / 32 : 1); }
 
   int tap(const char* name, const __half* buf, int C, int S, int n, cudaStream_t st) {
     if (tap_out == nullptr || tap_name != name || tap_hit) return 0;
@@ -609,8 +612,8 @@ struct nope_unet {
   // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418).  x's GroupNorm(1) statistics
   // were emitted into SB by the producer of x; to_out[1]'s come from the to_out conv epilogue.
   int linattn(const std::string& p, const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
-    const int nslab = gn_nslab(S * S, n);
-    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB, nslab, 1))
+    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
+           emit_parts_of(S * S), 1))
       return -1;
     if (conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
     linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD, TC, S * S);
@@ -624,8 +627,8 @@ struct nope_unet {
   // Residual(PreNorm(Attention)) (model_utils.py:367-390)
   int midattn(const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
     NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
-    const int nslab = gn_nslab(S * S, n);
-    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB, nslab, 1))
+    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
+           emit_parts_of(S * S), 1))
       return -1;
     if (conv(convs.at("mid_attn.qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
     midattn_kernel<<<n, 128, 0, st>>>(TD, TC, S * S);

@@ -187,3 +187,21 @@ def test_batch_of_queries_is_independent(gpu_model):
         assert torch.equal(one["sim"][0], full["sim"][b])
         assert torch.equal(one["topi"][0], full["topi"][b])
         assert torch.equal(one["emb"][0], full["emb"][b])
+
+
+def test_shard_size_invariance(gpu_model):
+    """What the multi-GPU path relies on: sweeping a slice of the pose grid gives bit-identical
+    scores to the same poses inside the full sweep, for any slice size (the launch size changes
+    tile composition and CTA counts, never a reduction order)."""
+    from nope_b200.poses import synthetic_pose_batch
+    g = torch.Generator().manual_seed(11)
+    rf = torch.randn(2, 8, 32, 32, generator=g) * 1.5
+    qf = torch.randn(2, 8, 32, 32, generator=g) * 1.5
+    poses, _ = synthetic_pose_batch(162, 2)
+    u = gpu_model.u_net
+    full = u.sweep(rf, poses, query_feat=qf, want_emb=False, k=5)
+    for lo, hi in [(0, 81), (81, 162), (0, 1), (5, 162), (100, 103)]:
+        part = u.sweep(rf, poses[:, lo:hi].contiguous(), query_feat=qf, want_emb=False,
+                       k=min(5, hi - lo), idx_base=lo)
+        assert torch.equal(part["sim"], full["sim"][:, lo:hi]), (lo, hi)
+        assert int(part["topi"].min()) >= lo and int(part["topi"].max()) < hi
