@@ -93,6 +93,23 @@ int nope_unet_profile(nope_unet_t* u, int enable);
 int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops,
                            int64_t* conv_launches, double* max_launch_tflops);
 
+/* ---- template encoder ----------------------------------------------------------------
+ * FeatureExtractor.encode_image (src/model/encoder/template.py:47-53): ResNet-50 without
+ * max-pool and with layer4 at stride 1 (src/model/encoder/resnet.py:93-152), eval-mode
+ * BatchNorm folded into the convolutions, projector ReLU-1x1-ReLU-1x1, normalize=False.
+ * Runs on the tcgen05 convolution kernel with split-precision (fp16 hi+lo) operands, so the
+ * latents match the reference's fp32 path to ~1e-6.  Keys are the reference's
+ * `backbone.*` / `projector.*` names (HOST fp32 pointers, shape-checked); 256x256 inputs. */
+typedef struct nope_encoder nope_encoder_t;
+int nope_encoder_create(nope_encoder_t** out, int descriptor_size, int device);
+void nope_encoder_destroy(nope_encoder_t* e);
+int nope_encoder_load_tensor(nope_encoder_t* e, const char* key, const float* data,
+                             const int64_t* shape, int ndim);
+int nope_encoder_finalize(nope_encoder_t* e);
+/* images [B, 3, 256, 256] fp32 NCHW (device) -> out [B, D, 32, 32] fp32 NCHW (device). */
+int nope_encoder_encode(nope_encoder_t* e, const float* images, int B, float* out, void* stream);
+int64_t nope_encoder_last_launch_count(const nope_encoder_t* e);
+
 /* Score materialised templates against a query and rank them: the arithmetic of
  * PoseConditional.retrieval (model.py:254-266) after encode_image.
  *   query_feat [B, C, HW] fp32, emb [B, N, C, HW] fp32 -> sim [B, N], topv/topi [B, k]. */

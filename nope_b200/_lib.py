@@ -26,6 +26,12 @@ SIGNATURES = {
     "nope_unet_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "nope_unet_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "nope_encoder_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "nope_encoder_destroy": (None, [C.c_void_p]),
+    "nope_encoder_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_f32p, C.POINTER(C.c_int64), C.c_int]),
+    "nope_encoder_finalize": (C.c_int, [C.c_void_p]),
+    "nope_encoder_encode": (C.c_int, [C.c_void_p, c_f32p, C.c_int, c_f32p, C.c_void_p]),
+    "nope_encoder_last_launch_count": (C.c_int64, [C.c_void_p]),
     "nope_score_topk": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, c_f32p, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
     "nope_topk": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_i64p, C.c_int64, C.c_void_p]),

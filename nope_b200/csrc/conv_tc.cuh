@@ -32,7 +32,8 @@ namespace nope {
 
 constexpr int kBM = 128;         // pixels per tile (UMMA M)
 constexpr int kBK = 64;          // channels per K-step (one 128-byte swizzle row)
-constexpr int kMaxSeg = 18;      // 9 taps x 2 sources
+constexpr int kMaxSeg = 32;      // 9 taps x 2 sources, or 9 taps x 3 split-precision products
+constexpr int kMaxAMaps = 8;     // 4 stride-2 lattices x (hi, lo)
 constexpr int kConvThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 
@@ -43,7 +44,8 @@ struct ConvSeg {
 };
 
 struct ConvParams {
-  CUtensorMap amap[4];
+  CUtensorMap amap[kMaxAMaps];
+  int n_amaps;
   CUtensorMap bmap;
   CUtensorMap bmap_half;  // box of BN/2 weight rows: the 2-CTA kernel (conv_tc2.cuh)
   CUtensorMap omap[4];  // one per output parity class when n_par == 4, else omap[0]
@@ -54,6 +56,14 @@ struct ConvParams {
   // stores through omap[parity] (the stride-2 sub-lattice of the 2H x 2W output).
   int n_par;          // 1 or 4
   int n_tiles_par;    // channel tiles per parity (== n_tiles when n_par == 1)
+  // Optional epilogue extras (template encoder: folded BatchNorm = bias, ReLU, residual add and
+  // fp32-accurate activations stored as an fp16 (hi, lo) pair).  All [pixel][n_total] row-major;
+  // not available together with n_par == 4.
+  int relu;
+  const __half* res_hi;   // residual, high halves (nullptr: none)
+  const __half* res_lo;   // residual, low halves (nullptr: residual is a single fp16 tensor)
+  __half* out_lo;         // low halves of the output (omap receives the high halves)
+  float* out_f32;         // fp32 output instead of the fp16 TMA store
   // optional GroupNorm partial statistics of the fp32 outputs (bias included), written
   // deterministically as stats[(img * parts + part) * n_oct + octet] = (sum, sum of squares)
   // over 32-pixel row segments x 8-channel octets; parts = max(1, H*W/32).
@@ -141,6 +151,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
   const int q = e & 3, hh = e >> 2;
   const int row = q * 32 + lane;
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
+  const bool extras = p.relu || p.res_hi || p.out_lo || p.out_f32;   // warp-uniform
+  const int grow = m_tile * kBM + row;                                // linear pixel index
+  const bool row_ok = grow < p.m_valid;
   uint32_t va[32], vb[32];
   tmem_ld_32x32(t_row, va);
 #pragma unroll
@@ -164,6 +177,45 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       f[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
       f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z;
       f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
+      if (extras) {
+        const size_t goff = (size_t)grow * p.stats_noct * 8 + n_chan0 + cc * 64 + hh * 32 + j * 8;
+        if (p.res_hi && row_ok) {
+          const uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + goff);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 t = __half22float2(h2[q]);
+            f[2 * q] += t.x;
+            f[2 * q + 1] += t.y;
+          }
+          if (p.res_lo) {
+            const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + goff);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 t = __half22float2(l2[q]);
+              f[2 * q] += t.x;
+              f[2 * q + 1] += t.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.out_f32 && row_ok) {
+          *reinterpret_cast<float4*>(p.out_f32 + goff) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(p.out_f32 + goff + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        if (p.out_lo && row_ok) {
+          float l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) l[i] = f[i] - __half2float(__float2half_rn(f[i]));
+          *reinterpret_cast<uint4*>(p.out_lo + goff) =
+              make_uint4(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]),
+                         pack_half2(l[6], l[7]));
+        }
+      }
       float s = (f[0] + f[1]) + (f[2] + f[3]) + ((f[4] + f[5]) + (f[6] + f[7]));
       float q2 = f[0] * f[0];
 #pragma unroll
@@ -216,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 4; ++i) prefetch_tmap(&p.amap[i]);
+    for (int i = 0; i < p.n_amaps; ++i) prefetch_tmap(&p.amap[i]);
     prefetch_tmap(&p.bmap);
     for (int i = 0; i < p.n_par; ++i) prefetch_tmap(&p.omap[i]);
   }

@@ -139,7 +139,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   const int tile0 = cluster_id_x(), tile_step = num_clusters_x();
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 4; ++i) prefetch_tmap(&p.amap[i]);
+    for (int i = 0; i < p.n_amaps; ++i) prefetch_tmap(&p.amap[i]);
     prefetch_tmap(&p.bmap_half);
     for (int i = 0; i < p.n_par; ++i) prefetch_tmap(&p.omap[i]);
   }

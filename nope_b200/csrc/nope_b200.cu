@@ -18,6 +18,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "kernels.cuh"
+#include "encoder.cuh"
 
 using namespace nope;
 
@@ -440,6 +441,7 @@ struct nope_unet {
     const CUtensorMap* m = nullptr;
     int nseg = 0, ksteps = 0;
     p.n_par = 1;
+    p.n_amaps = 4;
     if (L.mode == 3) {
       // So is the OUTPUT side (2x the source side); tiles and input maps use the source geometry
       NOPE_CHECK(in1 == nullptr && So % 2 == 0, "upsample conv takes one source");
@@ -971,6 +973,61 @@ int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_top
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// template encoder
+// ---------------------------------------------------------------------------------
+int nope_encoder_create(nope_encoder_t** out, int descriptor_size, int device) {
+  NOPE_CHECK(out != nullptr, "null out pointer");
+  NOPE_CHECK(descriptor_size >= 1 && descriptor_size <= 64, "descriptor_size must be in [1, 64]");
+  int ndev = 0;
+  NOPE_CUDA(cudaGetDeviceCount(&ndev));
+  NOPE_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+  cudaDeviceProp prop;
+  NOPE_CUDA(cudaGetDeviceProperties(&prop, device));
+  NOPE_CHECK(prop.major == 10, "nope_b200 kernels are built for sm_100a only");
+  auto e = std::make_unique<nope_encoder>();
+  e->D = descriptor_size;
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  e->build_schema();
+  *out = e.release();
+  return 0;
+}
+
+void nope_encoder_destroy(nope_encoder_t* e) { delete e; }
+
+int nope_encoder_load_tensor(nope_encoder_t* e, const char* key, const float* data, const int64_t* shape,
+                             int ndim) {
+  NOPE_CHECK(e && key && data && shape, "null argument");
+  NOPE_CHECK(!e->finalized, "encoder already finalized");
+  auto it = e->expected.find(key);
+  NOPE_CHECK(it != e->expected.end(), std::string("unexpected encoder state_dict key: ") + key);
+  NOPE_CHECK((int)it->second.size() == ndim, std::string("rank mismatch for ") + key);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    NOPE_CHECK(it->second[i] == shape[i], std::string("shape mismatch for ") + key);
+    n *= (size_t)shape[i];
+  }
+  auto& slot = e->host[key];
+  slot.first.assign(shape, shape + ndim);
+  slot.second.assign(data, data + n);
+  return 0;
+}
+
+int nope_encoder_finalize(nope_encoder_t* e) {
+  NOPE_CHECK(e, "null encoder");
+  return e->finalize();
+}
+
+int nope_encoder_encode(nope_encoder_t* e, const float* images, int B, float* out, void* stream) {
+  NOPE_CHECK(e && e->finalized, "encoder not finalized");
+  NOPE_CHECK(images && out && B >= 1 && B <= 64, "bad arguments");
+  NOPE_CUDA(cudaSetDevice(e->device));
+  return e->encode(images, B, out, static_cast<cudaStream_t>(stream));
+}
+
+int64_t nope_encoder_last_launch_count(const nope_encoder_t* e) { return e ? e->launches : 0; }
 
 // ---------------------------------------------------------------------------------
 // per-op entry points

@@ -205,3 +205,28 @@ def test_shard_size_invariance(gpu_model):
                        k=min(5, hi - lo), idx_base=lo)
         assert torch.equal(part["sim"], full["sim"][:, lo:hi]), (lo, hi)
         assert int(part["topi"].min()) >= lo and int(part["topi"].max()) < hi
+
+
+def test_native_encoder_matches_oracle_and_torch(gpu_model, seeded_state_dict):
+    """template encoder on the tcgen05 kernel with split-precision operands
+    vs the oracle's torch-CPU fp32 restatement and vs the cuDNN fp32 module: fp32-level parity
+    (the latents feed the score directly; TF32 / fp16 would be 2-3e-3 off)."""
+    from oracle import inputs, unet_oracle as orc
+    from nope_b200.encoder import FeatureExtractor
+    enc_sd = {k[len("encoder."):]: v for k, v in seeded_state_dict.items() if k.startswith("encoder.")}
+    q, r = inputs.make_images(seed=5, batch=2)
+    x = torch.cat([q, r])[:3]                       # batch 3: odd tile counts at every level
+    with torch.no_grad():
+        ref = orc.encode_image(enc_sd, x)
+    enc = gpu_model.u_net.encoder
+    assert enc.backend in ("auto", "b200")
+    got = enc.encode_image(x)
+    e = rel_l2(got, ref)
+    m = max_rel(got, ref)
+    fe_t = FeatureExtractor(descriptor_size=8, backend="torch").cuda()
+    fe_t.load_state_dict({k: v for k, v in enc_sd.items()
+                          if k.startswith("backbone.") or k.startswith("projector.")})
+    e_t = rel_l2(fe_t.encode_image(x), ref)
+    log("native_encoder", rel_l2=e, max_rel=m, cudnn_fp32_rel_l2=e_t)
+    assert e < 2e-5 and m < 1e-4
+    assert torch.equal(enc.encode_image(x), got)    # deterministic
