@@ -48,7 +48,32 @@ def write_pose_grids():
     return {k: v.shape[0] for k, v in out.items()}
 
 
+def write_geodesic_fixture():
+    """tests/golden/geodesic.npz: the reference's GeodesicError (src/model/loss.py:74-115) on
+    seeded random rotations with all three symmetry classes.  pytorch3d is absent, so its
+    so3_relative_angle is the restatement in oracle/ref_import.py: this pins the reference's OWN
+    symmetry / top-k logic, not pytorch3d's acos extrapolation near 0 and 180 degrees."""
+    ref = import_reference()
+    from src.model.loss import GeodesicError
+    g = torch.Generator().manual_seed(4)
+    q = torch.randn(24 * 5 + 24, 4, generator=g, dtype=torch.float64)
+    R = ref.rotation_conversions.quaternion_to_matrix(q / q.norm(dim=1, keepdim=True))
+    predR, gtR = R[:120].reshape(24, 5, 3, 3), R[120:]
+    sym = torch.tensor([0, 1, 2] * 8, dtype=torch.float32)
+    out = {"predR": predR.numpy(), "gtR": gtR.numpy(), "symmetry": sym.numpy()}
+    for name, s in (("sym0", torch.zeros(24)), ("mixed", sym)):
+        err, res = GeodesicError()(predR.clone(), gtR.clone(), s)
+        out[f"{name}_err"] = err.double().numpy()
+        for k, v in res.items():
+            out[f"{name}|{k}"] = np.array(float(v))
+    np.savez_compressed(os.path.join(OUT, "geodesic.npz"), **out)
+    return {k: float(v) for k, v in out.items() if "|" in k}
+
+
 def main():
+    if "--only-geodesic" in sys.argv:
+        print(json.dumps(write_geodesic_fixture(), indent=1))
+        return
     torch.set_num_threads(os.cpu_count())
     os.makedirs(OUT, exist_ok=True)
     meta = {"torch": torch.__version__, "reference_root": REFERENCE_ROOT}
@@ -134,6 +159,7 @@ def main():
             emb_b0_n0=emb2[0, 0].numpy(), emb_b1_n25=emb2[1, 25].numpy(),
             template_poses=tposes2.numpy())
 
+    meta["geodesic"] = write_geodesic_fixture()
     meta["oracle_vs_reference_rel_err"] = errs
     print(json.dumps(meta, indent=1))
     for k, v in errs.items():

@@ -112,3 +112,42 @@ def test_encoder_module_matches_oracle(sds):
     q, _ = inputs.make_images(seed=3, batch=1)
     with torch.no_grad():
         assert rel(fe.encode_image(q), orc.encode_image(enc, q)) < 1e-5
+
+
+def test_geodesic_metric_properties():
+    """nope_b200.metrics (restated loss.py:14-115): known angles, symmetry handling, top-k keys."""
+    import math
+    from nope_b200.metrics import GeodesicError, so3_relative_angle_with_symmetry
+
+    def rot(axis, deg):
+        a = math.radians(deg)
+        c, s = math.cos(a), math.sin(a)
+        m = {"x": [[1, 0, 0], [0, c, -s], [0, s, c]], "y": [[c, 0, s], [0, 1, 0], [-s, 0, c]],
+             "z": [[c, -s, 0], [s, c, 0], [0, 0, 1]]}[axis]
+        return torch.tensor(m, dtype=torch.float64)
+    gt = torch.stack([torch.eye(3, dtype=torch.float64)] * 3)
+    pred = torch.stack([rot("x", 30), rot("y", 180), rot("z", 40)])
+    e0 = torch.rad2deg(so3_relative_angle_with_symmetry(pred, gt, torch.zeros(3)))
+    assert torch.allclose(e0, torch.tensor([30.0, 180.0, 40.0], dtype=torch.float64), atol=1.0)
+    e1 = torch.rad2deg(so3_relative_angle_with_symmetry(pred, gt, torch.ones(3)))
+    assert e1[1] < 1.0 and abs(float(e1[0]) - 30.0) < 1.0           # Y-180 symmetric object
+    e2 = torch.rad2deg(so3_relative_angle_with_symmetry(pred, gt, torch.full((3,), 2.0)))
+    assert e2[2] < 1.0                                              # in-plane rotation ignored
+    predk = torch.stack([pred, pred.flip(0), gt, gt, gt], dim=1)    # [3, 5, 3, 3]
+    err, res = GeodesicError()(predk, gt, torch.zeros(3))
+    assert set(res) == {"top1, accuracy_15", "top1, median", "top3, accuracy_15", "top3, median",
+                        "top5, accuracy_15", "top5, median"}
+    assert float(res["top3, accuracy_15"]) == 100.0 and float(res["top1, accuracy_15"]) == 0.0
+
+
+def test_geodesic_metric_against_reference_fixture(golden_dir):
+    """nope_b200.metrics.GeodesicError == the reference's GeodesicError (loss.py:74-115) on the
+    fixture oracle/make_golden.py generated from the unmodified reference module."""
+    from nope_b200.metrics import GeodesicError
+    g = np.load(os.path.join(golden_dir, "geodesic.npz"))
+    predR, gtR = torch.from_numpy(g["predR"]), torch.from_numpy(g["gtR"])
+    for name, sym in (("sym0", torch.zeros(24)), ("mixed", torch.from_numpy(g["symmetry"]))):
+        err, res = GeodesicError()(predR, gtR, sym)
+        assert np.allclose(err.numpy(), g[f"{name}_err"], atol=2e-3), name   # degrees (ref is fp32)
+        for k, v in res.items():
+            assert abs(float(v) - float(g[f"{name}|{k}"])) < 2e-3, (name, k)
