@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=N_POSES, help="poses per GPU")
+    ap.add_argument("--queries", type=int, default=1, help="queries (batch) per step")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("NOPE_CHUNK", "642")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", default=os.environ.get("NOPE_CONV_IMPL", "tcgen05_2cta"),
@@ -213,8 +214,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"256x256, {N_POSES}-pose icosphere grid, batch=1 query; each step a "
-                               f"{sample}-pose sample of the grid (+2 encoder calls) on host CPU",
+        "config": {"workload": f"configs[1]: 256x256, {N_POSES}-pose icosphere grid per GPU, batch=1 query, "
+                               "fp32 reference modules on the host CPU, l2 score + top-5",
+                   "sample": f"each step = a {sample}-pose sample of the grid + 2 encoder calls",
                    "poses_per_step": sample},
         "cpu_baseline": {"value": v, "unit": "hyp/s", "cores": threads, "kind": kind,
                          "sample": f"{sample} poses + 2 encoder calls per step, {threads} of "
@@ -259,14 +261,15 @@ def main():
         model.dist = ShardedSweep()
 
     # global grid: one icosphere-642 grid per GPU shard (pose VALUES do not affect timing)
-    poses_g, tposes = synthetic_pose_batch(n_local, 1)
-    poses_g = poses_g.repeat(1, world, 1)           # [1, n_global, 6]
+    Q = args.queries
+    poses_g, tposes = synthetic_pose_batch(n_local, Q)
+    poses_g = poses_g.repeat(1, world, 1)           # [Q, n_global, 6]
     g = torch.Generator().manual_seed(0)
-    q_img = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
-    r_img = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    q_img = (torch.rand(Q, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    r_img = (torch.rand(Q, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
     poses_host = poses_g.clone().pin_memory()
     h2d = q_img.numel() * 4 + r_img.numel() * 4 + poses_host.numel() * 4
-    d2h = 5 * 8 + n_global * 4                      # top-5 indices (int64) + similarity row
+    d2h = Q * (5 * 8 + n_global * 4)                # top-5 indices (int64) + similarity rows
 
     # ---- resident inputs for `value`
     q_feat = unet.encoder.encode_image(q_img.to(dev))
@@ -331,15 +334,15 @@ def main():
             dist.destroy_process_group()
         return
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()
-    value = n_global / (ms * 1e-3)
+    value = Q * n_global / (ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
         "config": {
-            "workload": f"configs[1]: 256x256, {n_local}-pose icosphere grid per GPU, batch=1 query, "
+            "workload": f"configs[1]: 256x256, {n_local}-pose icosphere grid per GPU, batch={Q} query, "
                         "fp16 UNet (fp32 accumulate / statistics), l2 score + top-5",
-            "poses_per_gpu": n_local, "global_poses": n_global, "queries": 1, "chunk": args.chunk,
+            "poses_per_gpu": n_local, "global_poses": n_global, "queries": Q, "chunk": args.chunk,
             "conv_impl": args.conv_impl,
             "weights": "seeded random init, reference state_dict schema (305.8 M params)",
             "l2": "not flushed: each step streams 0.61 GB of fp16 weights and ~1.4 GB of "
@@ -347,7 +350,7 @@ def main():
             "parallelism": f"pose grid sharded {world}-way, all-gather of top-k" if world > 1 else "1 GPU",
         },
         "clocks": clocks,
-        "e2e": {"value": n_global / (ms_e2e * 1e-3), "unit": "hyp/s", "ms_per_step": ms_e2e,
+        "e2e": {"value": Q * n_global / (ms_e2e * 1e-3), "unit": "hyp/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "PoseConditional.predict_pose (pinned host images -> encoder x2 -> sweep -> top-5 -> host)"},
         "gpu_launches": int(launches_per_step * args.steps),

@@ -1,5 +1,6 @@
-"""One warm sweep + one sweep inside cudaProfilerStart/Stop, for ncu
-(`ncu --profile-from-start off ...`).  642 poses, 1 query, chunk from NOPE_CHUNK."""
+"""One warm step + one step inside cudaProfilerStart/Stop, for ncu
+(`ncu --profile-from-start off ...`): the public predict_pose path = native encoder (2
+images) + sweep over the pose grid + fused score/top-k.  642 poses, 1 query."""
 import os
 import sys
 
@@ -15,14 +16,14 @@ model = build_model(device="cuda:0", chunk=int(os.environ.get("NOPE_CHUNK", "642
 model.load_state_dict(weights.make_full_state_dict(seed=0)).eval()
 poses, _ = synthetic_pose_batch(n, 1)
 g = torch.Generator().manual_seed(0)
-rf = (torch.randn(1, 8, 32, 32, generator=g) * 1.5).cuda()
-qf = (torch.randn(1, 8, 32, 32, generator=g) * 1.5).cuda()
+q = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).cuda()
+r = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).cuda()
 poses = poses.cuda()
 for _ in range(int(os.environ.get("NOPE_WARM", "1"))):
-    model.u_net.sweep(rf, poses, query_feat=qf, want_emb=False, k=5)
+    model.predict_pose(q, r, poses, None, k=5)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-out = model.u_net.sweep(rf, poses, query_feat=qf, want_emb=False, k=5)
+_, idx, sim = model.predict_pose(q, r, poses, None, k=5)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("top5", out["topi"].tolist(), "launches", model.u_net.last_launch_count)
+print("top5", idx.tolist(), "launches", model.u_net.last_launch_count)
