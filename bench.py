@@ -100,6 +100,18 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the convolution kernel from the committed ncu capture
+    (profiles/roofline_traffic.json, written by tools/summarize_ncu_raw.py), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -358,7 +370,9 @@ def main():
             "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)",
             "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": conv_tf / peak_tf if peak_tf else None, "peak_source": f"{peak_src} (sustained bf16 cuBLAS)",
-            "traffic": None, "launches_per_step": prof["conv_launches"],
+            "traffic": ncu_traffic(), "traffic_source": "profiles/roofline_traffic.json (ncu --set full, "
+            "dram__bytes_read.sum + dram__bytes_write.sum per launch, sweep convolutions)",
+            "launches_per_step": prof["conv_launches"],
             "conv_ms_per_step": prof["conv_ms"], "conv_share_of_step": prof["conv_ms"] / ms if ms else None,
             "algorithmic_tflop_per_step": prof["conv_flops"] / 1e12,
             "best_single_launch_tflops": prof["max_launch_tflops"],

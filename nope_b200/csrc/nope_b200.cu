@@ -54,12 +54,6 @@ struct Act {  // NHWC fp16 activation [n_img, S, S, C]
   int S = 0;  // spatial side
 };
 
-template <typename T>
-int dev_alloc(T** p, size_t n) {
-  NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
-  return 0;
-}
-
 }  // namespace
 
 struct nope_unet {
