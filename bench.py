@@ -166,6 +166,41 @@ def cpu_baseline(seconds=12.0, chunk=16):
                       f"(fastest of a probe), {dt:.1f} s"}
 
 
+def eager_gpu_baseline(dev, chunk=64, reps=3):
+    """the reference ships no custom kernel, so the on-box GPU baseline is the same
+    module in PyTorch eager (cuDNN/cuBLAS), fp16.  /root/reference does not exist on the GPU box:
+    the oracle's torch restatement of UNet.forward runs on CUDA half tensors instead, batched
+    `chunk` hypotheses per forward.  hyp/s (UNet + l2 score only, no encoder)."""
+    import torch
+    from oracle import unet_oracle as orc, weights
+    from nope_b200.poses import synthetic_pose_batch
+    sd = {k: v.to(dev, torch.float16) for k, v in weights.make_unet_state_dict(seed=0).items()}
+    g = torch.Generator().manual_seed(0)
+    rf = (torch.randn(1, 8, 32, 32, generator=g) * 1.5).to(dev, torch.float16)
+    qf = (torch.randn(1, 8, 32, 32, generator=g) * 1.5).to(dev)
+    poses, _ = synthetic_pose_batch(N_POSES, 1)
+    poses = poses.to(dev, torch.float16)
+    x = rf.expand(chunk, -1, -1, -1).contiguous(memory_format=torch.channels_last)
+
+    def run():
+        with torch.no_grad():
+            emb = orc.unet_forward(sd, x, poses[0, :chunk])
+            orc.l2_similarity(qf, emb.float()[None])
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": chunk / (ms * 1e-3), "unit": "hyp/s", "kind": "oracle port, torch-eager CUDA fp16 "
+            "channels_last (cuDNN/cuBLAS)", "sample": f"{chunk} hypotheses per forward, {reps} forwards, "
+            "UNet + l2 score"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path, bounded sample per step."""
     import torch
@@ -346,6 +381,12 @@ def main():
             dist.destroy_process_group()
         return
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()
+    eager = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            eager = eager_gpu_baseline(dev)
+        except Exception as exc:                      # informational leg only
+            eager = {"unavailable": repr(exc)[:200]}
     value = Q * n_global / (ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
@@ -379,6 +420,7 @@ def main():
             "whole_step_tflops": value * GFLOP_PER_HYP / 1e3,
         },
         "cpu_baseline": cpu,
+        "eager_gpu_baseline": eager,
     }
     print(json.dumps(line))
     if world > 1:

@@ -70,7 +70,42 @@ def write_geodesic_fixture():
     return {k: float(v) for k, v in out.items() if "|" in k}
 
 
+def write_full_grid_fixture():
+    """tests/golden/level2_642_b1.npz: BASELINE configs[1] at full size -- the reference's own
+    UNet + encoder modules (batched 16 hypotheses per forward, which model.py:212-222's loop is
+    arithmetically equal to) over the shipped 642-pose level-2 grid, its "l2" similarity
+    (model.py:260-262) and topk(5)."""
+    model = build_reference_model()
+    sd = weights.make_full_state_dict(seed=0)
+    model.u_net.load_state_dict(sd, strict=True)
+    q, r = inputs.make_images(seed=2, batch=1)
+    relR, tposes = inputs.make_pose_batch("level2_all", batch=1)
+    with torch.no_grad():
+        qf = model.u_net.encoder.encode_image(q)
+        rf = model.u_net.encoder.encode_image(r)
+        embs = []
+        t0 = time.time()
+        for s0 in range(0, 642, 16):
+            p = relR[0, s0:s0 + 16]
+            embs.append(model.u_net(rf.expand(p.shape[0], -1, -1, -1), p))
+        emb = torch.cat(embs)[None]
+        d = (qf.unsqueeze(1).repeat(1, 642, 1, 1, 1) - emb) ** 2
+        sim = -torch.norm(d, dim=2).sum(axis=3).sum(axis=2)
+        _, idx = sim.topk(k=5, dim=1)
+        secs = time.time() - t0
+    srt = torch.sort(sim, dim=1, descending=True).values
+    gap = float(((srt[:, :-1] - srt[:, 1:]) / srt[:, :-1].abs())[:, :5].min())
+    np.savez_compressed(os.path.join(OUT, "level2_642_b1.npz"), query_feat=qf.numpy(), ref_feat=rf.numpy(),
+                        all_relativeR=relR.numpy(), similarity=sim.numpy(), nearest_idx=idx.numpy(),
+                        emb_n0=emb[0, 0].numpy(), emb_n641=emb[0, 641].numpy())
+    return {"reference_cpu_seconds": secs, "top5": idx.tolist(), "min_rel_gap_top6": gap}
+
+
 def main():
+    if "--only-full-grid" in sys.argv:
+        torch.set_num_threads(os.cpu_count())
+        print(json.dumps(write_full_grid_fixture(), indent=1))
+        return
     if "--only-geodesic" in sys.argv:
         print(json.dumps(write_geodesic_fixture(), indent=1))
         return
@@ -160,6 +195,7 @@ def main():
             template_poses=tposes2.numpy())
 
     meta["geodesic"] = write_geodesic_fixture()
+    meta["level2_642"] = write_full_grid_fixture()
     meta["oracle_vs_reference_rel_err"] = errs
     print(json.dumps(meta, indent=1))
     for k, v in errs.items():

@@ -232,3 +232,27 @@ def test_native_encoder_matches_oracle_and_torch(gpu_model, seeded_state_dict):
     # A_lo*W_lo term dropped, and the tensor core's non-IEEE fp32 accumulation over K <= 13824
     assert e < 1.5e-4 and m < 3e-4
     assert torch.equal(enc.encode_image(x), got)    # deterministic
+
+
+def test_full_level2_grid_against_reference_golden(gpu_model, golden_dir):
+    """BASELINE configs[1] at full size against the reference itself: 642-pose level-2 grid
+    (the grid the reference ships), one query; fixture = the unmodified reference modules on CPU
+    (tests/golden/level2_642_b1.npz, oracle/make_golden.py --only-full-grid)."""
+    from oracle import inputs
+    g = np.load(f"{golden_dir}/level2_642_b1.npz")
+    poses = torch.from_numpy(g["all_relativeR"])
+    # (a) from the reference's latents: UNet sweep + score only
+    out = gpu_model.u_net.sweep(torch.from_numpy(g["ref_feat"]), poses,
+                                query_feat=torch.from_numpy(g["query_feat"]), want_emb=True, k=5)
+    e_sim = max_rel(out["sim"], torch.from_numpy(g["similarity"]))
+    e0 = rel_l2(out["emb"][0, 0], torch.from_numpy(g["emb_n0"]))
+    e1 = rel_l2(out["emb"][0, 641], torch.from_numpy(g["emb_n641"]))
+    # (b) from the images, through the native encoder and the public predict_pose
+    q, r = inputs.make_images(seed=2, batch=1)
+    _, idx2, sim2 = gpu_model.predict_pose(q, r, poses, None, k=5)
+    e_sim2 = max_rel(sim2, torch.from_numpy(g["similarity"]))
+    log("level2_642_golden", sim_max_rel=e_sim, sim_max_rel_from_images=e_sim2, emb0=e0, emb641=e1,
+        topi=out["topi"].tolist(), topi_from_images=idx2.tolist(), ref=g["nearest_idx"].tolist())
+    assert e_sim < SIM_TOL and e_sim2 < SIM_TOL and max(e0, e1) < EMB_TOL
+    _cmp_ranking(g["similarity"], g["nearest_idx"], out["topi"], SIM_TOL)
+    _cmp_ranking(g["similarity"], g["nearest_idx"], idx2, SIM_TOL)

@@ -3,7 +3,6 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi -L
-echo "== dist check"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tools/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?"; grep -E "rank|DIST_CHECK|Error|error" gpurun_out/dist_check_$N.log | head -20
+nvidia-smi -L | head -8
+echo "== dist check"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tools/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?"; grep -E "DIST_CHECK|Error|error" gpurun_out/dist_check_$N.log | head -5
 echo "== bench N=$N"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_n$N.log
-echo "== reference arm N=$N"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_ref_n$N.log | cut -c1-300
