@@ -70,6 +70,7 @@ struct ConvParams {
   float2* stats;
   int stats_hw;       // H*W of one output image
   int stats_noct;     // n_total / 8
+  int n_total;        // output channels (row stride of res_* / out_lo / out_f32)
   int m_valid;        // n_img * H * W (rows beyond it are padding)
   int nseg;
   int ksteps;         // sum of nchunks
@@ -178,7 +179,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z;
       f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
       if (extras) {
-        const size_t goff = (size_t)grow * p.stats_noct * 8 + n_chan0 + cc * 64 + hh * 32 + j * 8;
+        const size_t goff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
         if (p.res_hi && row_ok) {
           const uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + goff);
           const __half2* h2 = reinterpret_cast<const __half2*>(&rh);

@@ -309,6 +309,7 @@ struct nope_encoder {
     p.stats = nullptr;
     p.stats_hw = Ho * Ho;
     p.stats_noct = L.cout / 8;
+    p.n_total = L.cout;
     p.m_valid = n_img * Ho * Ho;
     p.nseg = nseg;
     p.ksteps = ksteps;

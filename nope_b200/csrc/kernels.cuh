@@ -67,8 +67,8 @@ __global__ void pose_embed_kernel(const float* __restrict__ poses, const float* 
                                   int rot_dim, int cemb) {
   const int h = blockIdx.x;
   if (h >= n_hyp) return;
-  extern __shared__ float sp[];
-  if (threadIdx.x < rot_dim) sp[threadIdx.x] = poses[(long long)h * rot_dim + threadIdx.x];
+  __shared__ float sp[8];      // rot_dim <= 8 (6-D rotations); padded so vectorised reads stay inside
+  if (threadIdx.x < 8) sp[threadIdx.x] = threadIdx.x < rot_dim ? poses[(long long)h * rot_dim + threadIdx.x] : 0.f;
   __syncthreads();
   for (int j = threadIdx.x; j < cemb; j += blockDim.x) {
     float a = b[j];

@@ -493,6 +493,7 @@ struct nope_unet {
     p.stats = stats;
     p.stats_hw = So * So;
     p.stats_noct = L.cout / 8;
+    p.n_total = L.cout;
     p.m_valid = n_img * So * So;
     p.nseg = nseg;
     p.ksteps = ksteps;
@@ -652,7 +653,7 @@ struct nope_unet {
     // hypothesis -> reference image
     iota_div(ref_of, hyp0, N, n, st);
     // pose embedding + all 19 pose projections in one GEMM
-    pose_embed_kernel<<<n, 256, rot_dim * sizeof(float), st>>>(poses + (size_t)hyp0 * rot_dim, pose_w,
+    pose_embed_kernel<<<n, 256, 0, st>>>(poses + (size_t)hyp0 * rot_dim, pose_w,
                                                                pose_b, cs, n, rot_dim, cemb);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
