@@ -62,6 +62,8 @@ struct ConvParams {
   int relu;
   const __half* res_hi;   // residual, high halves (nullptr: none)
   const __half* res_lo;   // residual, low halves (nullptr: residual is a single fp16 tensor)
+  const int* res_map;     // optional: image -> residual image (a per-reference tensor shared by
+  int res_hw;             //   all hypotheses of that reference); res_hw = pixels per image
   __half* out_lo;         // low halves of the output (omap receives the high halves)
   float* out_f32;         // fp32 output instead of the fp16 TMA store
   // optional GroupNorm partial statistics of the fp32 outputs (bias included), written
@@ -155,6 +157,11 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
   const bool extras = p.relu || p.res_hi || p.out_lo || p.out_f32;   // warp-uniform
   const int grow = m_tile * kBM + row;                                // linear pixel index
   const bool row_ok = grow < p.m_valid;
+  int rrow = grow;                                                    // residual row
+  if (p.res_map && row_ok) {
+    const int img = grow / p.res_hw;
+    rrow = p.res_map[img] * p.res_hw + (grow - img * p.res_hw);
+  }
   uint32_t va[32], vb[32];
   tmem_ld_32x32(t_row, va);
 #pragma unroll
@@ -181,7 +188,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       if (extras) {
         const size_t goff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
         if (p.res_hi && row_ok) {
-          const uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + goff);
+          const size_t roff = (size_t)rrow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
+          const uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + roff);
           const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -190,7 +198,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
             f[2 * q + 1] += t.y;
           }
           if (p.res_lo) {
-            const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + goff);
+            const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + roff);
             const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {

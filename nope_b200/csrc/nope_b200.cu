@@ -24,6 +24,15 @@ using namespace nope;
 
 namespace {
 
+// optional epilogue extras of one convolution launch (see ConvParams)
+struct ConvExtras {
+  const __half* res_hi = nullptr;
+  const __half* res_lo = nullptr;
+  const int* res_map = nullptr;
+  int res_hw = 0;
+  __half* out_lo = nullptr;
+};
+
 constexpr int kAbiVersion = 1;
 constexpr int kHeadsHidden = 128;  // 4 heads x 32 (model_utils.py:368,394)
 
@@ -82,6 +91,7 @@ struct nope_unet {
   __half *TA = nullptr, *TB = nullptr, *TC = nullptr, *TD = nullptr, *XA = nullptr, *XB = nullptr,
          *RB = nullptr, *cs = nullptr, *pb = nullptr;
   __half *x0 = nullptr, *g1 = nullptr, *pt = nullptr;  // per-reference pre-stage
+  __half *rc1h = nullptr, *rc1l = nullptr, *rc2h = nullptr, *rc2l = nullptr;  // r halves of final_res_block
   float2* gn_partial = nullptr;   // gn_stats_kernel output (per-op test path only)
   float2 *SA = nullptr, *SB = nullptr;   // fused statistics: conv epilogue / gn_apply emit
   int* ref_of = nullptr;
@@ -198,6 +208,22 @@ struct nope_unet {
     owned.push_back(*out);
     NOPE_CUDA(cudaMemcpy(*out, it->second.data.data(), it->second.data.size() * sizeof(float),
                          cudaMemcpyHostToDevice));
+    return 0;
+  }
+  // host[dst] = host[src][:, lo:hi, :, :]
+  int slice_cin(const std::string& src, const std::string& dst, int lo, int hi) {
+    auto it = host.find(src);
+    NOPE_CHECK(it != host.end(), "missing tensor " + src);
+    const auto& sh = it->second.shape;
+    const int cout = (int)sh[0], cin = (int)sh[1], taps = (int)(sh[2] * sh[3]);
+    NOPE_CHECK(lo >= 0 && hi <= cin && lo < hi, "slice_cin: bad range");
+    HostTensor t;
+    t.shape = {cout, hi - lo, sh[2], sh[3]};
+    t.data.resize((size_t)cout * (hi - lo) * taps);
+    for (int o = 0; o < cout; ++o)
+      std::memcpy(&t.data[(size_t)o * (hi - lo) * taps], &it->second.data[((size_t)o * cin + lo) * taps],
+                  sizeof(float) * (size_t)(hi - lo) * taps);
+    host[dst] = std::move(t);
     return 0;
   }
   // pack one conv weight (+ bias) into a ConvLayer.  mode 3 (nearest-x2 upsample + conv3x3,
@@ -339,6 +365,19 @@ struct nope_unet {
       }
     }
     if (make_resblock("final_res_block") || make_resblock("final_conv.0")) return -1;
+    // final_res_block sees cat(x, r) (u_net.py:194-195) with r = init_conv(reference) shared by
+    // every hypothesis of a reference: split its two convs over cat() along Cin so the r halves
+    // run once per reference (prestage) and enter the per-hypothesis convs as a residual.
+    if (slice_cin("final_res_block.block1.proj.weight", "__frb.b1x", 0, dim) ||
+        slice_cin("final_res_block.block1.proj.weight", "__frb.b1r", dim, 2 * dim) ||
+        slice_cin("final_res_block.res_conv.weight", "__frb.rx", 0, dim) ||
+        slice_cin("final_res_block.res_conv.weight", "__frb.rr", dim, 2 * dim))
+      return -1;
+    if (make_conv("final_res_block.block1x", "__frb.b1x", "final_res_block.block1.proj.bias", 0) ||
+        make_conv("final_res_block.block1r", "__frb.b1r", "", 0) ||
+        make_conv("final_res_block.resx", "__frb.rx", "final_res_block.res_conv.bias", 1) ||
+        make_conv("final_res_block.resr", "__frb.rr", "", 1))
+      return -1;
     if (make_poseproj()) return -1;
     host.clear();
     finalized = true;
@@ -376,7 +415,9 @@ struct nope_unet {
       return -1;
     const size_t r = (size_t)cap_ref;
     if (ws_alloc_half(&x0, r * big / 2) || ws_alloc_half(&g1, r * big / 2) ||
-        ws_alloc_half(&pt, r * big / 2))
+        ws_alloc_half(&pt, r * big / 2) || ws_alloc_half(&rc1h, r * big / 2) ||
+        ws_alloc_half(&rc1l, r * big / 2) || ws_alloc_half(&rc2h, r * big / 2) ||
+        ws_alloc_half(&rc2l, r * big / 2))
       return -1;
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&gn_partial),
                          (size_t)std::max(cap, cap_ref) * 8 * 8 * sizeof(float2)));
@@ -410,9 +451,11 @@ struct nope_unet {
   // ------------------------------------------------------------------ op launchers
   // out[n_img, So, So, cout] = conv(L, in0 (++ in1))
   int conv(const ConvLayer& L, const __half* in0, int c0, const __half* in1, int c1, __half* out,
-           int So, int n_img, int cap_img, cudaStream_t st, float2* stats = nullptr) {
+           int So, int n_img, int cap_img, cudaStream_t st, float2* stats = nullptr,
+           const ConvExtras* ex = nullptr) {
     NOPE_CHECK(c0 + c1 == L.cin, "conv: channel mismatch");
     ++launches;
+    NOPE_CHECK(!(ex && (conv_impl == 1 || L.mode == 3)), "conv extras need the tcgen05 kernel, n_par == 1");
     if (conv_impl == 1) {
       SimtConvArgs a;
       a.src0 = in0; a.src1 = in1; a.C0 = c0; a.C1 = c1; a.w = L.w; a.bias = L.bias; a.out = out;
@@ -495,6 +538,10 @@ struct nope_unet {
     p.stats_noct = L.cout / 8;
     p.n_total = L.cout;
     p.m_valid = n_img * So * So;
+    if (ex) {
+      p.res_hi = ex->res_hi; p.res_lo = ex->res_lo; p.res_map = ex->res_map; p.res_hw = ex->res_hw;
+      p.out_lo = ex->out_lo;
+    }
     p.nseg = nseg;
     p.ksteps = ksteps;
     p.m_tiles = geom_m_tiles(g, n_img);
@@ -643,8 +690,21 @@ struct nope_unet {
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     if (conv(convs.at("downs.0.0.block1"), x0, dim, nullptr, 0, pt, S0, B, cap_ref, st, SA)) return -1;
-    return gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st, SA,
-              st_parts_of(S0), dim / 8);
+    if (gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st, SA,
+           st_parts_of(S0), dim / 8))
+      return -1;
+    if (conv_impl != 1) {
+      // r halves of final_res_block's convs over cat(x, r), kept as fp16 (hi, lo) pairs so the
+      // later fp32 add in the per-hypothesis epilogue loses nothing
+      ConvExtras e1, e2;
+      e1.out_lo = rc1l;
+      e2.out_lo = rc2l;
+      if (conv(convs.at("final_res_block.block1r"), x0, dim, nullptr, 0, rc1h, S0, B, cap_ref, st, nullptr, &e1))
+        return -1;
+      if (conv(convs.at("final_res_block.resr"), x0, dim, nullptr, 0, rc2h, S0, B, cap_ref, st, nullptr, &e2))
+        return -1;
+    }
+    return 0;
   }
 
   // UNet.forward for hypotheses [hyp0, hyp0 + n) of the flattened (b, pose) list
@@ -661,13 +721,17 @@ struct nope_unet {
 
     // r (= init_conv output) and the hoisted block1 output, broadcast per hypothesis
     const int hw0 = S0 * S0;
-    bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-        x0, ref_of, nullptr, 0, 0, RB, n, hw0, dim);
+    const bool need_rb = conv_impl == 1 || (tap_out && tap_name == "init_conv");
+    if (need_rb) {   // r per hypothesis: only the SIMT twin (no epilogue extras) and the debug tap
+      bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
+          x0, ref_of, nullptr, 0, 0, RB, n, hw0, dim);
+      ++launches;
+    }
     bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
         g1, ref_of, pb, P, pb_off.at("downs.0.0"), TB, n, hw0, dim);
     NOPE_CUDA(cudaGetLastError());
-    launches += 2;
-    if (tap("init_conv", RB, dim, S0, n, st)) return -1;
+    ++launches;
+    if (need_rb && tap("init_conv", RB, dim, S0, n, st)) return -1;
 
     // ---- downs
     __half* cur = nullptr;
@@ -727,7 +791,26 @@ struct nope_unet {
       if (tap((p + ".3").c_str(), cur, din, S, n, st)) return -1;
     }
     // ---- head
-    if (resblock("final_res_block", cur, dim, RB, dim, oth, S, n, true, st)) return -1;
+    if (conv_impl == 1) {
+      if (resblock("final_res_block", cur, dim, RB, dim, oth, S, n, true, st)) return -1;
+    } else {
+      // ResnetBlock over cat(x, r) with the r halves of both convs hoisted per reference:
+      // conv(cat(x, r)) = conv_x(x) + conv_r(r); the hoisted half enters as an epilogue residual
+      // (before the GroupNorm partial sums, which must see the full conv output).
+      const std::string p = "final_res_block";
+      const int parts = st_parts_of(S);
+      ConvExtras e1, e2;
+      e1.res_hi = rc1h; e1.res_lo = rc1l; e1.res_map = ref_of; e1.res_hw = S * S;
+      e2.res_hi = rc2h; e2.res_lo = rc2l; e2.res_map = ref_of; e2.res_hw = S * S;
+      if (conv(convs.at(p + ".block1x"), cur, dim, nullptr, 0, TA, S, n, cap, st, SA, &e1)) return -1;
+      if (gn(&norms.at(p + ".norm1"), TA, TB, S, dim, n, true, pb_off.at(p), nullptr, nullptr, st, SA, parts,
+             dim / 8))
+        return -1;
+      if (conv(convs.at(p + ".block2"), TB, dim, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
+      if (conv(convs.at(p + ".resx"), cur, dim, nullptr, 0, TC, S, n, cap, st, nullptr, &e2)) return -1;
+      if (gn(&norms.at(p + ".norm2"), TA, oth, S, dim, n, true, -1, TC, nullptr, st, SA, parts, dim / 8))
+        return -1;
+    }
     std::swap(cur, oth);
     if (tap("final_res_block", cur, dim, S, n, st)) return -1;
     if (resblock("final_conv.0", cur, dim, nullptr, 0, oth, S, n, false, st)) return -1;
