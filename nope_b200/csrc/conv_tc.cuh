@@ -64,6 +64,14 @@ struct ConvParams {
   const __half* res_lo;   // residual, low halves (nullptr: residual is a single fp16 tensor)
   const int* res_map;     // optional: image -> residual image (a per-reference tensor shared by
   int res_hw;             //   all hypotheses of that reference); res_hw = pixels per image
+  // Folded GroupNorm(1, C) pre-norm (PreNorm -> 1x1 conv, model_utils.py:226-234): with
+  // W' = W diag(gamma), conv(GN(x)) = rstd_h (W' x) + c1 - rstd_h mean_h c2, c1 = W beta (passed
+  // as `bias`), c2[n] = sum_c W'[n, c].  (mean_h, rstd_h) come from the per-image partial sums
+  // rs_stats[img][rs_parts] (emitted by the producer of x).
+  const float2* rs_stats;
+  const float* rs_c2;
+  int rs_parts, rs_hw;
+  float rs_inv_cnt, rs_eps;
   __half* out_lo;         // low halves of the output (omap receives the high halves)
   float* out_f32;         // fp32 output instead of the fp16 TMA store
   // optional GroupNorm partial statistics of the fp32 outputs (bias included), written
@@ -90,7 +98,7 @@ struct ConvSmem {
   static constexpr int kOutBytes = (BN / 64) * kBM * 128;
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
-  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;  // + alignment slack
+  static constexpr int kTotal = kBiasOffset + 2 * BN * 4 + 1024;  // bias + c2 vectors, alignment slack
 };
 
 __device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int m_tile, int& b0,
@@ -162,6 +170,21 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
     const int img = grow / p.res_hw;
     rrow = p.res_map[img] * p.res_hw + (grow - img * p.res_hw);
   }
+  // folded pre-norm: per-row scale rstd and offset -rstd*mean (row = one pixel of image img)
+  float rs = 1.f, rsm = 0.f;
+  if (p.rs_stats) {
+    const int img = (grow < p.m_valid ? grow : p.m_valid - 1) / p.rs_hw;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < p.rs_parts; ++i) {
+      const float2 t = p.rs_stats[(size_t)img * p.rs_parts + i];
+      s1 += t.x;
+      s2 += t.y;
+    }
+    const float mean = s1 * p.rs_inv_cnt;
+    const float var = fmaxf(s2 * p.rs_inv_cnt - mean * mean, 0.f);
+    rs = rsqrtf(var + p.rs_eps);
+    rsm = -rs * mean;
+  }
   uint32_t va[32], vb[32];
   tmem_ld_32x32(t_row, va);
 #pragma unroll
@@ -185,6 +208,15 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       f[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
       f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z;
       f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
+      if (p.rs_stats) {
+        const float4 c0 = *reinterpret_cast<const float4*>(bs + BN + j * 8);
+        const float4 c1 = *reinterpret_cast<const float4*>(bs + BN + j * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float cc2[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          f[i] = fmaf(__uint_as_float(v[j * 8 + i]), rs, fmaf(rsm, cc2[i], bb[i]));
+      }
       if (extras) {
         const size_t goff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
         if (p.res_hi && row_ok) {
@@ -374,7 +406,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
       const int n_chan0 = (n_tile - par * p.n_tiles_par) * BN;   // first output channel of the tile
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
-      if (etid < BN) s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
+      if (etid < BN) {
+        s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
+        s_bias[BN + etid] = p.rs_c2 ? __ldg(p.rs_c2 + n_chan0 + etid) : 0.f;
+      }
       // staging buffer must have been fully read by the previous TMA store; bias visible
       if (etid == 0) tma_store_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -109,7 +109,7 @@ struct Conv2Smem {
   static constexpr int kOutBytes = (BN / 64) * kBM * 128;
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
-  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;
+  static constexpr int kTotal = kBiasOffset + 2 * BN * 4 + 1024;
 };
 
 template <int BN, int STAGES>
@@ -235,7 +235,10 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       const int n_chan0 = (n_tile - par * p.n_tiles_par) * BN;
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
-      if (etid < BN) s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
+      if (etid < BN) {
+        s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
+        s_bias[BN + etid] = p.rs_c2 ? __ldg(p.rs_c2 + n_chan0 + etid) : 0.f;
+      }
       if (etid == 0) tma_store_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);

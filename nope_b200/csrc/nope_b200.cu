@@ -31,6 +31,10 @@ struct ConvExtras {
   const int* res_map = nullptr;
   int res_hw = 0;
   __half* out_lo = nullptr;
+  // folded GroupNorm(1, C) pre-norm (see ConvParams::rs_stats)
+  const float2* rs_stats = nullptr;
+  int rs_parts = 0, rs_hw = 0;
+  float rs_inv_cnt = 0.f;
 };
 
 constexpr int kAbiVersion = 1;
@@ -46,6 +50,7 @@ struct ConvLayer {
   int cin = 0, cout = 0, K = 0, bn = 0;
   __half* w = nullptr;    // [cout][K] fp16
   float* bias = nullptr;  // [cout] fp32 or nullptr
+  float* c2 = nullptr;    // folded pre-norm only: c2[n] = sum_c W'[n, c] (fp16-rounded W')
   CUtensorMap wmap;
   CUtensorMap wmap_half;  // BN/2-row box for the 2-CTA kernel
   bool has_map = false;
@@ -271,6 +276,41 @@ struct nope_unet {
     convs[name] = L;
     return 0;
   }
+  // PreNorm(GroupNorm(1, C)) followed by a bias-free 1x1 conv (to_qkv), folded:
+  //   conv(GN(x))[n] = rstd (W' x)[n] + c1[n] - rstd mean c2[n],  W' = W diag(gamma),
+  //   c1 = W beta, c2[n] = sum_c fp16(W'[n, c])  -- the conv then reads x directly and the
+  // normalised tensor is never materialised (model_utils.py:226-234, 399).
+  int make_prenorm_conv(const std::string& name, const std::string& wkey, const std::string& normprefix) {
+    const HostTensor& W = host.at(wkey);
+    const auto& g = host.at(normprefix + ".weight").data;
+    const auto& b = host.at(normprefix + ".bias").data;
+    const int cout = (int)W.shape[0], cin = (int)W.shape[1];
+    HostTensor Wf, c1;
+    Wf.shape = W.shape;
+    Wf.data.resize(W.data.size());
+    c1.shape = {cout};
+    c1.data.resize(cout);
+    std::vector<float> c2(cout);
+    for (int o = 0; o < cout; ++o) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int c = 0; c < cin; ++c) {
+        const float wf = W.data[(size_t)o * cin + c] * g[c];
+        Wf.data[(size_t)o * cin + c] = wf;
+        a1 += (double)W.data[(size_t)o * cin + c] * (double)b[c];
+        a2 += (double)__half2float(__float2half_rn(wf));
+      }
+      c1.data[o] = (float)a1;
+      c2[o] = (float)a2;
+    }
+    host["__pn." + wkey] = std::move(Wf);
+    host["__pn." + wkey + ".c1"] = std::move(c1);
+    if (make_conv(name, "__pn." + wkey, "__pn." + wkey + ".c1", 1)) return -1;
+    ConvLayer& L = convs[name];
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.c2), cout * sizeof(float)));
+    owned.push_back(L.c2);
+    NOPE_CUDA(cudaMemcpy(L.c2, c2.data(), cout * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+  }
   int make_norm(const std::string& name, const std::string& prefix, int G) {
     NormLayer n;
     auto it = host.find(prefix + ".weight");
@@ -295,6 +335,7 @@ struct nope_unet {
   int make_linattn(const std::string& p) {
     if (make_norm(p + ".prenorm", p + ".fn.norm", 1)) return -1;
     if (make_conv(p + ".qkv", p + ".fn.fn.to_qkv.weight", "", 1)) return -1;
+    if (make_prenorm_conv(p + ".qkvf", p + ".fn.fn.to_qkv.weight", p + ".fn.norm")) return -1;
     if (make_conv(p + ".out", p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", 1)) return -1;
     if (make_norm(p + ".outnorm", p + ".fn.fn.to_out.1", 1)) return -1;
     return 0;
@@ -353,6 +394,7 @@ struct nope_unet {
     if (make_resblock("mid_block1") || make_resblock("mid_block2")) return -1;
     if (make_norm("mid_attn.prenorm", "mid_attn.fn.norm", 1)) return -1;
     if (make_conv("mid_attn.qkv", "mid_attn.fn.fn.to_qkv.weight", "", 1)) return -1;
+    if (make_prenorm_conv("mid_attn.qkvf", "mid_attn.fn.fn.to_qkv.weight", "mid_attn.fn.norm")) return -1;
     if (make_conv("mid_attn.out", "mid_attn.fn.fn.to_out.weight", "mid_attn.fn.fn.to_out.bias", 1))
       return -1;
     for (int j = 0; j < 4; ++j) {
@@ -541,6 +583,11 @@ struct nope_unet {
     if (ex) {
       p.res_hi = ex->res_hi; p.res_lo = ex->res_lo; p.res_map = ex->res_map; p.res_hw = ex->res_hw;
       p.out_lo = ex->out_lo;
+      if (ex->rs_stats) {
+        NOPE_CHECK(L.c2 != nullptr, "folded pre-norm needs a layer built by make_prenorm_conv");
+        p.rs_stats = ex->rs_stats; p.rs_parts = ex->rs_parts; p.rs_hw = ex->rs_hw;
+        p.rs_inv_cnt = ex->rs_inv_cnt; p.rs_eps = 1e-5f; p.rs_c2 = L.c2;
+      }
     }
     p.nseg = nseg;
     p.ksteps = ksteps;
@@ -653,13 +700,28 @@ struct nope_unet {
               emit_g1 ? SB : nullptr);
   }
 
+  // TD = to_qkv(GroupNorm(1, C)(x)).  tcgen05 paths: the norm is folded into the conv (weights
+  // scaled by gamma, per-hypothesis rstd / mean applied in the epilogue from the SB partial sums
+  // the producer of x emitted); the SIMT twin keeps the explicit two-step form.
+  int qkv_prenorm(const std::string& p, const __half* x, int C, int S, int n, cudaStream_t st) {
+    if (conv_impl == 1) {
+      if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
+             emit_parts_of(S * S), 1))
+        return -1;
+      return conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st);
+    }
+    ConvExtras e;
+    e.rs_stats = SB;
+    e.rs_parts = emit_parts_of(S * S);
+    e.rs_hw = S * S;
+    e.rs_inv_cnt = 1.0f / ((float)(S * S) * (float)C);
+    return conv(convs.at(p + ".qkvf"), x, C, nullptr, 0, TD, S, n, cap, st, nullptr, &e);
+  }
+
   // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418).  x's GroupNorm(1) statistics
   // were emitted into SB by the producer of x; to_out[1]'s come from the to_out conv epilogue.
   int linattn(const std::string& p, const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
-    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
-           emit_parts_of(S * S), 1))
-      return -1;
-    if (conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
+    if (qkv_prenorm(p, x, C, S, n, st)) return -1;
     linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD, TC, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
@@ -671,10 +733,7 @@ struct nope_unet {
   // Residual(PreNorm(Attention)) (model_utils.py:367-390)
   int midattn(const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
     NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
-    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
-           emit_parts_of(S * S), 1))
-      return -1;
-    if (conv(convs.at("mid_attn.qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
+    if (qkv_prenorm("mid_attn", x, C, S, n, st)) return -1;
     midattn_kernel<<<n, 128, 0, st>>>(TD, TC, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
