@@ -256,3 +256,31 @@ def test_full_level2_grid_against_reference_golden(gpu_model, golden_dir):
     assert e_sim < SIM_TOL and e_sim2 < SIM_TOL and max(e0, e1) < EMB_TOL
     _cmp_ranking(g["similarity"], g["nearest_idx"], out["topi"], SIM_TOL)
     _cmp_ranking(g["similarity"], g["nearest_idx"], idx2, SIM_TOL)
+
+
+@pytest.mark.parametrize("dim", [64, 128])
+def test_other_unet_widths_vs_live_oracle(dim):
+    """UNet(u_net_dim=64 / 128) -- the widths the reference's own smoke block uses
+    (u_net.py:201-217 builds u_net_dim=64): exercises the 64- and 128-channel N-tile variants of
+    the convolution kernel through the whole pipeline, against the oracle run here on CPU."""
+    from oracle import unet_oracle as orc, weights
+    from nope_b200.encoder import FeatureExtractor
+    from nope_b200.unet import UNet
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    sd = weights.make_unet_state_dict(seed=3, u_net_dim=dim)
+    unet = UNet(u_net_dim=dim, rot_representation_dim=6, encoder=FeatureExtractor(descriptor_size=8),
+                pose_mlp_name="single_layer", device="cuda:0")
+    unet.load_state_dict(sd)
+    g = torch.Generator().manual_seed(dim)
+    rf = torch.randn(2, 8, 32, 32, generator=g) * 1.5
+    qf = torch.randn(2, 8, 32, 32, generator=g) * 1.5
+    poses = torch.randn(2, 5, 6, generator=g)
+    out = unet.sweep(rf, poses, query_feat=qf, want_emb=True, k=3)
+    with torch.no_grad():
+        emb = orc.generate_templates(sd, rf, poses)
+        sim = orc.l2_similarity(qf, emb)
+    e_emb, e_sim = rel_l2(out["emb"], emb), max_rel(out["sim"], sim)
+    log("unet_width", dim=dim, emb_rel_l2=e_emb, sim_max_rel=e_sim)
+    assert e_emb < EMB_TOL and e_sim < 2 * SIM_TOL
+    assert torch.equal(out["topi"].cpu(), orc.topk_lowest_index(out["sim"].cpu(), 3))
