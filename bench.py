@@ -293,7 +293,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, (world, args.gpus)
 
-    from oracle import weights                      # seeded synthetic weights (random init)
+    from nope_b200 import synth_weights as weights  # seeded random-init weights, reference schema
     from nope_b200.model import build_model
     from nope_b200.dist import ShardedSweep
     from nope_b200.poses import synthetic_pose_batch

@@ -1,204 +1,8 @@
-"""TEST INFRASTRUCTURE ONLY -- seeded synthetic weights with the reference's
-state_dict schema (SURVEY.md section 8b "Weights").
-
-No trained checkpoint ships with the reference, so parity is pinned on seeded
-random weights.  The recipe below does not need the reference tree: it
-enumerates the keys/shapes that `UNet.state_dict()` and
-`FeatureExtractor.state_dict()` produce
-(reference: src/model/u_net/denoising_diffusion_pytorch/u_net.py:27-158,
-src/model/encoder/template.py:24-45, src/model/encoder/resnet.py:93-133) and
-fills each tensor from a torch CPU generator, which is platform independent.
-`oracle/make_golden.py` loads the result into the reference's own modules with
-strict=True, which pins the schema.
-
-Distributions: conv/linear weights U(-b, b) with b = gain / sqrt(fan_in)
-(PyTorch's default family), biases U(-b, b); norm weights 1 + 0.2 U(-1,1),
-norm biases 0.2 U(-1,1) so affine-handling bugs are visible; BatchNorm running
-mean 0.1 U(-1,1), running var 1 + 0.2 U(-1,1).
-"""
-from collections import OrderedDict
-import math
-import torch
-
-
-def _resblock_shapes(prefix, cin, cout, cemb, with_mlp=True):
-    s = OrderedDict()
-    if with_mlp:
-        s[f"{prefix}.mlp.1.weight"] = (cout, cemb)
-        s[f"{prefix}.mlp.1.bias"] = (cout,)
-    s[f"{prefix}.block1.proj.weight"] = (cout, cin, 3, 3)
-    s[f"{prefix}.block1.proj.bias"] = (cout,)
-    s[f"{prefix}.block1.norm.weight"] = (cout,)
-    s[f"{prefix}.block1.norm.bias"] = (cout,)
-    s[f"{prefix}.block2.proj.weight"] = (cout, cout, 3, 3)
-    s[f"{prefix}.block2.proj.bias"] = (cout,)
-    s[f"{prefix}.block2.norm.weight"] = (cout,)
-    s[f"{prefix}.block2.norm.bias"] = (cout,)
-    if cin != cout:
-        s[f"{prefix}.res_conv.weight"] = (cout, cin, 1, 1)
-        s[f"{prefix}.res_conv.bias"] = (cout,)
-    return s
-
-
-def _linattn_shapes(prefix, dim, hidden=128):
-    # Residual(PreNorm(dim, LinearAttention(dim))): model_utils.py:393-418,226-234
-    s = OrderedDict()
-    s[f"{prefix}.fn.fn.to_qkv.weight"] = (hidden * 3, dim, 1, 1)
-    s[f"{prefix}.fn.fn.to_out.0.weight"] = (dim, hidden, 1, 1)
-    s[f"{prefix}.fn.fn.to_out.0.bias"] = (dim,)
-    s[f"{prefix}.fn.fn.to_out.1.weight"] = (dim,)
-    s[f"{prefix}.fn.fn.to_out.1.bias"] = (dim,)
-    s[f"{prefix}.fn.norm.weight"] = (dim,)
-    s[f"{prefix}.fn.norm.bias"] = (dim,)
-    return s
-
-
-def unet_param_shapes(u_net_dim=192, channels=8, rot_dim=6, dim_mults=(1, 2, 4, 8)):
-    """Key -> shape for the default UNet, encoder keys excluded (u_net.py:27-158)."""
-    cemb = u_net_dim * 4
-    dims = [u_net_dim] + [u_net_dim * m for m in dim_mults]
-    in_out = list(zip(dims[:-1], dims[1:]))
-    s = OrderedDict()
-    s["pose_mlp.0.weight"] = (cemb, rot_dim)
-    s["pose_mlp.0.bias"] = (cemb,)
-    s["init_conv.weight"] = (u_net_dim, channels, 3, 3)
-    s["init_conv.bias"] = (u_net_dim,)
-    for i, (din, dout) in enumerate(in_out):
-        last = i == len(in_out) - 1
-        s.update(_resblock_shapes(f"downs.{i}.0", din, din, cemb))
-        s.update(_resblock_shapes(f"downs.{i}.1", din, din, cemb))
-        s.update(_linattn_shapes(f"downs.{i}.2", din))
-        if not last:
-            s[f"downs.{i}.3.1.weight"] = (dout, din * 4, 1, 1)
-            s[f"downs.{i}.3.1.bias"] = (dout,)
-        else:
-            s[f"downs.{i}.3.weight"] = (dout, din, 3, 3)
-            s[f"downs.{i}.3.bias"] = (dout,)
-    mid = dims[-1]
-    # Residual(PreNorm(mid, Attention(mid))): model_utils.py:367-390
-    s["mid_attn.fn.fn.to_qkv.weight"] = (384, mid, 1, 1)
-    s["mid_attn.fn.fn.to_out.weight"] = (mid, 128, 1, 1)
-    s["mid_attn.fn.fn.to_out.bias"] = (mid,)
-    s["mid_attn.fn.norm.weight"] = (mid,)
-    s["mid_attn.fn.norm.bias"] = (mid,)
-    s.update(_resblock_shapes("mid_block1", mid, mid, cemb))
-    s.update(_resblock_shapes("mid_block2", mid, mid, cemb))
-    for i, (din, dout) in enumerate(reversed(in_out)):
-        last = i == len(in_out) - 1
-        s.update(_resblock_shapes(f"ups.{i}.0", dout + din, dout, cemb))
-        s.update(_resblock_shapes(f"ups.{i}.1", dout + din, dout, cemb))
-        s.update(_linattn_shapes(f"ups.{i}.2", dout))
-        if not last:
-            s[f"ups.{i}.3.1.weight"] = (din, dout, 3, 3)
-            s[f"ups.{i}.3.1.bias"] = (din,)
-        else:
-            s[f"ups.{i}.3.weight"] = (din, dout, 3, 3)
-            s[f"ups.{i}.3.bias"] = (din,)
-    s.update(_resblock_shapes("final_res_block", u_net_dim * 2, u_net_dim, cemb))
-    # final_conv.0 is a ResnetBlock built with the partial's time_emb_dim, so it
-    # owns an (unused) mlp.1 as well (u_net.py:154-157; forward gets no emb).
-    s.update(_resblock_shapes("final_conv.0", u_net_dim, u_net_dim, cemb))
-    s["final_conv.1.weight"] = (channels, u_net_dim, 1, 1)
-    s["final_conv.1.bias"] = (channels,)
-    return s
-
-
-def _bn_shapes(prefix, c):
-    return OrderedDict([(f"{prefix}.weight", (c,)), (f"{prefix}.bias", (c,)),
-                        (f"{prefix}.running_mean", (c,)), (f"{prefix}.running_var", (c,)),
-                        (f"{prefix}.num_batches_tracked", ())])
-
-
-def encoder_param_shapes(descriptor_size=8):
-    """Key -> shape for FeatureExtractor.backbone/.projector (resnet.py:93-133,
-    template.py:29-39).  The reference registers the same tensors a second time
-    as encoder.{0,1}.* (template.py:40); `alias_encoder_keys` adds those."""
-    s = OrderedDict()
-    s["backbone.conv1.weight"] = (64, 3, 7, 7)
-    s.update(_bn_shapes("backbone.bn1", 64))
-    inplanes = 64
-    for li, (planes, blocks, stride) in enumerate(
-            [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 1)], start=1):
-        for b in range(blocks):
-            p = f"backbone.layer{li}.{b}"
-            s[f"{p}.conv1.weight"] = (planes, inplanes, 1, 1)
-            s.update(_bn_shapes(f"{p}.bn1", planes))
-            s[f"{p}.conv2.weight"] = (planes, planes, 3, 3)
-            s.update(_bn_shapes(f"{p}.bn2", planes))
-            s[f"{p}.conv3.weight"] = (planes * 4, planes, 1, 1)
-            s.update(_bn_shapes(f"{p}.bn3", planes * 4))
-            if b == 0 and (stride != 1 or inplanes != planes * 4):
-                s[f"{p}.downsample.0.weight"] = (planes * 4, inplanes, 1, 1)
-                s.update(_bn_shapes(f"{p}.downsample.1", planes * 4))
-            inplanes = planes * 4
-    s["backbone.fc.weight"] = (1, 2048)   # resnet50(num_classes=1), unused
-    s["backbone.fc.bias"] = (1,)
-    s["projector.1.weight"] = (256, 2048, 1, 1)
-    s["projector.3.weight"] = (descriptor_size, 256, 1, 1)
-    return s
-
-
-def _fill(name, shape, g):
-    if len(shape) == 0:
-        return torch.zeros((), dtype=torch.long)
-    u = lambda: torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1
-    leaf = name.rsplit(".", 1)[-1]
-    is_norm = (".norm." in name or "to_out.1." in name or ".bn" in name
-               or "downsample.1." in name)
-    if leaf == "running_mean":
-        return 0.1 * u()
-    if leaf == "running_var":
-        return 1.0 + 0.2 * u()
-    if is_norm and len(shape) == 1:
-        return (1.0 + 0.2 * u()) if leaf == "weight" else 0.2 * u()
-    if leaf == "weight":
-        fan_in = 1
-        for d in shape[1:]:
-            fan_in *= d
-        gain = math.sqrt(3.0) if "backbone" in name or "projector" in name else 1.0
-        return u() * (gain / math.sqrt(fan_in))
-    # bias of conv / linear
-    return u() * 0.1
-
-
-def make_unet_state_dict(seed=0, u_net_dim=192, channels=8):
-    g = torch.Generator(device="cpu").manual_seed(1000 + seed)
-    return OrderedDict((k, _fill(k, shp, g))
-                       for k, shp in unet_param_shapes(u_net_dim, channels).items())
-
-
-def make_encoder_state_dict(seed=0, descriptor_size=8):
-    g = torch.Generator(device="cpu").manual_seed(2000 + seed)
-    return OrderedDict((k, _fill(k, shp, g))
-                       for k, shp in encoder_param_shapes(descriptor_size).items())
-
-
-def alias_encoder_keys(enc_sd):
-    """FeatureExtractor.state_dict() lists every tensor under backbone./projector.
-    and again under encoder.0./encoder.1. (template.py:40)."""
-    out = OrderedDict(enc_sd)
-    for k, v in enc_sd.items():
-        if k.startswith("backbone."):
-            out["encoder.0." + k[len("backbone."):]] = v
-        elif k.startswith("projector."):
-            out["encoder.1." + k[len("projector."):]] = v
-    return out
-
-
-def make_full_state_dict(seed=0, u_net_dim=192, descriptor_size=8):
-    """state_dict of reference `UNet` (u_net + 'encoder.'-prefixed encoder)."""
-    sd = OrderedDict()
-    enc = alias_encoder_keys(make_encoder_state_dict(seed, descriptor_size))
-    for k, v in enc.items():
-        sd["encoder." + k] = v
-    sd.update(make_unet_state_dict(seed, u_net_dim, descriptor_size))
-    return sd
-
-
-def checksum(sd):
-    """Order-sensitive fp64 checksum used to assert RNG determinism across boxes."""
-    acc = 0.0
-    for i, (k, v) in enumerate(sd.items()):
-        if v.dtype.is_floating_point:
-            acc += float(v.double().sum()) * (1 + (i % 7)) + float(v.double().abs().sum())
-    return acc
+"""TEST INFRASTRUCTURE ONLY -- the seeded synthetic weights (reference state_dict schema)
+used by the oracle and the golden generator.  The recipe lives in the product package
+(`nope_b200/synth_weights.py`) because the bench and the tools need random-init weights too and
+must not import oracle/."""
+from nope_b200.synth_weights import *  # noqa: F401,F403
+from nope_b200.synth_weights import (alias_encoder_keys, checksum, encoder_param_shapes,  # noqa: F401
+                                     make_encoder_state_dict, make_full_state_dict,
+                                     make_unet_state_dict, unet_param_shapes)

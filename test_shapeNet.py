@@ -74,7 +74,7 @@ def main():
         model.load_state_dict(sd.get("state_dict", sd))
         weights_desc = args.checkpoint
     else:
-        from oracle import weights                    # seeded random init, reference schema
+        from nope_b200 import synth_weights as weights
         model.load_state_dict(weights.make_full_state_dict(seed=0))
         weights_desc = "seeded random init (no trained checkpoint available)"
     if world > 1:

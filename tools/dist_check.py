@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-from oracle import weights
+from nope_b200 import synth_weights as weights
 from nope_b200.dist import ShardedSweep
 from nope_b200.model import build_model
 from nope_b200.poses import synthetic_pose_batch

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn as nn
 
-from oracle import weights
+from nope_b200 import synth_weights as weights
 from nope_b200.encoder import FeatureExtractor
 
 torch.backends.cudnn.allow_tf32 = False

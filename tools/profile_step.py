@@ -7,7 +7,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from oracle import weights
+from nope_b200 import synth_weights as weights
 from nope_b200.model import build_model
 from nope_b200.poses import synthetic_pose_batch
 
