@@ -441,7 +441,10 @@ struct nope_unet {
     cap = std::max(cap, need_cap);
     cap_ref = std::max(cap_ref, need_ref);
     const size_t c = (size_t)cap;
-    const size_t big = (size_t)S0 * S0 * dim * 2;  // S0^2 x 2*dim halfs (qkv / upsampled input)
+    // temporaries hold the widest full-resolution tensor: a concat-conv output (<= 2*dim
+    // channels) or the attention qkv tensor (3 x 128 channels, independent of dim)
+    const size_t big = (size_t)S0 * S0 * std::max(dim * 2, 3 * kHeadsHidden);
+    const size_t xsz = (size_t)S0 * S0 * dim;      // one full-resolution feature map
     for (int i = 0; i < 4; ++i) {
       const int s = S0 >> i;
       for (int b = 0; b < 2; ++b) {
@@ -451,15 +454,14 @@ struct nope_unet {
       }
     }
     if (ws_alloc_half(&TA, c * big) || ws_alloc_half(&TB, c * big) || ws_alloc_half(&TC, c * big) ||
-        ws_alloc_half(&TD, c * big) || ws_alloc_half(&XA, c * big / 2) ||
-        ws_alloc_half(&XB, c * big / 2) || ws_alloc_half(&RB, c * big / 2) ||
+        ws_alloc_half(&TD, c * big) || ws_alloc_half(&XA, c * xsz) ||
+        ws_alloc_half(&XB, c * xsz) || ws_alloc_half(&RB, c * xsz) ||
         ws_alloc_half(&cs, c * cemb) || ws_alloc_half(&pb, c * P))
       return -1;
     const size_t r = (size_t)cap_ref;
-    if (ws_alloc_half(&x0, r * big / 2) || ws_alloc_half(&g1, r * big / 2) ||
-        ws_alloc_half(&pt, r * big / 2) || ws_alloc_half(&rc1h, r * big / 2) ||
-        ws_alloc_half(&rc1l, r * big / 2) || ws_alloc_half(&rc2h, r * big / 2) ||
-        ws_alloc_half(&rc2l, r * big / 2))
+    if (ws_alloc_half(&x0, r * xsz) || ws_alloc_half(&g1, r * xsz) || ws_alloc_half(&pt, r * xsz) ||
+        ws_alloc_half(&rc1h, r * xsz) || ws_alloc_half(&rc1l, r * xsz) ||
+        ws_alloc_half(&rc2h, r * xsz) || ws_alloc_half(&rc2l, r * xsz))
       return -1;
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&gn_partial),
                          (size_t)std::max(cap, cap_ref) * 8 * 8 * sizeof(float2)));
