@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnope_b200.so")
+_DEFAULT_LIB_PATH = os.path.join(_HERE, "lib", "libnope_b200.so")
+LIB_PATH = _DEFAULT_LIB_PATH
 
 c_f32p = C.c_void_p   # raw device / host pointers travel as integers
 c_i64p = C.c_void_p
@@ -61,6 +62,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and LIB_PATH == _DEFAULT_LIB_PATH and \
+            not os.environ.get("NOPE_NO_AUTOBUILD"):
+        # the library is built in-tree by `python -m nope_b200.build` / __graft_entry__.build();
+        # on a fresh checkout compile it now (nvcc, sm_100a) -- still the CUDA path, never a fallback
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as exc:
+            raise NopeError(f"{LIB_PATH} is missing and building it failed: {exc}") from exc
     if not os.path.exists(LIB_PATH):
         raise NopeError(
             f"{LIB_PATH} is missing: build it with `python -m nope_b200.build` "
