@@ -284,3 +284,27 @@ def test_other_unet_widths_vs_live_oracle(dim):
     log("unet_width", dim=dim, emb_rel_l2=e_emb, sim_max_rel=e_sim)
     assert e_emb < EMB_TOL and e_sim < 2 * SIM_TOL
     assert torch.equal(out["topi"].cpu(), orc.topk_lowest_index(out["sim"].cpu(), 3))
+
+
+@pytest.mark.parametrize("B,N,chunk", [(1, 1, 642), (1, 7, 3), (2, 9, 5), (3, 17, 642), (1, 131, 128),
+                                       (2, 65, 64)])
+def test_ragged_batches_equal_single_hypothesis_runs(gpu_model, B, N, chunk):
+    """Every (reference, pose) forward is independent (model.py:212-222): for ragged sizes (partial
+    128-pixel tiles at every resolution, odd CTA-pair counts, chunk tails of 1) the batched sweep
+    must equal, bit for bit, the same hypothesis swept alone."""
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    rf = torch.randn(B, 8, 32, 32, generator=g) * 1.5
+    qf = torch.randn(B, 8, 32, 32, generator=g) * 1.5
+    poses = torch.randn(B, N, 6, generator=g)
+    u = gpu_model.u_net
+    u.set_chunk(chunk)
+    full = u.sweep(rf, poses, query_feat=qf, want_emb=True, k=min(5, N))
+    u.set_chunk(642)
+    picks = sorted({0, N - 1, N // 2, min(N - 1, chunk), max(0, chunk - 1) % N})
+    for b in range(B):
+        for n in picks:
+            one = u.sweep(rf[b:b + 1], poses[b:b + 1, n:n + 1], query_feat=qf[b:b + 1], want_emb=True)
+            assert torch.equal(one["emb"][0, 0], full["emb"][b, n]), (b, n)
+            assert torch.equal(one["sim"][0, 0], full["sim"][b, n]), (b, n)
+    assert torch.equal(full["topi"].cpu(),
+                       __import__("oracle.unet_oracle", fromlist=["x"]).topk_lowest_index(full["sim"].cpu(), min(5, N)))
