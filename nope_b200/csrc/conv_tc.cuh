@@ -174,11 +174,15 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
   float rs = 1.f, rsm = 0.f;
   if (p.rs_stats) {
     const int img = (grow < p.m_valid ? grow : p.m_valid - 1) / p.rs_hw;
+    float2 t[8];                                   // rs_parts <= 8: all loads in flight together
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      t[i] = i < p.rs_parts ? p.rs_stats[(size_t)img * p.rs_parts + i] : make_float2(0.f, 0.f);
     float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < p.rs_parts; ++i) {
-      const float2 t = p.rs_stats[(size_t)img * p.rs_parts + i];
-      s1 += t.x;
-      s2 += t.y;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s1 += t[i].x;
+      s2 += t[i].y;
     }
     const float mean = s1 * p.rs_inv_cnt;
     const float var = fmaxf(s2 * p.rs_inv_cnt - mean * mean, 0.f);
@@ -194,6 +198,17 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
     if (cc + 1 < BN / 64) tmem_ld_32x32(t_row + (cc + 1) * 64, (cc & 1) ? va : vb);
     const float* bs = s_bias + cc * 64 + hh * 32;
     uint8_t* srow = out_stage + cc * (kBM * 128) + row * 128;
+    // residual operands of this sub-tile: issue all loads before the math (one round trip per
+    // sub-tile instead of one per 8-channel octet)
+    uint4 rh[4], rl[4];
+    if (p.res_hi && row_ok) {
+      const size_t roff = (size_t)rrow * p.n_total + n_chan0 + cc * 64 + hh * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rh[j] = *reinterpret_cast<const uint4*>(p.res_hi + roff + j * 8);
+        rl[j] = p.res_lo ? *reinterpret_cast<const uint4*>(p.res_lo + roff + j * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
     float st[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {   // 4 x 16-byte chunks of 8 channels
@@ -220,24 +235,13 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       if (extras) {
         const size_t goff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
         if (p.res_hi && row_ok) {
-          const size_t roff = (size_t)rrow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
-          const uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + roff);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&rh[j]);
+          const __half2* l2 = reinterpret_cast<const __half2*>(&rl[j]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 t = __half22float2(h2[q]);
-            f[2 * q] += t.x;
-            f[2 * q + 1] += t.y;
-          }
-          if (p.res_lo) {
-            const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + roff);
-            const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 t = __half22float2(l2[q]);
-              f[2 * q] += t.x;
-              f[2 * q + 1] += t.y;
-            }
+            const float2 th = __half22float2(h2[q]), tl = __half22float2(l2[q]);
+            f[2 * q] += th.x + tl.x;
+            f[2 * q + 1] += th.y + tl.y;
           }
         }
         if (p.relu) {
