@@ -62,16 +62,6 @@ struct ConvParams {
   int relu;
   const __half* res_hi;   // residual, high halves (nullptr: none)
   const __half* res_lo;   // residual, low halves (nullptr: residual is a single fp16 tensor)
-  const int* res_map;     // optional: image -> residual image (a per-reference tensor shared by
-  int res_hw;             //   all hypotheses of that reference); res_hw = pixels per image
-  // Folded GroupNorm(1, C) pre-norm (PreNorm -> 1x1 conv, model_utils.py:226-234): with
-  // W' = W diag(gamma), conv(GN(x)) = rstd_h (W' x) + c1 - rstd_h mean_h c2, c1 = W beta (passed
-  // as `bias`), c2[n] = sum_c W'[n, c].  (mean_h, rstd_h) come from the per-image partial sums
-  // rs_stats[img][rs_parts] (emitted by the producer of x).
-  const float2* rs_stats;
-  const float* rs_c2;
-  int rs_parts, rs_hw;
-  float rs_inv_cnt, rs_eps;
   __half* out_lo;         // low halves of the output (omap receives the high halves)
   float* out_f32;         // fp32 output instead of the fp16 TMA store
   // optional GroupNorm partial statistics of the fp32 outputs (bias included), written
@@ -98,7 +88,7 @@ struct ConvSmem {
   static constexpr int kOutBytes = (BN / 64) * kBM * 128;
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
-  static constexpr int kTotal = kBiasOffset + 2 * BN * 4 + 1024;  // bias + c2 vectors, alignment slack
+  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int m_tile, int& b0,
@@ -155,40 +145,18 @@ __device__ __forceinline__ int butterfly8(float (&v)[8], int lane) {
 // Epilogue of one 128 x BN accumulator tile, executed by the 8 epilogue warps of a CTA.
 // Warp e reads TMEM lanes 32*(e&3).. (its pixel rows) and the 32-column half (e>>2) of every
 // 64-column sub-tile: +bias (from smem) -> GroupNorm partial sums -> fp16 -> swizzled staging.
-template <int BN>
+// EXTRAS (compile time) enables ReLU / residual add / (hi, lo) split / fp32 output: the template
+// encoder's epilogue.  The sweep instantiates EXTRAS = false so its epilogue stays minimal (the
+// extra predicates and registers cost ~10 % on the large convolutions when merely present).
+template <int BN, bool EXTRAS>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t* out_stage,
                                                    const float* s_bias, uint32_t t_acc, int m_tile,
                                                    int n_chan0, int e, int lane) {
   const int q = e & 3, hh = e >> 2;
   const int row = q * 32 + lane;
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
-  const bool extras = p.relu || p.res_hi || p.out_lo || p.out_f32;   // warp-uniform
   const int grow = m_tile * kBM + row;                                // linear pixel index
   const bool row_ok = grow < p.m_valid;
-  int rrow = grow;                                                    // residual row
-  if (p.res_map && row_ok) {
-    const int img = grow / p.res_hw;
-    rrow = p.res_map[img] * p.res_hw + (grow - img * p.res_hw);
-  }
-  // folded pre-norm: per-row scale rstd and offset -rstd*mean (row = one pixel of image img)
-  float rs = 1.f, rsm = 0.f;
-  if (p.rs_stats) {
-    const int img = (grow < p.m_valid ? grow : p.m_valid - 1) / p.rs_hw;
-    float2 t[8];                                   // rs_parts <= 8: all loads in flight together
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      t[i] = i < p.rs_parts ? p.rs_stats[(size_t)img * p.rs_parts + i] : make_float2(0.f, 0.f);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s1 += t[i].x;
-      s2 += t[i].y;
-    }
-    const float mean = s1 * p.rs_inv_cnt;
-    const float var = fmaxf(s2 * p.rs_inv_cnt - mean * mean, 0.f);
-    rs = rsqrtf(var + p.rs_eps);
-    rsm = -rs * mean;
-  }
   uint32_t va[32], vb[32];
   tmem_ld_32x32(t_row, va);
 #pragma unroll
@@ -198,11 +166,10 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
     if (cc + 1 < BN / 64) tmem_ld_32x32(t_row + (cc + 1) * 64, (cc & 1) ? va : vb);
     const float* bs = s_bias + cc * 64 + hh * 32;
     uint8_t* srow = out_stage + cc * (kBM * 128) + row * 128;
-    // residual operands of this sub-tile: issue all loads before the math (one round trip per
-    // sub-tile instead of one per 8-channel octet)
+    // residual operands of this sub-tile: all loads issued before the math
     uint4 rh[4], rl[4];
-    if (p.res_hi && row_ok) {
-      const size_t roff = (size_t)rrow * p.n_total + n_chan0 + cc * 64 + hh * 32;
+    if (EXTRAS && p.res_hi && row_ok) {
+      const size_t roff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         rh[j] = *reinterpret_cast<const uint4*>(p.res_hi + roff + j * 8);
@@ -223,16 +190,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       f[5] = __uint_as_float(v[j * 8 + 5]) + b1.y;
       f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z;
       f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
-      if (p.rs_stats) {
-        const float4 c0 = *reinterpret_cast<const float4*>(bs + BN + j * 8);
-        const float4 c1 = *reinterpret_cast<const float4*>(bs + BN + j * 8 + 4);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const float cc2[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          f[i] = fmaf(__uint_as_float(v[j * 8 + i]), rs, fmaf(rsm, cc2[i], bb[i]));
-      }
-      if (extras) {
+      if (EXTRAS) {
         const size_t goff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
         if (p.res_hi && row_ok) {
           const __half2* h2 = reinterpret_cast<const __half2*>(&rh[j]);
@@ -290,7 +248,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool EXTRAS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using S = ConvSmem<BN, STAGES>;
@@ -410,16 +368,13 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
       const int n_chan0 = (n_tile - par * p.n_tiles_par) * BN;   // first output channel of the tile
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
-      if (etid < BN) {
-        s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
-        s_bias[BN + etid] = p.rs_c2 ? __ldg(p.rs_c2 + n_chan0 + etid) : 0.f;
-      }
+      if (etid < BN) s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
       // staging buffer must have been fully read by the previous TMA store; bias visible
       if (etid == 0) tma_store_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      conv_epilogue_tile<BN>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
+      conv_epilogue_tile<BN, EXTRAS>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       // accumulator fully read: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -539,27 +494,35 @@ inline int pick_bn(int n_total) {
   return 0;
 }
 
-template <int BN, int STAGES>
+inline bool conv_needs_extras(const ConvParams& p) {
+  return p.relu || p.res_hi || p.out_lo || p.out_f32;
+}
+
+template <int BN, int STAGES, bool EXTRAS>
 inline int launch_conv_tc_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using S = ConvSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    NOPE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>,
+    NOPE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, EXTRAS>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  conv_tc_kernel<BN, STAGES><<<grid, kConvThreads, S::kTotal, stream>>>(p);
+  conv_tc_kernel<BN, STAGES, EXTRAS><<<grid, kConvThreads, S::kTotal, stream>>>(p);
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }
 
 inline int launch_conv_tc(const ConvParams& p, int bn, int num_sms, cudaStream_t stream) {
+  const bool ex = conv_needs_extras(p);
   switch (bn) {
-    case 192: return launch_conv_tc_t<192, 4>(p, num_sms, stream);
-    case 128: return launch_conv_tc_t<128, 5>(p, num_sms, stream);
-    case 64: return launch_conv_tc_t<64, 6>(p, num_sms, stream);
+    case 192: return ex ? launch_conv_tc_t<192, 4, true>(p, num_sms, stream)
+                        : launch_conv_tc_t<192, 4, false>(p, num_sms, stream);
+    case 128: return ex ? launch_conv_tc_t<128, 5, true>(p, num_sms, stream)
+                        : launch_conv_tc_t<128, 5, false>(p, num_sms, stream);
+    case 64: return ex ? launch_conv_tc_t<64, 6, true>(p, num_sms, stream)
+                       : launch_conv_tc_t<64, 6, false>(p, num_sms, stream);
   }
   return fail("launch_conv_tc: unsupported BN");
 }

@@ -109,10 +109,10 @@ struct Conv2Smem {
   static constexpr int kOutBytes = (BN / 64) * kBM * 128;
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
-  static constexpr int kTotal = kBiasOffset + 2 * BN * 4 + 1024;
+  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool EXTRAS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   using S = Conv2Smem<BN, STAGES>;
@@ -235,15 +235,12 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       const int n_chan0 = (n_tile - par * p.n_tiles_par) * BN;
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
-      if (etid < BN) {
-        s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
-        s_bias[BN + etid] = p.rs_c2 ? __ldg(p.rs_c2 + n_chan0 + etid) : 0.f;
-      }
+      if (etid < BN) s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
       if (etid == 0) tma_store_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      conv_epilogue_tile<BN>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
+      conv_epilogue_tile<BN, EXTRAS>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       // this CTA's accumulator half is drained: tell the leader's MMA warp
       tc_fence_before();
       __syncwarp();
@@ -270,28 +267,32 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   if (warp == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool EXTRAS>
 inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using S = Conv2Smem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    NOPE_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES>,
+    NOPE_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, EXTRAS>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = num_sms / 2;
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
-  conv_tc2_kernel<BN, STAGES><<<2 * clusters, kConvThreads, S::kTotal, stream>>>(p);
+  conv_tc2_kernel<BN, STAGES, EXTRAS><<<2 * clusters, kConvThreads, S::kTotal, stream>>>(p);
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }
 
 inline int launch_conv_tc2(const ConvParams& p, int bn, int num_sms, cudaStream_t stream) {
+  const bool ex = conv_needs_extras(p);
   switch (bn) {
-    case 192: return launch_conv_tc2_t<192, 6>(p, num_sms, stream);
-    case 128: return launch_conv_tc2_t<128, 7>(p, num_sms, stream);
-    case 64: return launch_conv_tc2_t<64, 8>(p, num_sms, stream);
+    case 192: return ex ? launch_conv_tc2_t<192, 6, true>(p, num_sms, stream)
+                        : launch_conv_tc2_t<192, 6, false>(p, num_sms, stream);
+    case 128: return ex ? launch_conv_tc2_t<128, 7, true>(p, num_sms, stream)
+                        : launch_conv_tc2_t<128, 7, false>(p, num_sms, stream);
+    case 64: return ex ? launch_conv_tc2_t<64, 8, true>(p, num_sms, stream)
+                       : launch_conv_tc2_t<64, 8, false>(p, num_sms, stream);
   }
   return fail("launch_conv_tc2: unsupported BN");
 }

@@ -24,19 +24,6 @@ using namespace nope;
 
 namespace {
 
-// optional epilogue extras of one convolution launch (see ConvParams)
-struct ConvExtras {
-  const __half* res_hi = nullptr;
-  const __half* res_lo = nullptr;
-  const int* res_map = nullptr;
-  int res_hw = 0;
-  __half* out_lo = nullptr;
-  // folded GroupNorm(1, C) pre-norm (see ConvParams::rs_stats)
-  const float2* rs_stats = nullptr;
-  int rs_parts = 0, rs_hw = 0;
-  float rs_inv_cnt = 0.f;
-};
-
 constexpr int kAbiVersion = 1;
 constexpr int kHeadsHidden = 128;  // 4 heads x 32 (model_utils.py:368,394)
 
@@ -50,7 +37,6 @@ struct ConvLayer {
   int cin = 0, cout = 0, K = 0, bn = 0;
   __half* w = nullptr;    // [cout][K] fp16
   float* bias = nullptr;  // [cout] fp32 or nullptr
-  float* c2 = nullptr;    // folded pre-norm only: c2[n] = sum_c W'[n, c] (fp16-rounded W')
   CUtensorMap wmap;
   CUtensorMap wmap_half;  // BN/2-row box for the 2-CTA kernel
   bool has_map = false;
@@ -96,7 +82,6 @@ struct nope_unet {
   __half *TA = nullptr, *TB = nullptr, *TC = nullptr, *TD = nullptr, *XA = nullptr, *XB = nullptr,
          *RB = nullptr, *cs = nullptr, *pb = nullptr;
   __half *x0 = nullptr, *g1 = nullptr, *pt = nullptr;  // per-reference pre-stage
-  __half *rc1h = nullptr, *rc1l = nullptr, *rc2h = nullptr, *rc2l = nullptr;  // r halves of final_res_block
   float2* gn_partial = nullptr;   // gn_stats_kernel output (per-op test path only)
   float2 *SA = nullptr, *SB = nullptr;   // fused statistics: conv epilogue / gn_apply emit
   int* ref_of = nullptr;
@@ -215,22 +200,6 @@ struct nope_unet {
                          cudaMemcpyHostToDevice));
     return 0;
   }
-  // host[dst] = host[src][:, lo:hi, :, :]
-  int slice_cin(const std::string& src, const std::string& dst, int lo, int hi) {
-    auto it = host.find(src);
-    NOPE_CHECK(it != host.end(), "missing tensor " + src);
-    const auto& sh = it->second.shape;
-    const int cout = (int)sh[0], cin = (int)sh[1], taps = (int)(sh[2] * sh[3]);
-    NOPE_CHECK(lo >= 0 && hi <= cin && lo < hi, "slice_cin: bad range");
-    HostTensor t;
-    t.shape = {cout, hi - lo, sh[2], sh[3]};
-    t.data.resize((size_t)cout * (hi - lo) * taps);
-    for (int o = 0; o < cout; ++o)
-      std::memcpy(&t.data[(size_t)o * (hi - lo) * taps], &it->second.data[((size_t)o * cin + lo) * taps],
-                  sizeof(float) * (size_t)(hi - lo) * taps);
-    host[dst] = std::move(t);
-    return 0;
-  }
   // pack one conv weight (+ bias) into a ConvLayer.  mode 3 (nearest-x2 upsample + conv3x3,
   // HardUpsample) first folds the 3x3 kernel into four 2x2 parity kernels (fold_upconv_kernel).
   int make_conv(const std::string& name, const std::string& wkey, const std::string& bkey, int mode) {
@@ -276,41 +245,6 @@ struct nope_unet {
     convs[name] = L;
     return 0;
   }
-  // PreNorm(GroupNorm(1, C)) followed by a bias-free 1x1 conv (to_qkv), folded:
-  //   conv(GN(x))[n] = rstd (W' x)[n] + c1[n] - rstd mean c2[n],  W' = W diag(gamma),
-  //   c1 = W beta, c2[n] = sum_c fp16(W'[n, c])  -- the conv then reads x directly and the
-  // normalised tensor is never materialised (model_utils.py:226-234, 399).
-  int make_prenorm_conv(const std::string& name, const std::string& wkey, const std::string& normprefix) {
-    const HostTensor& W = host.at(wkey);
-    const auto& g = host.at(normprefix + ".weight").data;
-    const auto& b = host.at(normprefix + ".bias").data;
-    const int cout = (int)W.shape[0], cin = (int)W.shape[1];
-    HostTensor Wf, c1;
-    Wf.shape = W.shape;
-    Wf.data.resize(W.data.size());
-    c1.shape = {cout};
-    c1.data.resize(cout);
-    std::vector<float> c2(cout);
-    for (int o = 0; o < cout; ++o) {
-      double a1 = 0.0, a2 = 0.0;
-      for (int c = 0; c < cin; ++c) {
-        const float wf = W.data[(size_t)o * cin + c] * g[c];
-        Wf.data[(size_t)o * cin + c] = wf;
-        a1 += (double)W.data[(size_t)o * cin + c] * (double)b[c];
-        a2 += (double)__half2float(__float2half_rn(wf));
-      }
-      c1.data[o] = (float)a1;
-      c2[o] = (float)a2;
-    }
-    host["__pn." + wkey] = std::move(Wf);
-    host["__pn." + wkey + ".c1"] = std::move(c1);
-    if (make_conv(name, "__pn." + wkey, "__pn." + wkey + ".c1", 1)) return -1;
-    ConvLayer& L = convs[name];
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.c2), cout * sizeof(float)));
-    owned.push_back(L.c2);
-    NOPE_CUDA(cudaMemcpy(L.c2, c2.data(), cout * sizeof(float), cudaMemcpyHostToDevice));
-    return 0;
-  }
   int make_norm(const std::string& name, const std::string& prefix, int G) {
     NormLayer n;
     auto it = host.find(prefix + ".weight");
@@ -335,7 +269,6 @@ struct nope_unet {
   int make_linattn(const std::string& p) {
     if (make_norm(p + ".prenorm", p + ".fn.norm", 1)) return -1;
     if (make_conv(p + ".qkv", p + ".fn.fn.to_qkv.weight", "", 1)) return -1;
-    if (make_prenorm_conv(p + ".qkvf", p + ".fn.fn.to_qkv.weight", p + ".fn.norm")) return -1;
     if (make_conv(p + ".out", p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", 1)) return -1;
     if (make_norm(p + ".outnorm", p + ".fn.fn.to_out.1", 1)) return -1;
     return 0;
@@ -394,7 +327,6 @@ struct nope_unet {
     if (make_resblock("mid_block1") || make_resblock("mid_block2")) return -1;
     if (make_norm("mid_attn.prenorm", "mid_attn.fn.norm", 1)) return -1;
     if (make_conv("mid_attn.qkv", "mid_attn.fn.fn.to_qkv.weight", "", 1)) return -1;
-    if (make_prenorm_conv("mid_attn.qkvf", "mid_attn.fn.fn.to_qkv.weight", "mid_attn.fn.norm")) return -1;
     if (make_conv("mid_attn.out", "mid_attn.fn.fn.to_out.weight", "mid_attn.fn.fn.to_out.bias", 1))
       return -1;
     for (int j = 0; j < 4; ++j) {
@@ -407,19 +339,6 @@ struct nope_unet {
       }
     }
     if (make_resblock("final_res_block") || make_resblock("final_conv.0")) return -1;
-    // final_res_block sees cat(x, r) (u_net.py:194-195) with r = init_conv(reference) shared by
-    // every hypothesis of a reference: split its two convs over cat() along Cin so the r halves
-    // run once per reference (prestage) and enter the per-hypothesis convs as a residual.
-    if (slice_cin("final_res_block.block1.proj.weight", "__frb.b1x", 0, dim) ||
-        slice_cin("final_res_block.block1.proj.weight", "__frb.b1r", dim, 2 * dim) ||
-        slice_cin("final_res_block.res_conv.weight", "__frb.rx", 0, dim) ||
-        slice_cin("final_res_block.res_conv.weight", "__frb.rr", dim, 2 * dim))
-      return -1;
-    if (make_conv("final_res_block.block1x", "__frb.b1x", "final_res_block.block1.proj.bias", 0) ||
-        make_conv("final_res_block.block1r", "__frb.b1r", "", 0) ||
-        make_conv("final_res_block.resx", "__frb.rx", "final_res_block.res_conv.bias", 1) ||
-        make_conv("final_res_block.resr", "__frb.rr", "", 1))
-      return -1;
     if (make_poseproj()) return -1;
     host.clear();
     finalized = true;
@@ -459,9 +378,7 @@ struct nope_unet {
         ws_alloc_half(&cs, c * cemb) || ws_alloc_half(&pb, c * P))
       return -1;
     const size_t r = (size_t)cap_ref;
-    if (ws_alloc_half(&x0, r * xsz) || ws_alloc_half(&g1, r * xsz) || ws_alloc_half(&pt, r * xsz) ||
-        ws_alloc_half(&rc1h, r * xsz) || ws_alloc_half(&rc1l, r * xsz) ||
-        ws_alloc_half(&rc2h, r * xsz) || ws_alloc_half(&rc2l, r * xsz))
+    if (ws_alloc_half(&x0, r * xsz) || ws_alloc_half(&g1, r * xsz) || ws_alloc_half(&pt, r * xsz))
       return -1;
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&gn_partial),
                          (size_t)std::max(cap, cap_ref) * 8 * 8 * sizeof(float2)));
@@ -495,11 +412,9 @@ struct nope_unet {
   // ------------------------------------------------------------------ op launchers
   // out[n_img, So, So, cout] = conv(L, in0 (++ in1))
   int conv(const ConvLayer& L, const __half* in0, int c0, const __half* in1, int c1, __half* out,
-           int So, int n_img, int cap_img, cudaStream_t st, float2* stats = nullptr,
-           const ConvExtras* ex = nullptr) {
+           int So, int n_img, int cap_img, cudaStream_t st, float2* stats = nullptr) {
     NOPE_CHECK(c0 + c1 == L.cin, "conv: channel mismatch");
     ++launches;
-    NOPE_CHECK(!(ex && (conv_impl == 1 || L.mode == 3)), "conv extras need the tcgen05 kernel, n_par == 1");
     if (conv_impl == 1) {
       SimtConvArgs a;
       a.src0 = in0; a.src1 = in1; a.C0 = c0; a.C1 = c1; a.w = L.w; a.bias = L.bias; a.out = out;
@@ -582,15 +497,6 @@ struct nope_unet {
     p.stats_noct = L.cout / 8;
     p.n_total = L.cout;
     p.m_valid = n_img * So * So;
-    if (ex) {
-      p.res_hi = ex->res_hi; p.res_lo = ex->res_lo; p.res_map = ex->res_map; p.res_hw = ex->res_hw;
-      p.out_lo = ex->out_lo;
-      if (ex->rs_stats) {
-        NOPE_CHECK(L.c2 != nullptr, "folded pre-norm needs a layer built by make_prenorm_conv");
-        p.rs_stats = ex->rs_stats; p.rs_parts = ex->rs_parts; p.rs_hw = ex->rs_hw;
-        p.rs_inv_cnt = ex->rs_inv_cnt; p.rs_eps = 1e-5f; p.rs_c2 = L.c2;
-      }
-    }
     p.nseg = nseg;
     p.ksteps = ksteps;
     p.m_tiles = geom_m_tiles(g, n_img);
@@ -702,28 +608,13 @@ struct nope_unet {
               emit_g1 ? SB : nullptr);
   }
 
-  // TD = to_qkv(GroupNorm(1, C)(x)).  tcgen05 paths: the norm is folded into the conv (weights
-  // scaled by gamma, per-hypothesis rstd / mean applied in the epilogue from the SB partial sums
-  // the producer of x emitted); the SIMT twin keeps the explicit two-step form.
-  int qkv_prenorm(const std::string& p, const __half* x, int C, int S, int n, cudaStream_t st) {
-    if (conv_impl == 1) {
-      if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
-             emit_parts_of(S * S), 1))
-        return -1;
-      return conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st);
-    }
-    ConvExtras e;
-    e.rs_stats = SB;
-    e.rs_parts = emit_parts_of(S * S);
-    e.rs_hw = S * S;
-    e.rs_inv_cnt = 1.0f / ((float)(S * S) * (float)C);
-    return conv(convs.at(p + ".qkvf"), x, C, nullptr, 0, TD, S, n, cap, st, nullptr, &e);
-  }
-
   // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418).  x's GroupNorm(1) statistics
   // were emitted into SB by the producer of x; to_out[1]'s come from the to_out conv epilogue.
   int linattn(const std::string& p, const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
-    if (qkv_prenorm(p, x, C, S, n, st)) return -1;
+    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
+           emit_parts_of(S * S), 1))
+      return -1;
+    if (conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
     linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD, TC, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
@@ -735,7 +626,10 @@ struct nope_unet {
   // Residual(PreNorm(Attention)) (model_utils.py:367-390)
   int midattn(const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
     NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
-    if (qkv_prenorm("mid_attn", x, C, S, n, st)) return -1;
+    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
+           emit_parts_of(S * S), 1))
+      return -1;
+    if (conv(convs.at("mid_attn.qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
     midattn_kernel<<<n, 128, 0, st>>>(TD, TC, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
@@ -751,21 +645,8 @@ struct nope_unet {
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     if (conv(convs.at("downs.0.0.block1"), x0, dim, nullptr, 0, pt, S0, B, cap_ref, st, SA)) return -1;
-    if (gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st, SA,
-           st_parts_of(S0), dim / 8))
-      return -1;
-    if (conv_impl != 1) {
-      // r halves of final_res_block's convs over cat(x, r), kept as fp16 (hi, lo) pairs so the
-      // later fp32 add in the per-hypothesis epilogue loses nothing
-      ConvExtras e1, e2;
-      e1.out_lo = rc1l;
-      e2.out_lo = rc2l;
-      if (conv(convs.at("final_res_block.block1r"), x0, dim, nullptr, 0, rc1h, S0, B, cap_ref, st, nullptr, &e1))
-        return -1;
-      if (conv(convs.at("final_res_block.resr"), x0, dim, nullptr, 0, rc2h, S0, B, cap_ref, st, nullptr, &e2))
-        return -1;
-    }
-    return 0;
+    return gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st, SA,
+              st_parts_of(S0), dim / 8);
   }
 
   // UNet.forward for hypotheses [hyp0, hyp0 + n) of the flattened (b, pose) list
@@ -782,17 +663,13 @@ struct nope_unet {
 
     // r (= init_conv output) and the hoisted block1 output, broadcast per hypothesis
     const int hw0 = S0 * S0;
-    const bool need_rb = conv_impl == 1 || (tap_out && tap_name == "init_conv");
-    if (need_rb) {   // r per hypothesis: only the SIMT twin (no epilogue extras) and the debug tap
-      bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-          x0, ref_of, nullptr, 0, 0, RB, n, hw0, dim);
-      ++launches;
-    }
+    bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
+        x0, ref_of, nullptr, 0, 0, RB, n, hw0, dim);
     bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
         g1, ref_of, pb, P, pb_off.at("downs.0.0"), TB, n, hw0, dim);
     NOPE_CUDA(cudaGetLastError());
-    ++launches;
-    if (need_rb && tap("init_conv", RB, dim, S0, n, st)) return -1;
+    launches += 2;
+    if (tap("init_conv", RB, dim, S0, n, st)) return -1;
 
     // ---- downs
     __half* cur = nullptr;
@@ -852,26 +729,7 @@ struct nope_unet {
       if (tap((p + ".3").c_str(), cur, din, S, n, st)) return -1;
     }
     // ---- head
-    if (conv_impl == 1) {
-      if (resblock("final_res_block", cur, dim, RB, dim, oth, S, n, true, st)) return -1;
-    } else {
-      // ResnetBlock over cat(x, r) with the r halves of both convs hoisted per reference:
-      // conv(cat(x, r)) = conv_x(x) + conv_r(r); the hoisted half enters as an epilogue residual
-      // (before the GroupNorm partial sums, which must see the full conv output).
-      const std::string p = "final_res_block";
-      const int parts = st_parts_of(S);
-      ConvExtras e1, e2;
-      e1.res_hi = rc1h; e1.res_lo = rc1l; e1.res_map = ref_of; e1.res_hw = S * S;
-      e2.res_hi = rc2h; e2.res_lo = rc2l; e2.res_map = ref_of; e2.res_hw = S * S;
-      if (conv(convs.at(p + ".block1x"), cur, dim, nullptr, 0, TA, S, n, cap, st, SA, &e1)) return -1;
-      if (gn(&norms.at(p + ".norm1"), TA, TB, S, dim, n, true, pb_off.at(p), nullptr, nullptr, st, SA, parts,
-             dim / 8))
-        return -1;
-      if (conv(convs.at(p + ".block2"), TB, dim, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
-      if (conv(convs.at(p + ".resx"), cur, dim, nullptr, 0, TC, S, n, cap, st, nullptr, &e2)) return -1;
-      if (gn(&norms.at(p + ".norm2"), TA, oth, S, dim, n, true, -1, TC, nullptr, st, SA, parts, dim / 8))
-        return -1;
-    }
+    if (resblock("final_res_block", cur, dim, RB, dim, oth, S, n, true, st)) return -1;
     std::swap(cur, oth);
     if (tap("final_res_block", cur, dim, S, n, st)) return -1;
     if (resblock("final_conv.0", cur, dim, nullptr, 0, oth, S, n, false, st)) return -1;
