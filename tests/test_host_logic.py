@@ -1,0 +1,61 @@
+"""CPU: host-side behaviour of the reference-facing Python surface that needs no GPU --
+constructor validation, error conventions, no silent fallback."""
+import pytest
+import torch
+
+from nope_b200 import NopeError
+from nope_b200.encoder import FeatureExtractor
+from nope_b200.model import PoseConditional, score_topk
+from nope_b200.unet import UNet
+
+
+def _unet(**kw):
+    args = dict(u_net_dim=192, rot_representation_dim=6, encoder=FeatureExtractor(descriptor_size=8),
+                pose_mlp_name="single_layer", device="cuda:0")
+    args.update(kw)
+    return UNet(**args)
+
+
+def test_unet_keeps_reference_attributes():
+    u = _unet()
+    assert u.channels == 8 and u.name == "template" and u.encoder.latent_dim == 8
+    assert callable(u) and hasattr(u.encoder, "encode_image")
+
+
+@pytest.mark.parametrize("kw", [dict(pose_mlp_name="two_layers"), dict(pose_mlp_name="posEncoding"),
+                                dict(rot_representation_dim=4), dict(dim_mults=(1, 2, 4)),
+                                dict(use_hard_up_down=False), dict(resnet_block_groups=4)])
+def test_unsupported_unet_configurations_are_rejected(kw):
+    with pytest.raises(ValueError):
+        _unet(**kw)
+
+
+def test_unknown_similarity_metric_raises_instead_of_returning_none():
+    # the reference's retrieval() falls through and returns None (src/model/model.py:256)
+    m = PoseConditional(_unet(), testing_config={"similarity_metric": "dot"})
+    with pytest.raises(ValueError):
+        m.retrieval(torch.zeros(1, 3, 256, 256), torch.zeros(1, 6, 8, 32, 32))
+    with pytest.raises(ValueError):
+        m.predict_pose(torch.zeros(1, 3, 256, 256), torch.zeros(1, 3, 256, 256), torch.zeros(1, 6, 6))
+    with pytest.raises(ValueError):
+        score_topk(torch.zeros(1, 8, 32, 32), torch.zeros(1, 6, 8, 32, 32), metric="dot")
+
+
+def test_no_cpu_fallback_for_the_hot_path():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(NopeError):
+        score_topk(torch.zeros(1, 8, 32, 32), torch.zeros(1, 6, 8, 32, 32))     # CPU tensors
+    u = _unet()
+    with pytest.raises(NopeError):
+        u.sweep(torch.zeros(1, 8, 32, 32), torch.zeros(1, 3, 6))                 # not loaded / no GPU
+    with pytest.raises(NopeError):
+        FeatureExtractor(descriptor_size=8, backend="b200").encode_image(torch.zeros(1, 3, 256, 256))
+
+
+def test_loss_type_and_compute_loss():
+    m = PoseConditional(_unet(), optim_config={"loss_type": "l2"})
+    a, b = torch.ones(2, 8, 32, 32), torch.zeros(2, 8, 32, 32)
+    assert float(m.compute_loss(a, b)) == 1.0
+    m1 = PoseConditional(_unet(), optim_config={"loss_type": "l1"})
+    assert float(m1.compute_loss(a * 3, b)) == 3.0
