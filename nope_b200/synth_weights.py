@@ -203,3 +203,147 @@ def checksum(sd):
         if v.dtype.is_floating_point:
             acc += float(v.double().sum()) * (1 + (i % 7)) + float(v.double().abs().sum())
     return acc
+
+
+# ---------------------------------------------------------------------------------------
+# LDM variant: UNetModelPose (reference: src/model/u_net/ldm/adapt_openaimodel.py:14-125,
+# src/model/u_net/ldm/openaimodel.py:428-760, src/model/u_net/ldm/attention.py:149-277;
+# configs/model/vae_cin_ldm.yaml:2-31)
+# ---------------------------------------------------------------------------------------
+def _ldm_resblock_shapes(p, cin, cout, temb):
+    s = OrderedDict()
+    s[f"{p}.in_layers.0.weight"] = (cin,)
+    s[f"{p}.in_layers.0.bias"] = (cin,)
+    s[f"{p}.in_layers.2.weight"] = (cout, cin, 3, 3)
+    s[f"{p}.in_layers.2.bias"] = (cout,)
+    s[f"{p}.emb_layers.1.weight"] = (cout, temb)
+    s[f"{p}.emb_layers.1.bias"] = (cout,)
+    s[f"{p}.out_layers.0.weight"] = (cout,)
+    s[f"{p}.out_layers.0.bias"] = (cout,)
+    s[f"{p}.out_layers.3.weight"] = (cout, cout, 3, 3)
+    s[f"{p}.out_layers.3.bias"] = (cout,)
+    if cin != cout:
+        s[f"{p}.skip_connection.weight"] = (cout, cin, 1, 1)
+        s[f"{p}.skip_connection.bias"] = (cout,)
+    return s
+
+
+def _ldm_transformer_shapes(p, c, ctx):
+    s = OrderedDict()
+    s[f"{p}.norm.weight"] = (c,)
+    s[f"{p}.norm.bias"] = (c,)
+    s[f"{p}.proj_in.weight"] = (c, c, 1, 1)
+    s[f"{p}.proj_in.bias"] = (c,)
+    t = f"{p}.transformer_blocks.0"
+    for a, kdim in (("attn1", c), ("attn2", ctx)):
+        s[f"{t}.{a}.to_q.weight"] = (c, c)
+        s[f"{t}.{a}.to_k.weight"] = (c, kdim)
+        s[f"{t}.{a}.to_v.weight"] = (c, kdim)
+        s[f"{t}.{a}.to_out.0.weight"] = (c, c)
+        s[f"{t}.{a}.to_out.0.bias"] = (c,)
+    s[f"{t}.ff.net.0.proj.weight"] = (8 * c, c)
+    s[f"{t}.ff.net.0.proj.bias"] = (8 * c,)
+    s[f"{t}.ff.net.2.weight"] = (c, 4 * c)
+    s[f"{t}.ff.net.2.bias"] = (c,)
+    for n in ("norm1", "norm2", "norm3"):
+        s[f"{t}.{n}.weight"] = (c,)
+        s[f"{t}.{n}.bias"] = (c,)
+    s[f"{p}.proj_out.weight"] = (c, c, 1, 1)
+    s[f"{p}.proj_out.bias"] = (c,)
+    return s
+
+
+def ldm_block_plan(model_channels=256, channel_mult=(1, 2, 4), num_res_blocks=2):
+    """The module list UNetModel.__init__ builds (openaimodel.py:543-719) for attention at every
+    level (vae_cin_ldm.yaml:8-16), as plain tuples:
+      input:  ("conv"|"res"|"down", cin, cout)   -- "res" is ResBlock + SpatialTransformer
+      middle: [("res", ch, ch), ("st", ch), ("res", ch, ch)]
+      output: ("res", cin_total, cout, skip_ch, upsample)"""
+    mc = model_channels
+    inp = [("conv", None, mc)]
+    chans = [mc]
+    ch = mc
+    for level, mult in enumerate(channel_mult):
+        for _ in range(num_res_blocks):
+            inp.append(("res", ch, mult * mc))
+            ch = mult * mc
+            chans.append(ch)
+        if level != len(channel_mult) - 1:
+            inp.append(("down", ch, ch))
+            chans.append(ch)
+    mid_ch = ch
+    out = []
+    for level, mult in list(enumerate(channel_mult))[::-1]:
+        for i in range(num_res_blocks + 1):
+            ich = chans.pop()
+            out.append(("res", ch + ich, mc * mult, ich, bool(level and i == num_res_blocks)))
+            ch = mc * mult
+    return inp, mid_ch, out
+
+
+def ldm_param_shapes(model_channels=256, channel_mult=(1, 2, 4), num_res_blocks=2, in_channels=4,
+                     out_channels=4, context_dim=512, rot_dim=6):
+    """Key -> shape of UNetModelPose.state_dict() without the (stubbed) encoder."""
+    mc = model_channels
+    temb = 4 * mc
+    inp, mid_ch, out = ldm_block_plan(mc, channel_mult, num_res_blocks)
+    s = OrderedDict()
+    s["time_embed.0.weight"] = (temb, mc)      # present in the state_dict, unused by forward
+    s["time_embed.0.bias"] = (temb,)           # (adapt_openaimodel.py:139-146: emb = zeros)
+    s["time_embed.2.weight"] = (temb, temb)
+    s["time_embed.2.bias"] = (temb,)
+    for i, b in enumerate(inp):
+        p = f"input_blocks.{i}"
+        if b[0] == "conv":
+            s[f"{p}.0.weight"] = (mc, in_channels, 3, 3)
+            s[f"{p}.0.bias"] = (mc,)
+        elif b[0] == "res":
+            s.update(_ldm_resblock_shapes(f"{p}.0", b[1], b[2], temb))
+            s.update(_ldm_transformer_shapes(f"{p}.1", b[2], context_dim))
+        else:
+            s[f"{p}.0.op.weight"] = (b[2], b[1], 3, 3)
+            s[f"{p}.0.op.bias"] = (b[2],)
+    s.update(_ldm_resblock_shapes("middle_block.0", mid_ch, mid_ch, temb))
+    s.update(_ldm_transformer_shapes("middle_block.1", mid_ch, context_dim))
+    s.update(_ldm_resblock_shapes("middle_block.2", mid_ch, mid_ch, temb))
+    for i, b in enumerate(out):
+        p = f"output_blocks.{i}"
+        s.update(_ldm_resblock_shapes(f"{p}.0", b[1], b[2], temb))
+        s.update(_ldm_transformer_shapes(f"{p}.1", b[2], context_dim))
+        if b[4]:
+            s[f"{p}.2.conv.weight"] = (b[2], b[2], 3, 3)
+            s[f"{p}.2.conv.bias"] = (b[2],)
+    s["out.0.weight"] = (mc,)
+    s["out.0.bias"] = (mc,)
+    s["out.2.weight"] = (out_channels, mc, 3, 3)
+    s["out.2.bias"] = (out_channels,)
+    s["pose_mlp.0.weight"] = (context_dim, rot_dim)
+    s["pose_mlp.0.bias"] = (context_dim,)
+    return s
+
+
+def _fill_ldm(name, shape, g):
+    u = lambda: torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1
+    leaf = name.rsplit(".", 1)[-1]
+    if len(shape) == 1 and any(t in name for t in (".in_layers.0.", ".out_layers.0.", ".norm.",
+                                                    ".norm1.", ".norm2.", ".norm3.", "out.0.")):
+        return (1.0 + 0.2 * u()) if leaf == "weight" else 0.2 * u()
+    if leaf == "weight":
+        fan_in = 1
+        for d in shape[1:]:
+            fan_in *= d
+        # unit-variance outputs (the reference zero-initialises out_layers.3 / proj_out / out.2,
+        # openaimodel.py:241-245,722-726 + attention.py:243-245, which would make the whole net a
+        # no-op: every layer gets live weights here); q/k a little hotter so the softmax over
+        # tokens is far from uniform
+        gain = math.sqrt(3.0) * (1.5 if (".to_q." in name or ".to_k." in name) else 1.0)
+        if ".proj_out." in name or ".out_layers.3." in name or ".ff.net.2." in name or ".to_out." in name:
+            gain *= 0.5     # residual branches: keep the residual stream's growth moderate
+        return u() * (gain / math.sqrt(fan_in))
+    return u() * 0.1
+
+
+def make_ldm_state_dict(seed=0, model_channels=256, channel_mult=(1, 2, 4), context_dim=512):
+    g = torch.Generator(device="cpu").manual_seed(3000 + seed)
+    return OrderedDict((k, _fill_ldm(k, shp, g)) for k, shp in
+                       ldm_param_shapes(model_channels, channel_mult, context_dim=context_dim).items())

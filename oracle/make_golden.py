@@ -12,6 +12,8 @@ Writes:
   tests/golden/grid26_b2.npz    B=2, N=26 'upper' level-0 grid: scores, top-5, embedding
                                 digests + two full templates
   tests/golden/unet_taps.npz    per-layer activation statistics of one UNet forward
+  tests/golden/ldm_b1_n3.npz    (--only-ldm) LDM-variant UNet (UNetModelPose): 3 hypotheses, embeddings,
+                                scores, per-block activation statistics
   tests/golden/meta.json        weight checksum, torch version, oracle-vs-reference errors
 It asserts (hard failure) that
   * the seeded state_dict loads into the reference modules with strict=True
@@ -101,7 +103,54 @@ def write_full_grid_fixture():
     return {"reference_cpu_seconds": secs, "top5": idx.tolist(), "min_rel_gap_top6": gap}
 
 
+def make_ldm_inputs(seed, batch, n):
+    """Seeded LDM-variant inputs: VAE-like latents N(0,1) [B,4,32,32] (the diffusers VAE itself
+    is absent, see ref_import.build_reference_ldm_unet) and [B,n,6] level-0 relative poses."""
+    g = torch.Generator(device="cpu").manual_seed(5000 + seed)
+    ref_lat = torch.randn((batch, 4, 32, 32), generator=g)
+    query_lat = torch.randn((batch, 4, 32, 32), generator=g)
+    relR, _ = inputs.make_pose_batch("level0_upper", batch=batch, n=n)
+    return ref_lat, query_lat, relR
+
+
+def write_ldm_fixture():
+    """tests/golden/ldm_b1_n3.npz: three hypotheses through the UNMODIFIED UNetModelPose
+    (src/model/u_net/ldm/adapt_openaimodel.py:127-158, wired as configs/model/vae_cin_ldm.yaml)
+    with the seeded weights of nope_b200.synth_weights.make_ldm_state_dict loaded strict=True,
+    scored with the reference's l2 formula (model.py:259-264 restated in unet_oracle), and the
+    restatement in oracle/ldm_oracle.py checked against it."""
+    from . import ldm_oracle
+    from .ref_import import build_reference_ldm_unet
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.time()
+    m = build_reference_ldm_unet()
+    sd = weights.make_ldm_state_dict(seed=0)
+    print("load_state_dict strict:", m.load_state_dict(sd, strict=True), f"{time.time() - t0:.0f}s")
+    ref_lat, query_lat, relR = make_ldm_inputs(0, 1, 3)
+    with torch.no_grad():
+        t0 = time.time()
+        emb_ref = m(ref_lat.expand(3, -1, -1, -1), relR[0])
+        secs = time.time() - t0
+        taps = {}
+        emb = ldm_oracle.ldm_forward(sd, ref_lat.expand(3, -1, -1, -1), relR[0], taps=taps)
+    err = rel_err(emb, emb_ref)
+    sim = orc.l2_similarity(query_lat, emb_ref[None])
+    tap_stats = {"tap:" + k: np.array([float(v.mean()), float(v.std()), float(v.abs().max())])
+                 for k, v in taps.items()}
+    np.savez_compressed(os.path.join(OUT, "ldm_b1_n3.npz"), ref_latent=ref_lat.numpy(),
+                        query_latent=query_lat.numpy(), all_relativeR=relR.numpy(),
+                        emb=emb_ref.numpy(), similarity=sim.numpy(), **tap_stats)
+    out = {"oracle_vs_reference_rel_err": err, "reference_cpu_seconds_3hyp": secs,
+           "weights_checksum_seed0": weights.checksum(sd), "emb_std": float(emb_ref.std()),
+           "emb_absmax": float(emb_ref.abs().max())}
+    assert err < 2e-5, f"ldm oracle disagrees with the reference: {err}"
+    return out
+
+
 def main():
+    if "--only-ldm" in sys.argv:
+        print(json.dumps(write_ldm_fixture(), indent=1))
+        return
     if "--only-full-grid" in sys.argv:
         torch.set_num_threads(os.cpu_count())
         print(json.dumps(write_full_grid_fixture(), indent=1))

@@ -121,6 +121,9 @@ def _install_stubs():
                  "ruamel.yaml", "omegaconf", "omegaconf.listconfig"):
         if _missing(name):
             _mod(name)
+    lc = sys.modules.get("omegaconf.listconfig")
+    if lc is not None and not hasattr(lc, "ListConfig"):
+        lc.ListConfig = type("ListConfig", (list,), {})   # openaimodel.py:495 only type-checks it
     if "moviepy.video.io.bindings" in sys.modules and not hasattr(
             sys.modules["moviepy.video.io.bindings"], "mplfig_to_npimage"):
         sys.modules["moviepy.video.io.bindings"].mplfig_to_npimage = lambda f: None
@@ -169,3 +172,28 @@ def build_reference_model(u_net_dim=192, descriptor_size=8, save_dir="/tmp/nope_
     model = ref.PoseConditional(u_net=unet, optim_config=optim,
                                 testing_config=testing, save_dir=save_dir)
     return model.eval()
+
+
+def build_reference_ldm_unet(model_channels=256, channel_mult=(1, 2, 4), context_dim=512,
+                             attention_resolutions=(4, 2, 1), num_res_blocks=2,
+                             num_head_channels=32):
+    """Reference UNetModelPose wired as configs/model/vae_cin_ldm.yaml:2-31 (encoder stubbed)."""
+    import torch
+    import_reference()
+    from src.model.u_net.ldm.adapt_openaimodel import UNetModelPose
+
+    class _LatentStub(torch.nn.Module):
+        # Stands in for VAE_StableDiffusion (src/model/encoder/AutoencoderKL.py:16-47, diffusers
+        # 0.14.0 AutoencoderKL: absent here): only `latent_dim` / `name` are read by
+        # UNetModelPose (adapt_openaimodel.py:123-125).  The LDM variant runs on latents.
+        latent_dim = 4
+        name = "VAE"
+
+    m = UNetModelPose(
+        injecting_condition_twice=False, pose_mlp_name="single_layer", rot_representation_dim=6,
+        encoder=_LatentStub(), image_size=32, in_channels=4, model_channels=model_channels,
+        out_channels=4, num_res_blocks=num_res_blocks,
+        attention_resolutions=list(attention_resolutions), channel_mult=list(channel_mult),
+        num_head_channels=num_head_channels, use_spatial_transformer=True, transformer_depth=1,
+        context_dim=context_dim)
+    return m.eval()
