@@ -155,6 +155,52 @@ int nope_unet_debug_tap(nope_unet_t* u, const float* ref_feat, const float* pose
                         const char* tap, float* out, int64_t out_capacity_floats,
                         int* out_C, int* out_H, void* stream);
 
+/* ---- LDM variant ------------------------------------------------------
+ * UNetModelPose (src/model/u_net/ldm/adapt_openaimodel.py:14-158 over ldm/openaimodel.py:428-760
+ * and ldm/attention.py:149-277; configs/model/vae_cin_ldm.yaml): ResBlocks + SpatialTransformers
+ * (self-attention on tcgen05, the one-token pose cross-attention folded to a per-hypothesis
+ * channel vector, GEGLU feed-forward), strided-conv down / nearest-x2+conv up, emb = 0.
+ * Supported configuration: channel_mult (1, 2, 4), 2 ResBlocks per level, attention at every
+ * level, num_head_channels 32, transformer_depth 1, injecting_condition_twice false,
+ * pose_mlp "single_layer", model_channels a multiple of 256, 32x32 latents.
+ * Keys are the reference's state_dict names (628 tensors for model_channels 256; the unused
+ * time_embed.* entries are accepted); HOST fp32 pointers, shape-checked.  The VAE encoder
+ * (diffusers AutoencoderKL, not part of the reference tree) is out of scope: the sweep takes
+ * latents.  Arguments of nope_ldm_sweep are those of nope_unet_sweep with
+ * ref_feat / query_feat = [B, latent_ch, 32, 32] latents. */
+typedef struct nope_ldm nope_ldm_t;
+int nope_ldm_create(nope_ldm_t** out, int model_channels, int context_dim, int latent_ch,
+                    int latent_hw, int device);
+void nope_ldm_destroy(nope_ldm_t* m);
+int nope_ldm_load_tensor(nope_ldm_t* m, const char* key, const float* data, const int64_t* shape,
+                         int ndim);
+int nope_ldm_finalize(nope_ldm_t* m);
+int nope_ldm_set_chunk(nope_ldm_t* m, int hyps_per_chunk);       /* ~20.5 MB workspace / hypothesis */
+/* conv_impl: 2 = tcgen05 CTA pairs (default), 0 = tcgen05 1-CTA tiles;
+ * attn_impl: 0 = tcgen05 attention (default), 1 = CUDA-core twin (bring-up). */
+int nope_ldm_set_impl(nope_ldm_t* m, int conv_impl, int attn_impl);
+int nope_ldm_sweep(nope_ldm_t* m, const float* ref_latent, const float* poses, int B, int N,
+                   const float* query_latent, float* out_emb, float* out_sim, int k,
+                   float* out_topv, int64_t* out_topi, int64_t idx_base, void* stream);
+int64_t nope_ldm_last_launch_count(const nope_ldm_t* m);
+/* Debug: as nope_unet_debug_tap; tap names follow the reference's module paths
+ * ("input_blocks.4.0" = ResBlock output, "input_blocks.4" = block output, "middle_block.1",
+ * "output_blocks.2.1", "output_blocks.2", ...). */
+int nope_ldm_debug_tap(nope_ldm_t* m, const float* ref_latent, const float* poses, int N,
+                       const char* tap, float* out, int64_t out_capacity_floats, int* out_C,
+                       int* out_H, void* stream);
+/* Debug / parity: run ONE module in isolation on fp32 NCHW device inputs.
+ *   name "<prefix>.0" of a ResBlock, "<prefix>.1" of a SpatialTransformer (poses [n, 6] needed),
+ *   "input_blocks.<i>.0.op" (Downsample), "output_blocks.<i>.2.conv" (Upsample; S = input side).
+ *   x0 [n, C0, S, S], x1 (optional, concatenated after x0) [n, C1, S, S] -> out fp32 NCHW.
+ * Synchronises the stream. */
+int nope_ldm_run_block(nope_ldm_t* m, const char* name, const float* x0, int C0, const float* x1,
+                       int C1, int S, int n, const float* poses, float* out, void* stream);
+/* Multi-head self-attention core (ldm/attention.py:177-194, heads of 32 channels):
+ * qkv [n_img, n_tok, 3C] fp32 (q | k | v) -> out [n_img, n_tok, C] fp32.  impl as attn_impl. */
+int nope_op_mh_attention(int impl, const float* qkv, float* out, int n_img, int n_tok, int C,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,20 @@ SIGNATURES = {
     "nope_op_linear_attention": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nope_op_attention": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nope_op_upsample2x": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nope_ldm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nope_ldm_destroy": (None, [C.c_void_p]),
+    "nope_ldm_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_f32p, C.POINTER(C.c_int64), C.c_int]),
+    "nope_ldm_finalize": (C.c_int, [C.c_void_p]),
+    "nope_ldm_set_chunk": (C.c_int, [C.c_void_p, C.c_int]),
+    "nope_ldm_set_impl": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "nope_ldm_sweep": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p,
+                                 c_f32p, C.c_int, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
+    "nope_ldm_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "nope_ldm_debug_tap": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_char_p, c_f32p,
+                                     C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    "nope_ldm_run_block": (C.c_int, [C.c_void_p, C.c_char_p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int,
+                                     C.c_int, c_f32p, c_f32p, C.c_void_p]),
+    "nope_op_mh_attention": (C.c_int, [C.c_int, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nope_unet_debug_tap": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_char_p, c_f32p,
                                       C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
 }

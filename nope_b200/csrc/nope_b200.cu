@@ -19,6 +19,7 @@
 #include "conv_tc2.cuh"
 #include "kernels.cuh"
 #include "encoder.cuh"
+#include "ldm.cuh"
 
 using namespace nope;
 
@@ -1213,6 +1214,212 @@ int nope_unet_debug_tap(nope_unet_t* u, const float* ref_feat, const float* pose
   NOPE_CHECK(u->tap_hit, std::string("unknown tap name: ") + tap);
   if (out_C) *out_C = u->tap_C;
   if (out_H) *out_H = u->tap_S;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// LDM variant
+// ---------------------------------------------------------------------------------
+int nope_ldm_create(nope_ldm_t** out, int model_channels, int context_dim, int latent_ch, int latent_hw,
+                    int device) {
+  NOPE_CHECK(out != nullptr, "null out pointer");
+  NOPE_CHECK(model_channels > 0 && model_channels % 256 == 0 && model_channels <= 512,
+             "model_channels must be 256 or 512 (GroupNorm(32) statistics ride on 8-channel octets)");
+  NOPE_CHECK(context_dim >= 1, "context_dim must be positive");
+  NOPE_CHECK(latent_ch >= 1 && latent_ch <= kMaxLatent, "latent_ch must be in [1, 8]");
+  NOPE_CHECK(latent_hw == 32, "latent_hw must be 32 in this build");
+  int ndev = 0;
+  NOPE_CUDA(cudaGetDeviceCount(&ndev));
+  NOPE_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+  cudaDeviceProp prop;
+  NOPE_CUDA(cudaGetDeviceProperties(&prop, device));
+  NOPE_CHECK(prop.major == 10, "nope_b200 kernels are built for sm_100a only");
+  auto m = std::make_unique<nope_ldm>();
+  m->mc = model_channels;
+  m->ctx = context_dim;
+  m->Cl = latent_ch;
+  m->S0 = latent_hw;
+  m->device = device;
+  m->num_sms = prop.multiProcessorCount;
+  m->build_plan();
+  m->build_schema();
+  *out = m.release();
+  return 0;
+}
+
+void nope_ldm_destroy(nope_ldm_t* m) { delete m; }
+
+int nope_ldm_load_tensor(nope_ldm_t* m, const char* key, const float* data, const int64_t* shape, int ndim) {
+  NOPE_CHECK(m && key && data && shape, "null argument");
+  NOPE_CHECK(!m->finalized, "engine already finalized");
+  auto it = m->expected.find(key);
+  NOPE_CHECK(it != m->expected.end(), std::string("unexpected state_dict key: ") + key);
+  NOPE_CHECK((int)it->second.size() == ndim, std::string("rank mismatch for ") + key);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    NOPE_CHECK(it->second[i] == shape[i], std::string("shape mismatch for ") + key);
+    n *= (size_t)shape[i];
+  }
+  if (std::strncmp(key, "time_embed.", 11) == 0 || std::strstr(key, ".emb_layers.1.weight") ||
+      std::strstr(key, ".attn2.to_q.") || std::strstr(key, ".attn2.to_k.") || std::strstr(key, ".norm2.")) {
+    // accepted for schema compatibility, never read: emb = 0 (adapt_openaimodel.py:143-146) and
+    // the one-token cross-attention does not depend on its queries / keys
+    m->host[key] = nope_ldm::HostT{std::vector<int64_t>(shape, shape + ndim), {}};
+    return 0;
+  }
+  auto& slot = m->host[key];
+  slot.first.assign(shape, shape + ndim);
+  slot.second.assign(data, data + n);
+  return 0;
+}
+
+int nope_ldm_finalize(nope_ldm_t* m) {
+  NOPE_CHECK(m, "null engine");
+  return m->finalize();
+}
+int nope_ldm_set_chunk(nope_ldm_t* m, int hyps) {
+  NOPE_CHECK(m && hyps >= 1 && hyps <= 2048, "chunk must be in [1, 2048]");
+  m->chunk = hyps;
+  return 0;
+}
+int nope_ldm_set_impl(nope_ldm_t* m, int conv_impl, int attn_impl) {
+  NOPE_CHECK(m && (conv_impl == 0 || conv_impl == 2), "conv_impl must be 0 (tcgen05) or 2 (tcgen05 2-CTA)");
+  NOPE_CHECK(attn_impl == 0 || attn_impl == 1, "attn_impl must be 0 (tcgen05) or 1 (CUDA cores)");
+  m->conv_impl = conv_impl;
+  m->attn_impl = attn_impl;
+  return 0;
+}
+int64_t nope_ldm_last_launch_count(const nope_ldm_t* m) { return m ? m->launches : 0; }
+
+int nope_ldm_sweep(nope_ldm_t* m, const float* ref_latent, const float* poses, int B, int N,
+                   const float* query_latent, float* out_emb, float* out_sim, int k, float* out_topv,
+                   int64_t* out_topi, int64_t idx_base, void* stream) {
+  NOPE_CHECK(m && m->finalized, "engine not finalized");
+  NOPE_CHECK(ref_latent && poses && B >= 1 && N >= 1, "bad arguments");
+  NOPE_CHECK(!(out_sim || k > 0) || query_latent, "scores / top-k need query_latent");
+  NOPE_CHECK(k >= 0 && k <= N && k <= 64, "k must be in [0, min(N, 64)]");
+  NOPE_CHECK(k == 0 || (out_topv && out_topi), "top-k outputs missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NOPE_CUDA(cudaSetDevice(m->device));
+  m->launches = 0;
+  const int total = B * N;
+  const int cap = std::min(m->chunk, total);
+  if (m->ensure_workspace(cap, B)) return -1;
+  const int hw = m->S0 * m->S0;
+  const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
+  float* part = nullptr;
+  if (query_latent) {
+    const size_t need = (size_t)total * nslab;
+    if (need > m->score_partial_cap) {
+      NOPE_CUDA(cudaStreamSynchronize(st));
+      if (m->score_partial) cudaFree(m->score_partial);
+      NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->score_partial), need * sizeof(float)));
+      m->score_partial_cap = need;
+    }
+    part = m->score_partial;
+  }
+  if (m->prestage(ref_latent, B, st)) return -1;
+  for (int h0 = 0; h0 < total; h0 += cap) {
+    const int n = std::min(cap, total - h0);
+    if (m->forward_chunk(poses, h0, n, N, query_latent, out_emb, part, st)) return -1;
+  }
+  if (query_latent && (out_sim || k > 0)) {
+    float* sim = out_sim;
+    if (!sim) {
+      if ((size_t)total > m->sim_buf_cap) {
+        NOPE_CUDA(cudaStreamSynchronize(st));
+        if (m->sim_buf) cudaFree(m->sim_buf);
+        NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->sim_buf), (size_t)total * sizeof(float)));
+        m->sim_buf_cap = total;
+      }
+      sim = m->sim_buf;
+    }
+    sim_topk_kernel<<<B, 256, 0, st>>>(part, nslab, sim, N, k, out_topv, reinterpret_cast<long long*>(out_topi),
+                                       (long long)idx_base);
+    NOPE_CUDA(cudaGetLastError());
+    ++m->launches;
+  }
+  return 0;
+}
+
+int nope_ldm_debug_tap(nope_ldm_t* m, const float* ref_latent, const float* poses, int N, const char* tap,
+                       float* out, int64_t out_capacity_floats, int* out_C, int* out_H, void* stream) {
+  NOPE_CHECK(m && m->finalized && ref_latent && poses && tap && out, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NOPE_CHECK(N <= m->chunk, "debug tap: N must fit one chunk");
+  if (m->ensure_workspace(N, 1)) return -1;
+  m->tap_name = tap;
+  m->tap_out = out;
+  m->tap_cap = out_capacity_floats;
+  m->tap_hit = false;
+  int rc = m->prestage(ref_latent, 1, st);
+  if (!rc) rc = m->forward_chunk(poses, 0, N, N, nullptr, nullptr, nullptr, st);
+  m->tap_out = nullptr;
+  if (rc) return rc;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  NOPE_CHECK(m->tap_hit, std::string("unknown tap name: ") + tap);
+  if (out_C) *out_C = m->tap_C;
+  if (out_H) *out_H = m->tap_S;
+  return 0;
+}
+
+int nope_ldm_run_block(nope_ldm_t* m, const char* name, const float* x0, int C0, const float* x1, int C1, int S,
+                       int n, const float* poses, float* out, void* stream) {
+  NOPE_CHECK(m && m->finalized && name && x0 && out && n >= 1, "bad argument");
+  NOPE_CHECK(S == 8 || S == 16 || S == 32, "side must be 8, 16 or 32");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NOPE_CUDA(cudaSetDevice(m->device));
+  if (m->ensure_workspace(std::max(n, 1), 1)) return -1;
+  NOPE_CHECK(n <= m->cap, "run_block: n exceeds the workspace");
+  const std::string nm = name;
+  // stage the inputs in XA / XB (NHWC fp16); results land in XC
+  nchw_f32_to_nhwc_f16_kernel<<<ew_grid((long long)n * C0 * S * S), 256, 0, st>>>(x0, m->XA, n, C0, S * S);
+  if (x1) nchw_f32_to_nhwc_f16_kernel<<<ew_grid((long long)n * C1 * S * S), 256, 0, st>>>(x1, m->XB, n, C1, S * S);
+  NOPE_CUDA(cudaGetLastError());
+  int Co = 0, So = S;
+  if (m->convs.count(nm + ".c1")) {
+    if (m->resblock(nm, m->XA, C0, x1 ? m->XB : nullptr, x1 ? C1 : 0, m->XC, S, n, st)) return -1;
+    Co = m->convs.at(nm + ".c2").cout;
+  } else if (m->convs.count(nm + ".qkv")) {
+    NOPE_CHECK(poses != nullptr && x1 == nullptr, "transformer block: poses required, one input");
+    if (m->cross_terms(poses, n, st)) return -1;
+    if (m->stats(m->XA, C0, nullptr, 0, S, n, m->S_out, st)) return -1;
+    if (m->transformer(nm, m->XA, m->XC, C0, S, n, m->cb, st)) return -1;
+    Co = C0;
+  } else if (m->convs.count(nm)) {
+    const LdmConv& L = m->convs.at(nm);
+    NOPE_CHECK(x1 == nullptr && L.cin == C0 && (L.mode == 3 || L.mode == 4), "run_block: not a resample conv");
+    So = L.mode == 3 ? 2 * S : S / 2;
+    if (m->conv(L, m->XA, m->XC, So, n, st)) return -1;
+    Co = L.cout;
+  } else {
+    return fail(std::string("run_block: unknown module ") + nm);
+  }
+  nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * Co * So * So), 256, 0, st>>>(m->XC, out, n, Co, So * So);
+  NOPE_CUDA(cudaGetLastError());
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nope_op_mh_attention(int impl, const float* qkv, float* out, int n_img, int n_tok, int C, void* stream) {
+  NOPE_CHECK(qkv && out && n_img >= 1 && n_tok >= 64 && n_tok % 64 == 0 && C % 32 == 0 && C >= 32,
+             "bad arguments (n_tok must be a multiple of 64, C of 32)");
+  NOPE_CHECK(impl == 0 || impl == 1, "impl must be 0 (tcgen05) or 1 (CUDA cores)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  nope_ldm e;    // only the attention staging buffers are used; freed by the destructor
+  e.attn_impl = impl;
+  const size_t tok = (size_t)n_img * n_tok;
+  __half *q16 = nullptr, *o16 = nullptr;
+  if (e.ws_half(&q16, tok * 3 * C) || e.ws_half(&o16, tok * C) || e.ws_half(&e.Qp, tok * 2 * C) ||
+      e.ws_half(&e.Kp, tok * 2 * C) || e.ws_half(&e.Vt, tok * C))
+    return -1;
+  // [n_img, n_tok, 3C] fp32 is already token-major: a plain fp32 -> fp16 cast ("NCHW" with hw = 1)
+  nchw_f32_to_nhwc_f16_kernel<<<ew_grid((long long)tok * 3 * C), 256, 0, st>>>(qkv, q16, (int)tok, 3 * C, 1);
+  NOPE_CUDA(cudaGetLastError());
+  if (e.attention(q16, o16, C, n_tok, n_img, st)) return -1;
+  nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)tok * C), 256, 0, st>>>(o16, out, (int)tok, C, 1);
+  NOPE_CUDA(cudaGetLastError());
+  NOPE_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

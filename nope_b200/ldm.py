@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's LDM-variant UNet, `UNetModelPose`
+(src/model/u_net/ldm/adapt_openaimodel.py:14-158; configs/model/vae_cin_ldm.yaml), on top of the
+C ABI in include/nope_b200.h (nope_ldm_*).
+
+Same constructor keywords as the reference class; `load_state_dict` takes its 628 keys unchanged;
+`__call__(x, pose)` is `UNetModelPose.forward`; `sweep` batches all pose hypotheses of a
+reference latent and fuses the l2 score + top-k like `nope_b200.unet.UNet.sweep`.  All arithmetic
+runs in libnope_b200.so.  The VAE encoder of this variant (diffusers AutoencoderKL,
+src/model/encoder/AutoencoderKL.py:16-47) is not part of the reference tree; pass any object
+with `latent_dim` / `name` (and `encode_image` if images are to be encoded) as `encoder`.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class UNetModelPose:
+    def __init__(self, injecting_condition_twice=False, pose_mlp_name="single_layer",
+                 rot_representation_dim=6, encoder=None, image_size=32, in_channels=4,
+                 model_channels=256, out_channels=4, num_res_blocks=2,
+                 attention_resolutions=(4, 2, 1), dropout=0, channel_mult=(1, 2, 4),
+                 num_head_channels=32, use_spatial_transformer=True, transformer_depth=1,
+                 context_dim=512, device="cuda:0", chunk=256, **kwargs):
+        # the configuration the reference ships (vae_cin_ldm.yaml:2-31); everything else raises
+        if injecting_condition_twice or pose_mlp_name != "single_layer":
+            raise ValueError("only injecting_condition_twice=False / pose_mlp_name='single_layer'")
+        if rot_representation_dim != 6 or tuple(channel_mult) != (1, 2, 4) or num_res_blocks != 2 \
+                or sorted(attention_resolutions) != [1, 2, 4] or num_head_channels != 32 \
+                or not use_spatial_transformer or transformer_depth != 1 or image_size != 32 \
+                or in_channels != out_channels or dropout != 0:
+            raise ValueError("unsupported UNetModelPose configuration (vae_cin_ldm.yaml values only)")
+        for k in ("use_scale_shift_norm", "resblock_updown", "num_classes", "n_embed", "use_fp16"):
+            if kwargs.get(k):
+                raise ValueError(f"unsupported option {k}")
+        self.encoder = encoder
+        self.channels = in_channels if encoder is None else encoder.latent_dim
+        self.name = "VAE" if encoder is None else encoder.name
+        if self.channels != in_channels:
+            raise ValueError("encoder.latent_dim must equal in_channels")
+        self.model_channels = model_channels
+        self.context_dim = context_dim
+        self.rot_representation_dim = rot_representation_dim
+        self.device = torch.device(device)
+        self._chunk = chunk
+        self._h = None
+        self._finalized = False
+
+    def _handle(self):
+        if self._h is None:
+            lib = _lib.load()
+            if self.device.type != "cuda":
+                raise _lib.NopeError("nope_b200.UNetModelPose needs a CUDA device (no CPU fallback)")
+            h = C.c_void_p()
+            _lib.check(lib.nope_ldm_create(C.byref(h), self.model_channels, self.context_dim,
+                                           self.channels, 32, self.device.index or 0))
+            self._h = h
+            _lib.check(lib.nope_ldm_set_chunk(h, self._chunk))
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.load().nope_ldm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Reference UNetModelPose.state_dict() keys; `encoder.*` entries are skipped."""
+        lib = _lib.load()
+        h = self._handle()
+        for k, v in state_dict.items():
+            if k.startswith("encoder."):
+                continue
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(lib.nope_ldm_load_tensor(h, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+        _lib.check(lib.nope_ldm_finalize(h))
+        self._finalized = True
+        return self
+
+    def set_chunk(self, hyps):
+        self._chunk = hyps
+        if self._h is not None:
+            _lib.check(_lib.load().nope_ldm_set_chunk(self._h, hyps))
+
+    def set_impl(self, conv="tcgen05_2cta", attn="tcgen05"):
+        _lib.check(_lib.load().nope_ldm_set_impl(self._handle(), {"tcgen05": 0, "tcgen05_2cta": 2}[conv],
+                                                 {"tcgen05": 0, "simt": 1}[attn]))
+
+    @property
+    def last_launch_count(self):
+        return int(_lib.load().nope_ldm_last_launch_count(self._handle()))
+
+    def sweep(self, ref_latent, poses, query_latent=None, want_emb=True, want_sim=None, k=0, idx_base=0):
+        """ref_latent [B,C,32,32], poses [B,N,6] (+ query_latent) -> dict(emb, sim, topv, topi)."""
+        if not self._finalized:
+            raise _lib.NopeError("load_state_dict() must be called before the sweep")
+        lib = _lib.load()
+        dev = self.device
+        ref_latent = ref_latent.to(dev, torch.float32).contiguous()
+        poses = poses.to(dev, torch.float32).contiguous()
+        B, N = poses.shape[0], poses.shape[1]
+        assert ref_latent.shape == (B, self.channels, 32, 32), ref_latent.shape
+        assert poses.shape[2] == self.rot_representation_dim
+        if want_sim is None:
+            want_sim = query_latent is not None
+        if query_latent is not None:
+            query_latent = query_latent.to(dev, torch.float32).contiguous()
+            assert query_latent.shape == ref_latent.shape
+        emb = torch.empty((B, N, self.channels, 32, 32), device=dev, dtype=torch.float32) if want_emb else None
+        sim = torch.empty((B, N), device=dev, dtype=torch.float32) if want_sim else None
+        topv = torch.empty((B, k), device=dev, dtype=torch.float32) if k > 0 else None
+        topi = torch.empty((B, k), device=dev, dtype=torch.int64) if k > 0 else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nope_ldm_sweep(self._handle(), _lib.ptr(ref_latent), _lib.ptr(poses), B, N,
+                                          _lib.ptr(query_latent), _lib.ptr(emb), _lib.ptr(sim), k,
+                                          _lib.ptr(topv), _lib.ptr(topi), idx_base, C.c_void_p(stream)))
+        return {"emb": emb, "sim": sim, "topv": topv, "topi": topi}
+
+    def __call__(self, x, pose):
+        """UNetModelPose.forward(x [B,C,32,32], pose [B,6]) -> [B,C,32,32]."""
+        return self.sweep(x, pose[:, None, :], want_emb=True)["emb"][:, 0]
+
+    forward = __call__
+
+    def predict_pose(self, query_latent, ref_latent, all_relativeR, template_poses, k=5):
+        """Latent-space form of nope_b200.model.PoseConditional.predict_pose for this UNet:
+        -> (R [B,k,3,3], nearest_idx [B,k], similarity [B,N])."""
+        out = self.sweep(ref_latent, all_relativeR, query_latent, want_emb=False, want_sim=True, k=k)
+        idx = out["topi"]
+        tp = template_poses.to(idx.device)
+        R = tp[idx] if tp.dim() == 3 else torch.stack([tp[b][idx[b]] for b in range(idx.shape[0])])
+        return R, idx, out["sim"]
+
+    # ------------------------------------------------------------------ debug / parity hooks
+    def debug_tap(self, ref_latent, poses, tap):
+        lib = _lib.load()
+        dev = self.device
+        ref_latent = ref_latent.to(dev, torch.float32).contiguous()
+        poses = poses.to(dev, torch.float32).contiguous()
+        N = poses.shape[0]
+        cap = N * 32 * 32 * 2 * self.model_channels
+        out = torch.empty(cap, device=dev, dtype=torch.float32)
+        c, s = C.c_int(), C.c_int()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nope_ldm_debug_tap(self._handle(), _lib.ptr(ref_latent), _lib.ptr(poses), N,
+                                              tap.encode(), _lib.ptr(out), cap, C.byref(c), C.byref(s),
+                                              C.c_void_p(stream)))
+        return out[: N * c.value * s.value * s.value].view(N, c.value, s.value, s.value)
+
+    def run_block(self, name, x0, x1=None, poses=None, out_channels=None, out_side=None):
+        """One module in isolation (fp32 NCHW in / out); see nope_ldm_run_block."""
+        lib = _lib.load()
+        dev = self.device
+        x0 = x0.to(dev, torch.float32).contiguous()
+        n, C0, S = x0.shape[0], x0.shape[1], x0.shape[2]
+        C1 = 0
+        if x1 is not None:
+            x1 = x1.to(dev, torch.float32).contiguous()
+            C1 = x1.shape[1]
+        if poses is not None:
+            poses = poses.to(dev, torch.float32).contiguous()
+        out = torch.empty((n, out_channels, out_side, out_side), device=dev, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nope_ldm_run_block(self._handle(), name.encode(), _lib.ptr(x0), C0, _lib.ptr(x1), C1,
+                                              S, n, _lib.ptr(poses), _lib.ptr(out), C.c_void_p(stream)))
+        return out
+
+
+def mh_attention(qkv, impl="tcgen05"):
+    """Multi-head self-attention core on qkv [n_img, n_tok, 3C] (CUDA fp32) -> [n_img, n_tok, C]."""
+    lib = _lib.load()
+    qkv = qkv.to(torch.float32).contiguous()
+    n_img, n_tok, c3 = qkv.shape
+    out = torch.empty((n_img, n_tok, c3 // 3), device=qkv.device, dtype=torch.float32)
+    stream = torch.cuda.current_stream(qkv.device).cuda_stream
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.nope_op_mh_attention({"tcgen05": 0, "simt": 1}[impl], _lib.ptr(qkv), _lib.ptr(out),
+                                            n_img, n_tok, c3 // 3, C.c_void_p(stream)))
+    return out

@@ -1,0 +1,11 @@
+#!/bin/bash
+# LDM-variant bring-up on the GPU box: parity tests (all, no -x) + a quick timing.
+mkdir -p gpurun_out
+rm -f gpurun_out/parity_log.jsonl
+timeout 1200 python -m pytest tests/test_ldm_gpu.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/ldm_tests.log 2>&1
+echo "pytest exit $?" >> gpurun_out/ldm_tests.log
+tail -60 gpurun_out/ldm_tests.log
+cp gpurun_out/parity_log.jsonl gpurun_out/ldm_parity_log.jsonl 2>/dev/null
+timeout 300 python tools/ldm_time.py 128 tcgen05 > gpurun_out/ldm_time.log 2>&1
+timeout 300 python tools/ldm_time.py 128 simt >> gpurun_out/ldm_time.log 2>&1
+cat gpurun_out/ldm_time.log
