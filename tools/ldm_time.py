@@ -1,7 +1,9 @@
 """Quick timing of the LDM-variant sweep (not the bench): N hypotheses of one reference latent."""
+import os
 import sys
 import time
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from nope_b200.ldm import UNetModelPose
@@ -28,6 +30,11 @@ for _ in range(reps):
     out = m.sweep(ref, poses, qry, want_emb=False, k=5)
 e1.record()
 torch.cuda.synchronize()
+if os.environ.get("NOPE_PROFILE"):
+    torch.cuda.profiler.start()
+    m.sweep(ref, poses, qry, want_emb=False, k=5)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 ms = e0.elapsed_time(e1) / reps
 print(f"LDM sweep N={N} attn={attn}: {ms:.2f} ms/sweep, {N / ms * 1e3:.0f} hyp/s, "
       f"{m.last_launch_count} launches, mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB torch", flush=True)
