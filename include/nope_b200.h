@@ -179,6 +179,11 @@ int nope_ldm_set_chunk(nope_ldm_t* m, int hyps_per_chunk);       /* ~20.5 MB wor
 /* conv_impl: 2 = tcgen05 CTA pairs (default), 0 = tcgen05 1-CTA tiles;
  * attn_impl: 0 = tcgen05 attention (default), 1 = CUDA-core twin (bring-up). */
 int nope_ldm_set_impl(nope_ldm_t* m, int conv_impl, int attn_impl);
+/* Named switches (bring-up / A-B measurements): "fuse_geglu" (default 1: GEGLU runs in the
+ * epilogue of its projection GEMM; 0: separate elementwise kernel), "hoist" (default 1: the
+ * pose-independent prefix -- input conv, first ResBlock, first transformer up to its
+ * self-attention -- runs once per reference instead of once per hypothesis). */
+int nope_ldm_set_option(nope_ldm_t* m, const char* name, int value);
 int nope_ldm_sweep(nope_ldm_t* m, const float* ref_latent, const float* poses, int B, int N,
                    const float* query_latent, float* out_emb, float* out_sim, int k,
                    float* out_topv, int64_t* out_topi, int64_t idx_base, void* stream);

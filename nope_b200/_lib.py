@@ -52,6 +52,7 @@ SIGNATURES = {
     "nope_ldm_finalize": (C.c_int, [C.c_void_p]),
     "nope_ldm_set_chunk": (C.c_int, [C.c_void_p, C.c_int]),
     "nope_ldm_set_impl": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "nope_ldm_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "nope_ldm_sweep": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p,
                                  c_f32p, C.c_int, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
     "nope_ldm_last_launch_count": (C.c_int64, [C.c_void_p]),

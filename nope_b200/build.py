@@ -8,8 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "nope_b200.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in
-        ("nope_b200.cu", "common.cuh", "conv_tc.cuh", "kernels.cuh")] + \
+CSRC = os.path.join(HERE, "csrc")
+DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + \
        [os.path.join(ROOT, "include", "nope_b200.h")]
 OUT_DIR = os.path.join(HERE, "lib")
 OUT = os.path.join(OUT_DIR, "libnope_b200.so")

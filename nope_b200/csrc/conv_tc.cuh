@@ -64,6 +64,10 @@ struct ConvParams {
   const __half* res_lo;   // residual, low halves (nullptr: residual is a single fp16 tensor)
   __half* out_lo;         // low halves of the output (omap receives the high halves)
   float* out_f32;         // fp32 output instead of the fp16 TMA store
+  // GEGLU epilogue (ldm/attention.py:44-51; 2-CTA kernel, BN = 128 only): every 128-column tile
+  // holds 64 "x" channels followed by their 64 "gate" channels (rows permuted on the host);
+  // the epilogue stores x * gelu(gate) as 64 fp16 channels at channel (n_tile * 64) of omap.
+  int geglu;
   // optional GroupNorm partial statistics of the fp32 outputs (bias included), written
   // deterministically as stats[(img * parts + part) * n_oct + octet] = (sum, sum of squares)
   // over 32-pixel row segments x 8-channel octets; parts = max(1, H*W/32).
@@ -245,6 +249,37 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
         dst[idx] = st[0];                            // idx = octet * 2 + {sum, sum of squares}
       }
     }
+  }
+}
+
+// GEGLU epilogue of one 128 x 128 accumulator tile: columns 0..63 = x, 64..127 = gate.
+// Warp e owns pixel rows 32*(e&3).. and the 32-column half (e>>2) of BOTH halves, so
+// x * gelu(gate) needs no exchange.  Exact (erf) GELU, F.gelu's default.
+__device__ __forceinline__ void conv_epilogue_geglu(uint8_t* out_stage, const float* s_bias, uint32_t t_acc,
+                                                    int e, int lane) {
+  const int q = e & 3, hh = e >> 2;
+  const int row = q * 32 + lane;
+  const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
+  uint32_t vx[32], vg[32];
+  tmem_ld_32x32(t_row, vx);
+  tmem_ld_32x32(t_row + 64, vg);
+  tmem_ld_wait();
+  const float* bx = s_bias + hh * 32;
+  const float* bg = s_bias + 64 + hh * 32;
+  uint8_t* srow = out_stage + row * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = __uint_as_float(vx[j * 8 + i]) + bx[j * 8 + i];
+      const float g = __uint_as_float(vg[j * 8 + i]) + bg[j * 8 + i];
+      f[i] = x * (0.5f * g * (1.f + erff(g * 0.70710678118654752f)));
+    }
+    const int phys = (hh * 4 + j) ^ (row & 7);
+    *reinterpret_cast<uint4*>(srow + phys * 16) =
+        make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]),
+                   pack_half2(f[6], f[7]));
   }
 }
 

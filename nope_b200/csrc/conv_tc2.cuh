@@ -112,7 +112,8 @@ struct Conv2Smem {
   static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;
 };
 
-template <int BN, int STAGES, bool EXTRAS>
+// EPI: 0 = plain epilogue (the sweep), 1 = extras (ReLU / residual / hi-lo / fp32), 2 = GEGLU
+template <int BN, int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   using S = Conv2Smem<BN, STAGES>;
@@ -240,7 +241,10 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      conv_epilogue_tile<BN, EXTRAS>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
+      if constexpr (EPI == 2)
+        conv_epilogue_geglu(out_stage, s_bias, tmem_base + acc * BN, e, lane);
+      else
+        conv_epilogue_tile<BN, EPI == 1>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       // this CTA's accumulator half is drained: tell the leader's MMA warp
       tc_fence_before();
       __syncwarp();
@@ -251,9 +255,13 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (etid == 0) {
+        if constexpr (EPI == 2) {
+          tma_store_4d(&p.omap[0], out_stage, n_chan0 / 2, 0, y0, b0);
+        } else {
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 64; ++cc)
-          tma_store_4d(&p.omap[par], out_stage + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
+          for (int cc = 0; cc < BN / 64; ++cc)
+            tma_store_4d(&p.omap[par], out_stage + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
+        }
         tma_store_commit();
       }
       acc ^= 1;
@@ -267,32 +275,36 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   if (warp == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
 }
 
-template <int BN, int STAGES, bool EXTRAS>
+template <int BN, int STAGES, int EPI>
 inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using S = Conv2Smem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    NOPE_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, EXTRAS>,
+    NOPE_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, EPI>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = num_sms / 2;
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
-  conv_tc2_kernel<BN, STAGES, EXTRAS><<<2 * clusters, kConvThreads, S::kTotal, stream>>>(p);
+  conv_tc2_kernel<BN, STAGES, EPI><<<2 * clusters, kConvThreads, S::kTotal, stream>>>(p);
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }
 
 inline int launch_conv_tc2(const ConvParams& p, int bn, int num_sms, cudaStream_t stream) {
   const bool ex = conv_needs_extras(p);
+  if (p.geglu) {
+    if (bn != 128 || ex || p.stats || p.n_par != 1) return fail("launch_conv_tc2: GEGLU epilogue needs BN = 128, no extras");
+    return launch_conv_tc2_t<128, 7, 2>(p, num_sms, stream);
+  }
   switch (bn) {
-    case 192: return ex ? launch_conv_tc2_t<192, 6, true>(p, num_sms, stream)
-                        : launch_conv_tc2_t<192, 6, false>(p, num_sms, stream);
-    case 128: return ex ? launch_conv_tc2_t<128, 7, true>(p, num_sms, stream)
-                        : launch_conv_tc2_t<128, 7, false>(p, num_sms, stream);
-    case 64: return ex ? launch_conv_tc2_t<64, 8, true>(p, num_sms, stream)
-                       : launch_conv_tc2_t<64, 8, false>(p, num_sms, stream);
+    case 192: return ex ? launch_conv_tc2_t<192, 6, 1>(p, num_sms, stream)
+                        : launch_conv_tc2_t<192, 6, 0>(p, num_sms, stream);
+    case 128: return ex ? launch_conv_tc2_t<128, 7, 1>(p, num_sms, stream)
+                        : launch_conv_tc2_t<128, 7, 0>(p, num_sms, stream);
+    case 64: return ex ? launch_conv_tc2_t<64, 8, 1>(p, num_sms, stream)
+                       : launch_conv_tc2_t<64, 8, 0>(p, num_sms, stream);
   }
   return fail("launch_conv_tc2: unsupported BN");
 }

@@ -16,7 +16,7 @@
 //                     GEGLU feed-forward (+x) -> proj_out (+x_in)
 //   Downsample        conv3x3 stride 2 through the four stride-2 TMA lattices of its input
 //   Upsample          nearest-x2 + conv3x3 folded into four 2x2 parity kernels
-//   out               GN32+SiLU -> conv3x3 (256 -> 4) fused with the l2 score
+//   out               GN32+SiLU -> conv3x3 (256 -> 4, padded to a 64-channel tile, fp32 store) -> l2 score
 // Every GEMM-shaped op runs on conv_tc2_kernel / conv_tc_kernel.
 #pragma once
 #include "conv_tc2.cuh"
@@ -37,6 +37,7 @@ struct LdmConv {
   int mode = 0;   // 0: 3x3 pad 1, 1: 1x1 / linear, 3: nearest-x2 + 3x3 (folded), 4: 3x3 stride 2 pad 1
   int cin = 0, cout = 0, K = 0, bn = 0;
   int skip_c = 0;          // channels of a folded 1x1 skip_connection (extra K columns)
+  bool geglu = false;      // rows permuted to (64 x | 64 gate) tiles; the epilogue emits x * gelu(gate)
   __half* w = nullptr;     // [rows][K] fp16
   float* bias = nullptr;
   CUtensorMap wmap, wmap_half;
@@ -67,6 +68,8 @@ struct nope_ldm {
   bool finalized = false;
   int conv_impl = 2;   // 2: tcgen05 CTA pairs (default), 0: tcgen05 1-CTA tiles
   int attn_impl = 0;   // 0: tcgen05 attention, 1: CUDA-core twin
+  bool hoist = true;        // pose-independent prefix once per reference (prestage)
+  bool fuse_geglu = true;   // GEGLU in the projection's epilogue (2-CTA kernel); false: separate kernel
   int chunk = 256;
   int64_t launches = 0;
 
@@ -80,7 +83,7 @@ struct nope_ldm {
   std::map<std::string, int> cb_off;   // transformer prefix -> offset in the cross-term vector
   int cb_width = 0;
   float *cross_w = nullptr, *cross_b = nullptr;      // [cb_width][6], [cb_width]
-  float *in_w = nullptr, *in_b = nullptr, *out_w = nullptr, *out_b = nullptr;
+  float *in_w = nullptr, *in_b = nullptr;
   std::vector<void*> owned;
 
   // workspace (per chunk of `cap` hypotheses; `cap_ref` reference latents)
@@ -88,9 +91,10 @@ struct nope_ldm {
   std::vector<__half*> HS;                     // skip stack, one buffer per input block
   __half *XA = nullptr, *XB = nullptr, *XC = nullptr, *R = nullptr, *T1 = nullptr, *T2 = nullptr,
          *T3 = nullptr, *XN = nullptr, *PI = nullptr, *PJ = nullptr, *QKV = nullptr, *Qp = nullptr,
-         *Kp = nullptr, *Vt = nullptr, *AO = nullptr, *FF = nullptr, *GG = nullptr, *x0ref = nullptr;
+         *Kp = nullptr, *Vt = nullptr, *AO = nullptr, *FF = nullptr, *GG = nullptr, *x0ref = nullptr, *Rref = nullptr, *Pref = nullptr;
   float2 *S_in = nullptr, *S_mid = nullptr, *S_out = nullptr;
   float* cb = nullptr;
+  float* OF = nullptr;                          // out[2] result, fp32 [cap * S0 * S0][64]
   int* ref_of = nullptr;
   float* score_partial = nullptr;
   size_t score_partial_cap = 0;
@@ -344,6 +348,34 @@ struct nope_ldm {
     if (make_conv(p + ".proj_out", p + ".proj_out.weight", p + ".proj_out.bias", 1)) return -1;
     if (make_conv(p + ".to_out", t + ".attn1.to_out.0.weight", t + ".attn1.to_out.0.bias", 1)) return -1;
     if (make_conv(p + ".ff1", t + ".ff.net.0.proj.weight", t + ".ff.net.0.proj.bias", 1)) return -1;
+    {  // the same projection with GEGLU fused into the epilogue (2-CTA kernel): tile t of 128 rows =
+       // x rows 64t..64t+63 followed by gate rows inner+64t..inner+64t+63
+      const HostT& W = H(t + ".ff.net.0.proj.weight");
+      const auto& b = H(t + ".ff.net.0.proj.bias").second;
+      const int inner = 4 * c;
+      HostT Wp;
+      Wp.first = W.first;
+      Wp.second.resize(W.second.size());
+      std::vector<float> bp(2 * inner);
+      for (int tl = 0; tl < inner / 64; ++tl)
+        for (int half = 0; half < 2; ++half)
+          for (int j = 0; j < 64; ++j) {
+            const int src = half * inner + tl * 64 + j, dst = tl * 128 + half * 64 + j;
+            std::copy(W.second.begin() + (size_t)src * c, W.second.begin() + (size_t)(src + 1) * c,
+                      Wp.second.begin() + (size_t)dst * c);
+            bp[dst] = b[src];
+          }
+      nope::LdmConv L;
+      L.mode = 1;
+      L.cin = c;
+      L.cout = 2 * inner;
+      L.K = c;
+      L.geglu = true;
+      if (alloc_w(L, 2 * inner) || pack_into(L.w, c, 0, 0, Wp, 2 * inner, c, 1) ||
+          finish_conv(p + ".ff1g", L, 2 * inner, bp))
+        return -1;
+      NOPE_CHECK(convs.at(p + ".ff1g").bn == 128, "GEGLU projection must tile by 128");
+    }
     if (make_conv(p + ".ff2", t + ".ff.net.2.weight", t + ".ff.net.2.bias", 1)) return -1;
     {  // q | k | v of the self-attention as one GEMM (no bias, ldm/attention.py:160-162)
       nope::LdmConv L;
@@ -407,9 +439,23 @@ struct nope_ldm {
     NOPE_CHECK(!finalized, "already finalized");
     for (const auto& kv : expected) NOPE_CHECK(host.count(kv.first), "state_dict is missing " + kv.first);
     NOPE_CUDA(cudaSetDevice(device));
-    if (upload(H("input_blocks.0.0.weight").second, &in_w) || upload(H("input_blocks.0.0.bias").second, &in_b) ||
-        upload(H("out.2.weight").second, &out_w) || upload(H("out.2.bias").second, &out_b))
+    if (upload(H("input_blocks.0.0.weight").second, &in_w) || upload(H("input_blocks.0.0.bias").second, &in_b))
       return -1;
+    {  // out[2]: Cl output channels padded to one 64-wide tile of the tensor-core kernel
+      HostT W;
+      W.first = {64, mc, 3, 3};
+      W.second.assign((size_t)64 * mc * 9, 0.f);
+      const auto& w = H("out.2.weight").second;
+      std::copy(w.begin(), w.end(), W.second.begin());
+      std::vector<float> bias(64, 0.f);
+      std::copy(H("out.2.bias").second.begin(), H("out.2.bias").second.end(), bias.begin());
+      nope::LdmConv L;
+      L.mode = 0;
+      L.cout = 64;
+      L.cin = mc;
+      L.K = 9 * mc;
+      if (alloc_w(L, 64) || pack_into(L.w, L.K, 0, 0, W, 64, mc, 9) || finish_conv("out.2", L, 64, bias)) return -1;
+    }
     for (size_t i = 1; i < inp.size(); ++i) {
       const std::string p = "input_blocks." + std::to_string(i);
       if (inp[i].kind == 1) {
@@ -467,11 +513,12 @@ struct nope_ldm {
         ws_half(&T1, c * 3 * u) || ws_half(&T2, c * u) || ws_half(&T3, c * u) || ws_half(&XN, c * u) ||
         ws_half(&PI, c * u) || ws_half(&PJ, c * u) || ws_half(&QKV, c * 3 * u) || ws_half(&Qp, c * 2 * u) ||
         ws_half(&Kp, c * 2 * u) || ws_half(&Vt, c * u) || ws_half(&AO, c * u) || ws_half(&FF, c * 8 * u) ||
-        ws_half(&GG, c * 4 * u) || ws_half(&x0ref, (size_t)cap_ref * u))
+        ws_half(&GG, c * 4 * u) || ws_half(&x0ref, (size_t)cap_ref * u) || ws_half(&Rref, (size_t)cap_ref * u) ||
+        ws_half(&Pref, (size_t)cap_ref * u))
       return -1;
     const size_t st = (size_t)32 * 256;   // parts (<= 32) x octets (<= 256) per image
     if (ws_any(&S_in, c * st) || ws_any(&S_mid, c * st) || ws_any(&S_out, c * st)) return -1;
-    if (ws_any(&cb, c * (size_t)cb_width) || ws_any(&ref_of, c)) return -1;
+    if (ws_any(&cb, c * (size_t)cb_width) || ws_any(&ref_of, c) || ws_any(&OF, c * S0 * S0 * 64)) return -1;
     return 0;
   }
 
@@ -495,7 +542,7 @@ struct nope_ldm {
   // out[n_img, So, So, cout] = conv(L, in) [+ 1x1 skip over cat(sk0, sk1)] + bias [+ res]
   int conv(const nope::LdmConv& L, const __half* in, __half* out, int So, int n_img, cudaStream_t st,
            float2* stats = nullptr, const __half* res = nullptr, const __half* sk0 = nullptr, int skc0 = 0,
-           const __half* sk1 = nullptr, int skc1 = 0) {
+           const __half* sk1 = nullptr, int skc1 = 0, float* out_f32 = nullptr) {
     using namespace nope;
     NOPE_CHECK(skc0 + skc1 == L.skip_c, "conv: skip channel mismatch");
     ++launches;
@@ -565,11 +612,13 @@ struct nope_ldm {
         p.omap[t] = *m;
       }
     } else {
-      if (get_map(&m, out, L.cout, g, -1)) return -1;
+      if (get_map(&m, out, L.geglu ? L.cout / 2 : L.cout, g, -1)) return -1;
       for (int t = 0; t < 4; ++t) p.omap[t] = *m;
     }
+    p.geglu = L.geglu ? 1 : 0;
     p.bias = L.bias;
     p.res_hi = res;
+    p.out_f32 = out_f32;
     p.stats = stats;
     p.stats_hw = So * So;
     p.stats_noct = L.cout / 8;
@@ -613,14 +662,14 @@ struct nope_ldm {
     return 0;
   }
   int ln(const nope::LdmNorm& N, const __half* x, __half* xout, const float* cbp, __half* y, int C, int S, int n,
-         cudaStream_t st) {
+         cudaStream_t st, const int* src_img = nullptr) {
     using namespace nope;
     const long long ntok = (long long)n * S * S;
     const unsigned grid = (unsigned)((ntok + 7) / 8);
     switch (C) {
-      case 256: ldm_ln_kernel<1><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S); break;
-      case 512: ldm_ln_kernel<2><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S); break;
-      case 1024: ldm_ln_kernel<4><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S); break;
+      case 256: ldm_ln_kernel<1><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S, src_img); break;
+      case 512: ldm_ln_kernel<2><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S, src_img); break;
+      case 1024: ldm_ln_kernel<4><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S, src_img); break;
       default: return fail("LayerNorm: channels must be 256, 512 or 1024");
     }
     NOPE_CUDA(cudaGetLastError());
@@ -697,27 +746,40 @@ struct nope_ldm {
   }
 
   // SpatialTransformer.forward (ldm/attention.py:264-277) with one BasicTransformerBlock
-  // (:229-233).  x_in's GroupNorm statistics must be in S_out.  cbp: cross-attention terms.
-  int transformer(const std::string& p, const __half* x_in, __half* out, int C, int S, int n, const float* cbp,
-                  cudaStream_t st) {
+  // (:229-233), in two halves.  st_pre: norm, proj_in, x = attn1(norm1(x)) + x -> `xs`; nothing in
+  // it depends on the pose.  x_in's GroupNorm statistics must be in S_out.
+  int st_pre(const std::string& p, const __half* x_in, __half* xs, int C, int S, int n, cudaStream_t st) {
     if (gn(norms.at(p + ".norm"), x_in, C, nullptr, 0, S_out, S, n, XN, false, 1e-6f, st)) return -1;
     if (conv(convs.at(p + ".proj_in"), XN, PI, S, n, st)) return -1;
-    // x = attn1(norm1(x)) + x
     if (ln(norms.at(p + ".ln1"), PI, nullptr, nullptr, XN, C, S, n, st)) return -1;
     if (conv(convs.at(p + ".qkv"), XN, QKV, S, n, st)) return -1;
     if (attention(QKV, AO, C, S * S, n, st)) return -1;
-    if (conv(convs.at(p + ".to_out"), AO, PJ, S, n, st, nullptr, PI)) return -1;
-    // x = attn2(norm2(x), context) + x: the one-token cross-attention is the per-hypothesis
-    // vector cb (see make_cross); added by the LayerNorm kernel, which also applies norm3
-    if (ln(norms.at(p + ".ln3"), PJ, PJ, cbp + cb_off.at(p), XN, C, S, n, st)) return -1;
-    // x = ff(norm3(x)) + x, GEGLU
-    if (conv(convs.at(p + ".ff1"), XN, FF, S, n, st)) return -1;
-    nope::ldm_geglu_kernel<<<nope::ew_grid((long long)n * S * S * C / 2), 256, 0, st>>>(FF, GG, (long long)n * S * S,
-                                                                                      4 * C);
-    NOPE_CUDA(cudaGetLastError());
-    ++launches;
+    return conv(convs.at(p + ".to_out"), AO, xs, S, n, st, nullptr, PI);
+  }
+  // st_post: x = attn2(norm2(x), context) + x -- the one-token cross-attention is the
+  // per-hypothesis vector cb (see make_cross), added by the LayerNorm kernel, which also applies
+  // norm3 -- then x = ff(norm3(x)) + x (GEGLU) and proj_out(x) + x_in.  `xs` may hold one image
+  // per reference (src_img maps hypothesis -> image); x_in and out are per hypothesis.
+  int st_post(const std::string& p, const __half* xs, const int* src_img, const __half* x_in, __half* out, int C,
+              int S, int n, const float* cbp, cudaStream_t st) {
+    if (ln(norms.at(p + ".ln3"), xs, PJ, cbp + cb_off.at(p), XN, C, S, n, st, src_img)) return -1;
+    // GEGLU: fused into the projection's epilogue on the 2-CTA kernel
+    if (conv_impl == 2 && fuse_geglu) {
+      if (conv(convs.at(p + ".ff1g"), XN, GG, S, n, st)) return -1;
+    } else {
+      if (conv(convs.at(p + ".ff1"), XN, FF, S, n, st)) return -1;
+      nope::ldm_geglu_kernel<<<nope::ew_grid((long long)n * S * S * C / 2), 256, 0, st>>>(FF, GG, (long long)n * S * S,
+                                                                                        4 * C);
+      NOPE_CUDA(cudaGetLastError());
+      ++launches;
+    }
     if (conv(convs.at(p + ".ff2"), GG, PI, S, n, st, nullptr, PJ)) return -1;
     return conv(convs.at(p + ".proj_out"), PI, out, S, n, st, nullptr, x_in);
+  }
+  int transformer(const std::string& p, const __half* x_in, __half* out, int C, int S, int n, const float* cbp,
+                  cudaStream_t st) {
+    if (st_pre(p, x_in, PJ, C, S, n, st)) return -1;
+    return st_post(p, PJ, nullptr, x_in, out, C, S, n, cbp, st);
   }
 
   int cross_terms(const float* poses, int n, cudaStream_t st) {
@@ -727,12 +789,22 @@ struct nope_ldm {
     return 0;
   }
 
-  // input_blocks.0 (pose independent), once per reference latent
+  // Pose-independent prefix, once per reference latent: input_blocks.0, the ResBlock of
+  // input_blocks.1 and its transformer up to (and including) the self-attention -- the pose only
+  // enters at the first cross-attention.  Leaves x0ref (conv), Rref (ResBlock output) and Pref
+  // (x after attn1), one image per reference.
   int prestage(const float* ref_lat, int B, cudaStream_t st) {
     nope::init_conv_kernel<<<nope::ew_grid((long long)B * S0 * S0 * mc), 256, 0, st>>>(ref_lat, in_w, in_b, x0ref, B,
                                                                                      Cl, S0, S0, mc);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
+    if (!hoist) return 0;
+    const size_t u = (size_t)S0 * S0 * mc;
+    for (int b0 = 0; b0 < B; b0 += cap) {       // the temporaries hold `cap` images
+      const int nb = std::min(cap, B - b0);
+      if (resblock("input_blocks.1.0", x0ref + b0 * u, mc, nullptr, 0, Rref + b0 * u, S0, nb, st)) return -1;
+      if (st_pre("input_blocks.1.1", Rref + b0 * u, Pref + b0 * u, mc, S0, nb, st)) return -1;
+    }
     return 0;
   }
 
@@ -754,7 +826,16 @@ struct nope_ldm {
     for (size_t i = 1; i < inp.size(); ++i) {
       const std::string p = "input_blocks." + std::to_string(i);
       const auto& b = inp[i];
-      if (b.kind == 1) {
+      if (b.kind == 1 && i == 1 && hoist) {
+        // prefix computed per reference in prestage(): broadcast the ResBlock output (the
+        // transformer's residual) and enter the transformer at the cross-attention
+        bcast_add_kernel<<<ew_grid((long long)n * S * S * mc / 8), 256, 0, st>>>(Rref, ref_of, nullptr, 0, 0, R, n,
+                                                                               S * S, mc);
+        NOPE_CUDA(cudaGetLastError());
+        ++launches;
+        if (tap(p + ".0", R, b.cout, S, n, st)) return -1;
+        if (st_post(p + ".1", Pref, ref_of, R, HS[i], b.cout, S, n, cb, st)) return -1;
+      } else if (b.kind == 1) {
         if (resblock(p + ".0", cur, C, nullptr, 0, R, S, n, st)) return -1;
         if (tap(p + ".0", R, b.cout, S, n, st)) return -1;
         if (transformer(p + ".1", R, HS[i], b.cout, S, n, cb, st)) return -1;
@@ -798,16 +879,10 @@ struct nope_ldm {
     if (gn(norms.at("out.0"), curw, C, nullptr, 0, S_in, S, n, T1, true, 1e-5f, st)) return -1;
     const int hw = S * S;
     const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
-    const size_t smem = (size_t)9 * Cl * mc * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      NOPE_CUDA(cudaFuncSetAttribute(ldm_out_conv_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
-    }
-    NOPE_CHECK(smem <= 96 * 1024, "out conv: weights do not fit in shared memory");
-    ldm_out_conv_score_kernel<<<dim3(nslab, n), kFinalThreads, smem, st>>>(
-        T1, out_w, out_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query, ref_of,
-        score_part ? score_part + (size_t)hyp0 * nslab : nullptr, S, mc, Cl);
+    if (conv(convs.at("out.2"), T1, T2, S, n, st, nullptr, nullptr, nullptr, 0, nullptr, 0, OF)) return -1;
+    ldm_score_kernel<<<dim3(nslab, n), kFinalThreads, 0, st>>>(
+        OF, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query, ref_of,
+        score_part ? score_part + (size_t)hyp0 * nslab : nullptr, hw, Cl);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     return 0;

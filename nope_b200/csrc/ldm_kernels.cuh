@@ -179,18 +179,22 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ldm_ln_kernel(const __half* __restrict__ x, __half* __restrict__ xout, const float* __restrict__ cb,
               int cb_stride, const float* __restrict__ gamma, const float* __restrict__ beta,
-              __half* __restrict__ y, long long n_tok, int tok_per_img) {
+              __half* __restrict__ y, long long n_tok, int tok_per_img, const int* __restrict__ src_img) {
   constexpr int C = 256 * NV;
   const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (tok >= n_tok) return;
   float f[NV][8];
-  const __half* xp = x + tok * C;
+  // src_img: x holds one image per REFERENCE (pose-independent prefix); hypothesis i reads image
+  // src_img[i] of it.  Outputs are always per hypothesis.
+  const long long img = tok / tok_per_img;
+  const long long src_tok = src_img ? (long long)src_img[img] * tok_per_img + (tok - img * tok_per_img) : tok;
+  const __half* xp = x + src_tok * C;
 #pragma unroll
   for (int j = 0; j < NV; ++j)
     unpack8(*reinterpret_cast<const uint4*>(xp + (j * 32 + lane) * 8), f[j]);
   if (cb) {
-    const float* cp = cb + (size_t)(tok / tok_per_img) * cb_stride;
+    const float* cp = cb + (size_t)img * cb_stride;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const float4 c0 = *reinterpret_cast<const float4*>(cp + (j * 32 + lane) * 8);
@@ -326,8 +330,8 @@ ldm_attn_prep_kernel(const __half* __restrict__ qkv, __half* __restrict__ Qp, __
 //               P -> fp16 -> shared memory as the K-major SWIZZLE_128B A operand
 //   O_blk = P V : tcgen05.mma M=128 x N=32 (head channels) x K=128 (keys), TMEM cols 128..159,
 //               folded into the running O in registers: O = O * alpha + O_blk
-// K / V^T blocks are double-buffered TMA loads; two CTAs share an SM, so one CTA's softmax
-// overlaps the other's MMAs.
+// K / V^T blocks are double-buffered TMA loads.  The MMAs are software-pipelined against the
+// softmax (see the loop) and two CTAs share an SM.
 // ----------------------------------------------------------------------------
 struct AttnParams {
   CUtensorMap qmap, kmap, vmap;   // 3-D: {64, n, img*H} / {64, n, img*H} / {n, 32, img*H}
@@ -338,6 +342,13 @@ struct AttnParams {
 constexpr int kAttnQBytes = 128 * 128, kAttnKBytes = 128 * 128, kAttnVBytes = 2 * 32 * 128,
               kAttnPBytes = 2 * 128 * 128;
 constexpr int kAttnSmem = kAttnQBytes + 2 * kAttnKBytes + 2 * kAttnVBytes + kAttnPBytes + 256 + 1024;
+
+// 2^x on the SFU (MUFU.EX2, ~2 ulp); exp2f() adds a denormal-range fix-up the softmax never needs.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
                                             int c1, int c2) {
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(128, 2) ldm_attn_tc_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 8);
 
   const int bh = blockIdx.x, qb = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int nblk = (p.n + 127) / 128;
 
   if (tid == 0) {
@@ -382,7 +393,11 @@ __global__ void __launch_bounds__(128, 2) ldm_attn_tc_kernel(const __grid_consta
   const uint32_t tS = tmem, tO = tmem + 128;
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
 
-  auto issue_kv = [&](int jb, int buf) {
+  constexpr uint32_t idesc_s = make_idesc_f16(128, 128, false);
+  constexpr uint32_t idesc_o = make_idesc_f16(128, 32, false);
+
+  auto issue_kv = [&](int jb) {      // TMA of K / V^T block jb into buffer jb & 1
+    const int buf = jb & 1;
     const int valid = min(128, p.n - jb * 128);
     const int nat = (valid + 63) / 64;
     mbar_expect_tx(&bar_kv[buf], kAttnKBytes + nat * 4096);
@@ -390,82 +405,127 @@ __global__ void __launch_bounds__(128, 2) ldm_attn_tc_kernel(const __grid_consta
     for (int a = 0; a < nat; ++a)
       tma_load_3d(sV + buf * kAttnVBytes + a * 4096, &p.vmap, &bar_kv[buf], jb * 128 + a * 64, 0, bh);
   };
+  auto issue_qk = [&](int jb) {      // S = Q K_jb^T (K = 32 real head channels: two 16-wide steps)
+    const int buf = jb & 1;
+    mbar_wait(&bar_kv[buf], (jb >> 1) & 1);
+    tc_fence_after();
+    const uint64_t adesc = kDescHi | (smem_u32(sQ) >> 4);
+    const uint64_t bdesc = kDescHi | (smem_u32(sK + buf * kAttnKBytes) >> 4);
+    umma_f16(tS, adesc, bdesc, idesc_s, 0u);
+    umma_f16(tS, adesc + 2, bdesc + 2, idesc_s, 1u);
+    umma_commit(bar_s);
+  };
   if (tid == 0) {
     mbar_expect_tx(bar_q, kAttnQBytes);
     tma_load_3d(sQ, &p.qmap, bar_q, 0, qb * 128, bh);
-    issue_kv(0, 0);
+    issue_kv(0);
+    if (nblk > 1) issue_kv(1);
+    mbar_wait(bar_q, 0);
+    issue_qk(0);
   }
+  __syncwarp();
 
-  constexpr uint32_t idesc_s = make_idesc_f16(128, 128, false);
-  constexpr uint32_t idesc_o = make_idesc_f16(128, 32, false);
+  // Software pipeline: while the threads run the softmax of block j, the tensor core finishes
+  // P V of block j-1 and (issued right after it) Q K^T of block j+1; O_blk(j-1) is folded into
+  // the running O in the middle of iteration j, when its MMA has long retired.
   float O[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) O[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
   const float c = p.scale_log2e;
+  uint8_t* prow = sP + tid * 128;
 
   for (int j = 0; j < nblk; ++j) {
     const int b = j & 1;
     const int valid = min(128, p.n - j * 128);
     const int nat = (valid + 63) / 64;
-    if (tid == 0) {
-      if (j + 1 < nblk) issue_kv(j + 1, b ^ 1);
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv[b], (j >> 1) & 1);
-      tc_fence_after();
-      const uint64_t adesc = kDescHi | (smem_u32(sQ) >> 4);
-      const uint64_t bdesc = kDescHi | (smem_u32(sK + b * kAttnKBytes) >> 4);
-      // K = 32 real head channels: two 16-wide steps (the pad halfs of each row are never read)
-      umma_f16(tS, adesc, bdesc, idesc_s, 0u);
-      umma_f16(tS, adesc + 2, bdesc + 2, idesc_s, 1u);
-      umma_commit(bar_s);
-    }
-    __syncwarp();
+    const bool full = valid == 128;
+
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
+    uint32_t s[128];
+    tmem_ld_32x32(tS + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+    tmem_ld_32x32(tS + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+    tmem_ld_32x32(tS + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+    tmem_ld_32x32(tS + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+    tmem_ld_wait();
+    tc_fence_before();      // S is in registers: Q K^T of the next block may overwrite it after the barrier
 
-    // ---- pass 1: row maximum over the valid keys
-    float bm = -INFINITY;
-    uint32_t v[32];
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      if (ch * 32 >= valid) break;
-      tmem_ld_32x32(tS + lane_off + ch * 32, v);
-      tmem_ld_wait();
+    float bm;
+    if (full) {
+      float m0 = __uint_as_float(s[0]), m1 = __uint_as_float(s[1]), m2 = __uint_as_float(s[2]),
+            m3 = __uint_as_float(s[3]);
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (ch * 32 + i < valid) bm = fmaxf(bm, __uint_as_float(v[i]));
+      for (int i = 4; i < 128; i += 4) {
+        m0 = fmaxf(m0, __uint_as_float(s[i]));
+        m1 = fmaxf(m1, __uint_as_float(s[i + 1]));
+        m2 = fmaxf(m2, __uint_as_float(s[i + 2]));
+        m3 = fmaxf(m3, __uint_as_float(s[i + 3]));
+      }
+      bm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    } else {
+      bm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; ++i)
+        if (i < valid) bm = fmaxf(bm, __uint_as_float(s[i]));
     }
     const float m_new = fmaxf(m_run, bm);
-    const float alpha = exp2f((m_run - m_new) * c);     // 0 on the first block (m_run = -inf)
+    const float alpha = fast_exp2((m_run - m_new) * c);     // 0 on the first block (m_run = -inf)
     const float mc = m_new * c;
-    // ---- pass 2: P = exp2(S c - m c) -> fp16 -> swizzled K-major rows of sP
-    float rs = 0.f;
-    uint8_t* prow = sP + tid * 128;
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      const bool live = ch * 32 < valid;
-      if (live) {
-        tmem_ld_32x32(tS + lane_off + ch * 32, v);
-        tmem_ld_wait();
+    float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 128; i += 4) {
+      float e0 = fast_exp2(fmaf(__uint_as_float(s[i]), c, -mc));
+      float e1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), c, -mc));
+      float e2 = fast_exp2(fmaf(__uint_as_float(s[i + 2]), c, -mc));
+      float e3 = fast_exp2(fmaf(__uint_as_float(s[i + 3]), c, -mc));
+      if (!full) {
+        if (i >= valid) e0 = 0.f;
+        if (i + 1 >= valid) e1 = 0.f;
+        if (i + 2 >= valid) e2 = 0.f;
+        if (i + 3 >= valid) e3 = 0.f;
       }
-      if (!live && ch * 32 >= nat * 64) break;    // atom not used by the P V product
-      uint8_t* arow = prow + (ch >> 1) * (128 * 128);
+      // row sum in fp32 of the unrounded probabilities (the fp16 rounding of P is unbiased)
+      rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3;
+      s[i] = __float_as_uint(e0);
+      s[i + 1] = __float_as_uint(e1);
+      s[i + 2] = __float_as_uint(e2);
+      s[i + 3] = __float_as_uint(e3);
+    }
+    l_run = fmaf(l_run, alpha, (rs0 + rs1) + (rs2 + rs3));
+    m_run = m_new;
+
+    if (j > 0) {
+      // fold in O_blk(j-1); its completion also frees sP and K/V buffer (j-1)&1 = (j+1)&1
+      mbar_wait(bar_o, (j - 1) & 1);
+      tc_fence_after();
+      if (tid == 0 && j + 1 < nblk) issue_kv(j + 1);
+      __syncwarp();
+      uint32_t v[32];
+      tmem_ld_32x32(tO + lane_off, v);
+      tmem_ld_wait();
+      tc_fence_before();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float pv[8];
+      for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha_prev, __uint_as_float(v[i]));
+    }
+    alpha_prev = alpha;
+
+    // P -> fp16 -> swizzled K-major rows of sP (atoms of 64 keys)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int kc = ch * 32 + g * 8 + i;
-          pv[i] = (live && kc < valid) ? exp2f(fmaf(__uint_as_float(v[g * 8 + i]), c, -mc)) : 0.f;
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch * 32 < nat * 64) {
+        uint8_t* arow = prow + (ch >> 1) * (128 * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int i0 = ch * 32 + g * 8;
+          const uint4 w = make_uint4(
+              pack_half2(__uint_as_float(s[i0]), __uint_as_float(s[i0 + 1])),
+              pack_half2(__uint_as_float(s[i0 + 2]), __uint_as_float(s[i0 + 3])),
+              pack_half2(__uint_as_float(s[i0 + 4]), __uint_as_float(s[i0 + 5])),
+              pack_half2(__uint_as_float(s[i0 + 6]), __uint_as_float(s[i0 + 7])));
+          const int chunk = (ch & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(arow + ((chunk ^ (tid & 7)) * 16)) = w;
         }
-        const uint4 w = pack8(pv);
-        float pr[8];
-        unpack8(w, pr);           // the sum runs over the fp16 values the MMA will see
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rs += pr[i];
-        const int chunk = (ch & 1) * 4 + g;
-        *reinterpret_cast<uint4*>(arow + ((chunk ^ (tid & 7)) * 16)) = w;
       }
     }
     fence_proxy_async_smem();
@@ -481,19 +541,20 @@ __global__ void __launch_bounds__(128, 2) ldm_attn_tc_kernel(const __grid_consta
           umma_f16(tO, adesc + 2 * k, bdesc + 2 * k, idesc_o, (a | k) != 0 ? 1u : 0u);
       }
       umma_commit(bar_o);
+      if (j + 1 < nblk) issue_qk(j + 1);
     }
     __syncwarp();
-    mbar_wait(bar_o, j & 1);
+  }
+
+  {
+    mbar_wait(bar_o, (nblk - 1) & 1);
     tc_fence_after();
+    uint32_t v[32];
     tmem_ld_32x32(tO + lane_off, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha, __uint_as_float(v[i]));
-    l_run = fmaf(l_run, alpha, rs);
-    m_run = m_new;
-    tc_fence_before();
+    for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha_prev, __uint_as_float(v[i]));
   }
-
   const int q_row = qb * 128 + tid;
   if (q_row < p.n) {
     const float inv = 1.f / l_run;
@@ -595,48 +656,26 @@ inline int make_tmap3_f16(CUtensorMap* m, const void* base, uint64_t d0, uint64_
 }
 
 // ----------------------------------------------------------------------------
-// out = conv3x3(x) (C -> Cl <= 8 latent channels; UNetModel.out[2], openaimodel.py:722-726) on the
-// already normalised + SiLU'd input, fused with the reference's "l2" score (model.py:260-262),
-// same outputs as final_conv_score_kernel.  w fp32 [Cl][C][3][3].  One thread per pixel.
-// grid (hw / 128, n_hyp); dynamic smem 9 * Cl * C floats.
+// UNetModel.out[2] (conv3x3, C -> Cl <= 8 latent channels, openaimodel.py:722-726) runs on the
+// tensor-core kernel with its output channels padded to 64 and an fp32 epilogue store
+// (ConvParams.out_f32); this kernel picks the Cl real channels out of o [n_hyp*hw][64] fp32,
+// writes the embeddings (NCHW fp32) and the reference's "l2" score partials
+// (model.py:260-262), same outputs as final_conv_score_kernel.  grid (hw / 128, n_hyp).
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFinalThreads)
-ldm_out_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ w,
-                          const float* __restrict__ bias, float* __restrict__ emb,
-                          const float* __restrict__ query, const int* __restrict__ ref_of,
-                          float* __restrict__ partial, int S, int C, int Cl) {
-  extern __shared__ float s_w3[];   // [tap][Cl][C]
+ldm_score_kernel(const float* __restrict__ o, float* __restrict__ emb, const float* __restrict__ query,
+                 const int* __restrict__ ref_of, float* __restrict__ partial, int hw, int Cl) {
   __shared__ float s_part[kFinalThreads / 32];
   const int slab = blockIdx.x, h = blockIdx.y, nslab = gridDim.x;
-  const int hw = S * S;
-  for (int i = threadIdx.x; i < 9 * Cl * C; i += kFinalThreads) {
-    const int cidx = i % C, cl = (i / C) % Cl, tap = i / (C * Cl);
-    s_w3[i] = w[((size_t)cl * C + cidx) * 9 + tap];
-  }
-  __syncthreads();
   const int p = slab * kFinalThreads + threadIdx.x;
-  float acc[kMaxLatent];
-#pragma unroll
-  for (int cc = 0; cc < kMaxLatent; ++cc) acc[cc] = (cc < Cl) ? bias[cc] : 0.f;
   float dist = 0.f;
   if (p < hw) {
-    const int py = p / S, px = p - py * S;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-      if (yy < 0 || yy >= S || xx < 0 || xx >= S) continue;
-      const __half* xp = x + ((size_t)h * hw + (size_t)yy * S + xx) * C;
-      const float* wt = s_w3 + (size_t)tap * Cl * C;
-      for (int k0 = 0; k0 < C; k0 += 8) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(xp + k0), f);
-#pragma unroll
-        for (int cc = 0; cc < kMaxLatent; ++cc)
-          if (cc < Cl) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[cc] = fmaf(f[i], wt[cc * C + k0 + i], acc[cc]);
-          }
-      }
-    }
+    const float* op = o + ((size_t)h * hw + p) * 64;
+    float acc[kMaxLatent];
+    const float4 a0 = *reinterpret_cast<const float4*>(op);
+    const float4 a1 = *reinterpret_cast<const float4*>(op + 4);
+    acc[0] = a0.x; acc[1] = a0.y; acc[2] = a0.z; acc[3] = a0.w;
+    acc[4] = a1.x; acc[5] = a1.y; acc[6] = a1.z; acc[7] = a1.w;
     if (emb) {
 #pragma unroll
       for (int cc = 0; cc < kMaxLatent; ++cc)
@@ -657,7 +696,7 @@ ldm_out_conv_score_kernel(const __half* __restrict__ x, const float* __restrict_
   }
   if (partial) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, o);
+    for (int off = 16; off > 0; off >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, off);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dist;
     __syncthreads();
     if (threadIdx.x == 0) {

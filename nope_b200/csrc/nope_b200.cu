@@ -1289,6 +1289,12 @@ int nope_ldm_set_impl(nope_ldm_t* m, int conv_impl, int attn_impl) {
   m->attn_impl = attn_impl;
   return 0;
 }
+int nope_ldm_set_option(nope_ldm_t* m, const char* name, int value) {
+  NOPE_CHECK(m && name, "null argument");
+  if (std::strcmp(name, "fuse_geglu") == 0) { m->fuse_geglu = value != 0; return 0; }
+  if (std::strcmp(name, "hoist") == 0) { m->hoist = value != 0; return 0; }
+  return fail(std::string("unknown option: ") + name);
+}
 int64_t nope_ldm_last_launch_count(const nope_ldm_t* m) { return m ? m->launches : 0; }
 
 int nope_ldm_sweep(nope_ldm_t* m, const float* ref_latent, const float* poses, int B, int N,

@@ -93,6 +93,9 @@ class UNetModelPose:
         _lib.check(_lib.load().nope_ldm_set_impl(self._handle(), {"tcgen05": 0, "tcgen05_2cta": 2}[conv],
                                                  {"tcgen05": 0, "simt": 1}[attn]))
 
+    def set_option(self, name, value):
+        _lib.check(_lib.load().nope_ldm_set_option(self._handle(), name.encode(), int(value)))
+
     @property
     def last_launch_count(self):
         return int(_lib.load().nope_ldm_last_launch_count(self._handle()))

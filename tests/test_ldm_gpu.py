@@ -131,6 +131,21 @@ def test_forward_vs_oracle(ldm_model, oracle_taps, golden, attn):
     assert e < EMB_TOL
 
 
+def test_geglu_fusion_matches_separate_kernel(ldm_model, oracle_taps):
+    """the GEGLU epilogue of the projection GEMM against the separate elementwise kernel"""
+    name = "input_blocks.4.1"
+    x = oracle_taps["input_blocks.4.0"]
+    want = oracle_taps["input_blocks.4"]
+    fused = ldm_model.run_block(name, x, poses=oracle_taps["poses"], out_channels=512, out_side=16)
+    ldm_model.set_option("fuse_geglu", 0)
+    try:
+        plain = ldm_model.run_block(name, x, poses=oracle_taps["poses"], out_channels=512, out_side=16)
+    finally:
+        ldm_model.set_option("fuse_geglu", 1)
+    log("ldm_geglu_fusion", fused=rel_l2(fused, want), separate=rel_l2(plain, want), fused_vs_separate=rel_l2(fused, plain))
+    assert rel_l2(fused, want) < BLOCK_TOL and rel_l2(plain, want) < BLOCK_TOL
+
+
 def test_taps_vs_oracle(ldm_model, oracle_taps, golden):
     """cumulative error along the network (informational thresholds: 2x the end-to-end tolerance)"""
     ref = torch.from_numpy(golden["ref_latent"])
@@ -163,6 +178,24 @@ def test_sweep_golden(ldm_model, golden):
     finally:
         ldm_model.set_chunk(8)
     assert torch.equal(out2["sim"][0], out["sim"][0])
+
+
+def test_hoisted_prefix_is_bitwise_neutral(ldm_model, golden):
+    """running the pose-independent prefix once per reference changes no bit of the result"""
+    ref = torch.from_numpy(golden["ref_latent"])
+    qry = torch.from_numpy(golden["query_latent"])
+    poses = torch.from_numpy(golden["all_relativeR"])
+    a = ldm_model.sweep(torch.cat([ref, qry]), torch.cat([poses, poses]), torch.cat([qry, ref]), want_emb=True, k=1)
+    n_hoist = ldm_model.last_launch_count
+    ldm_model.set_option("hoist", 0)
+    try:
+        b = ldm_model.sweep(torch.cat([ref, qry]), torch.cat([poses, poses]), torch.cat([qry, ref]), want_emb=True, k=1)
+        n_plain = ldm_model.last_launch_count
+    finally:
+        ldm_model.set_option("hoist", 1)
+    log("ldm_hoist", launches_hoisted=n_hoist, launches_plain=n_plain,
+        max_abs_diff=float((a["emb"] - b["emb"]).abs().max()))
+    assert torch.equal(a["emb"], b["emb"]) and torch.equal(a["sim"], b["sim"])
 
 
 def test_rejects_bad_input(ldm_model):
