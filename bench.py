@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--queries", type=int, default=1, help="queries (batch) per step")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("NOPE_CHUNK", "642")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="default", choices=["default", "ldm"],
+                    help="default: template_base UNet (BASELINE configs); ldm: the LDM-variant UNetModelPose "
+                         "sweep on latents (SURVEY.md 8 f2), an additional line for profiles/")
     ap.add_argument("--conv-impl", default=os.environ.get("NOPE_CONV_IMPL", "tcgen05_2cta"),
                     choices=["tcgen05", "tcgen05_2cta"])
     return ap.parse_args()
@@ -275,8 +278,141 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------
+def ldm_cpu_baseline(seconds=12.0, chunk=4):
+    """oracle/ldm_oracle.py (CPU port of UNetModelPose.forward) + the l2 score, hyp/s."""
+    import torch
+    from oracle import ldm_oracle, unet_oracle as orc
+    from nope_b200.synth_weights import make_ldm_state_dict
+    from nope_b200.poses import synthetic_pose_batch
+    sd = make_ldm_state_dict(seed=0)
+    g = torch.Generator().manual_seed(0)
+    rl = torch.randn(1, 4, 32, 32, generator=g)
+    ql = torch.randn(1, 4, 32, 32, generator=g)
+    poses, _ = synthetic_pose_batch(N_POSES, 1)
+    done = 0
+    with torch.no_grad():
+        threads = pick_threads(lambda: ldm_oracle.ldm_sweep(sd, rl, poses[:, :2], chunk=2))
+        t0 = time.time()
+        while time.time() - t0 < seconds and done + chunk <= N_POSES:
+            emb = ldm_oracle.ldm_sweep(sd, rl, poses[:, done:done + chunk], chunk=chunk)
+            orc.l2_similarity(ql, emb)
+            done += chunk
+    dt = time.time() - t0
+    return {"value": done / dt, "unit": "hyp/s", "cores": threads, "kind": "port",
+            "sample": f"first {done} poses of the {N_POSES}-pose grid, batched {chunk}/forward, fp32 torch-CPU "
+                      f"oracle of UNetModelPose, {threads} of {os.cpu_count()} host threads, {dt:.1f} s"}
+
+
+def main_ldm(args):
+    """LDM-variant sweep (UNetModelPose on VAE-sized latents): same metric and timing rules as main()."""
+    import torch
+    from nope_b200.ldm import UNetModelPose
+    from nope_b200.poses import synthetic_pose_batch
+    from nope_b200.synth_weights import ldm_flops_per_hyp, make_ldm_state_dict
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    assert int(os.environ.get("WORLD_SIZE", "1")) == 1, "--variant ldm is a single-GPU line"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n = args.poses
+    chunk = min(args.chunk, 642)
+    m = UNetModelPose(device=str(dev), chunk=chunk)
+    m.load_state_dict(make_ldm_state_dict(seed=0))
+    Q = args.queries
+    poses, _ = synthetic_pose_batch(n, Q)
+    g = torch.Generator().manual_seed(0)
+    ref_h = torch.randn(Q, 4, 32, 32, generator=g).pin_memory()
+    qry_h = torch.randn(Q, 4, 32, 32, generator=g).pin_memory()
+    poses_h = poses.clone().pin_memory()
+    ref_d, qry_d, poses_d = ref_h.to(dev), qry_h.to(dev), poses.to(dev)
+    h2d = (ref_h.numel() + qry_h.numel() + poses_h.numel()) * 4
+    d2h = Q * (5 * 8 + n * 4)
+
+    def step_resident():
+        return m.sweep(ref_d, poses_d, qry_d, want_emb=False, k=5)
+
+    def step_e2e():
+        out = m.sweep(ref_h.to(dev, non_blocking=True), poses_h.to(dev, non_blocking=True),
+                      qry_h.to(dev, non_blocking=True), want_emb=False, k=5)
+        return out["topi"].cpu(), out["sim"].cpu()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches = m.last_launch_count
+    clocks = sampler.stop()
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    m.profile(True)
+    step_resident()
+    prof = m.profile_read()
+    m.profile(False)
+    peak_tf, _, peak_src = measured_peaks()
+    gm, at = prof["gemm"], prof["attention"]
+    gemm_tf = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+    attn_tf = at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0
+    fl = ldm_flops_per_hyp()
+    value = Q * n / (ms * 1e-3)
+    cpu = None if args.no_cpu_baseline else ldm_cpu_baseline()
+    line = {
+        "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": {
+            "workload": f"LDM variant (SURVEY.md 8 f2): UNetModelPose of configs/model/vae_cin_ldm.yaml on 4x32x32 "
+                        f"latents, {n}-pose grid, batch={Q} query, fp16 storage / fp32 accumulate, l2 score + top-5",
+            "poses_per_gpu": n, "queries": Q, "chunk": chunk,
+            "weights": "seeded random init, reference state_dict schema (395.0 M params)",
+            "gflop_per_hyp": fl["total"] / 1e9,
+            "encoder": "none: the diffusers VAE of this variant is not in the reference tree; inputs are latents",
+            "l2": "not flushed: each step streams 0.79 GB of fp16 weights and > 5 GB of activations, >> 126 MB L2",
+        },
+        "clocks": clocks,
+        "e2e": {"value": Q * n / (ms_e2e * 1e-3), "unit": "hyp/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "UNetModelPose.sweep (pinned host latents + poses -> sweep -> top-5 -> host)"},
+        "gpu_launches": int(launches * args.steps),
+        "roofline": {
+            "bound": "tensor", "kernel": "conv_tc2_kernel (tcgen05 implicit-GEMM conv / linear layers)",
+            "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None,
+            "peak_source": f"{peak_src} (sustained bf16 cuBLAS)", "traffic": None,
+            "launches_per_step": gm["launches"], "gemm_ms_per_step": gm["ms"],
+            "gemm_share_of_step": gm["ms"] / ms if ms else None,
+            "algorithmic_tflop_per_step": gm["flops"] / 1e12,
+            "attention": {"kernel": "ldm_attn_tc_kernel (tcgen05 QK^T / PV, softmax in registers)",
+                          "achieved": attn_tf, "unit": "TFLOP/s", "ms_per_step": at["ms"],
+                          "launches_per_step": at["launches"], "share_of_step": at["ms"] / ms if ms else None},
+            "whole_step_tflops": value * fl["total"] / 1e12,
+        },
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
+    if args.variant == "ldm":
+        if args.impl == "reference":
+            line = {"impl": "reference", "metric": METRIC, "unit": "hyp/s", "higher_is_better": True}
+            cpu = ldm_cpu_baseline(seconds=20.0)
+            line.update({"value": cpu["value"], "cpu_baseline": cpu, "n_gpus": 1,
+                         "config": {"workload": "LDM variant, oracle port on host cores"},
+                         "e2e": {"value": cpu["value"], "unit": "hyp/s", "h2d_bytes_per_step": 0,
+                                 "d2h_bytes_per_step": 0}})
+            print(json.dumps(line))
+            return
+        main_ldm(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

@@ -188,6 +188,12 @@ int nope_ldm_sweep(nope_ldm_t* m, const float* ref_latent, const float* poses, i
                    const float* query_latent, float* out_emb, float* out_sim, int k,
                    float* out_topv, int64_t* out_topi, int64_t idx_base, void* stream);
 int64_t nope_ldm_last_launch_count(const nope_ldm_t* m);
+/* Profiling hook (bench.py roofline), as nope_unet_profile: CUDA events around every tensor-core
+ * GEMM / convolution launch (index 0) and every attention launch (index 1) of later sweeps.
+ * nope_ldm_profile_read fills ms[2], flops[2] (algorithmic, 2*M*N*K resp. 4*n^2*C per image),
+ * launches[2] and synchronises the device. */
+int nope_ldm_profile(nope_ldm_t* m, int enable);
+int nope_ldm_profile_read(nope_ldm_t* m, double* ms, double* flops, int64_t* launches);
 /* Debug: as nope_unet_debug_tap; tap names follow the reference's module paths
  * ("input_blocks.4.0" = ResBlock output, "input_blocks.4" = block output, "middle_block.1",
  * "output_blocks.2.1", "output_blocks.2", ...). */

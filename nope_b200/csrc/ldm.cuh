@@ -90,8 +90,8 @@ struct nope_ldm {
   int cap = 0, cap_ref = 0;
   std::vector<__half*> HS;                     // skip stack, one buffer per input block
   __half *XA = nullptr, *XB = nullptr, *XC = nullptr, *R = nullptr, *T1 = nullptr, *T2 = nullptr,
-         *T3 = nullptr, *XN = nullptr, *PI = nullptr, *PJ = nullptr, *QKV = nullptr, *Qp = nullptr,
-         *Kp = nullptr, *Vt = nullptr, *AO = nullptr, *FF = nullptr, *GG = nullptr, *x0ref = nullptr, *Rref = nullptr, *Pref = nullptr;
+         *T3 = nullptr, *XN = nullptr, *PI = nullptr, *PJ = nullptr, *QKV = nullptr,
+         *Vt = nullptr, *AO = nullptr, *FF = nullptr, *GG = nullptr, *x0ref = nullptr, *Rref = nullptr, *Pref = nullptr;
   float2 *S_in = nullptr, *S_mid = nullptr, *S_out = nullptr;
   float* cb = nullptr;
   float* OF = nullptr;                          // out[2] result, fp32 [cap * S0 * S0][64]
@@ -103,6 +103,28 @@ struct nope_ldm {
   std::vector<void*> ws_owned;
   std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;
   std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps3;
+
+  // per-launch CUDA-event profile (bench.py roofline): kind 0 = convolution / GEMM, 1 = attention
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<double> prof_flops;
+  std::vector<int> prof_kind;
+  int prof_begin(cudaStream_t st) {
+    cudaEvent_t e0;
+    NOPE_CUDA(cudaEventCreate(&e0));
+    NOPE_CUDA(cudaEventRecord(e0, st));
+    prof_ev.push_back(e0);
+    return 0;
+  }
+  int prof_end(cudaStream_t st, double flops, int kind) {
+    cudaEvent_t e1;
+    NOPE_CUDA(cudaEventCreate(&e1));
+    NOPE_CUDA(cudaEventRecord(e1, st));
+    prof_ev.push_back(e1);
+    prof_flops.push_back(flops);
+    prof_kind.push_back(kind);
+    return 0;
+  }
 
   // debug tap
   std::string tap_name;
@@ -116,6 +138,7 @@ struct nope_ldm {
     for (void* p : ws_owned) cudaFree(p);
     if (score_partial) cudaFree(score_partial);
     if (sim_buf) cudaFree(sim_buf);
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   }
 
   // ------------------------------------------------------------------ plan + schema
@@ -508,11 +531,10 @@ struct nope_ldm {
       }
     }
     // widest tensors: block outputs <= 2u (512 ch at 32^2 after the last upsample), ResBlock
-    // inputs <= 3u (768 ch at 32^2), q|k|v 3u, padded Q / K 2u each, GEGLU input 8u, output 4u
+    // inputs <= 3u (768 ch at 32^2), q|k|v 3u, V^T 1u, GEGLU input 8u, output 4u
     if (ws_half(&XA, c * 2 * u) || ws_half(&XB, c * 2 * u) || ws_half(&XC, c * 2 * u) || ws_half(&R, c * u) ||
         ws_half(&T1, c * 3 * u) || ws_half(&T2, c * u) || ws_half(&T3, c * u) || ws_half(&XN, c * u) ||
-        ws_half(&PI, c * u) || ws_half(&PJ, c * u) || ws_half(&QKV, c * 3 * u) || ws_half(&Qp, c * 2 * u) ||
-        ws_half(&Kp, c * 2 * u) || ws_half(&Vt, c * u) || ws_half(&AO, c * u) || ws_half(&FF, c * 8 * u) ||
+        ws_half(&PI, c * u) || ws_half(&PJ, c * u) || ws_half(&QKV, c * 3 * u) || ws_half(&Vt, c * u) || ws_half(&AO, c * u) || ws_half(&FF, c * 8 * u) ||
         ws_half(&GG, c * 4 * u) || ws_half(&x0ref, (size_t)cap_ref * u) || ws_half(&Rref, (size_t)cap_ref * u) ||
         ws_half(&Pref, (size_t)cap_ref * u))
       return -1;
@@ -634,7 +656,12 @@ struct nope_ldm {
     p.b_cnt = g.b_cnt;
     NOPE_CHECK(nseg <= kMaxSeg && ksteps * 64 == L.K, "conv: K mismatch");
     NOPE_CHECK(!((stats || res) && L.mode == 3), "upsample conv has no fused statistics / residual");
-    return conv_impl == 2 ? launch_conv_tc2(p, L.bn, num_sms, st) : launch_conv_tc(p, L.bn, num_sms, st);
+    if (profile && prof_begin(st)) return -1;
+    const int rc = conv_impl == 2 ? launch_conv_tc2(p, L.bn, num_sms, st) : launch_conv_tc(p, L.bn, num_sms, st);
+    // executed FLOPs (the folded upsample runs 4 parity GEMMs of K = 4 Cin over the source pixels)
+    if (profile && prof_end(st, 2.0 * (double)n_img * g.H * g.W * (double)(L.mode == 3 ? 4 * L.cout : L.cout) * (double)L.K, 0))
+      return -1;
+    return rc;
   }
 
   static int parts_of(int S) { return S * S < 32 ? 1 : S * S / 32; }
@@ -691,13 +718,14 @@ struct nope_ldm {
   int attention(const __half* qkv, __half* out, int C, int ntok, int n, cudaStream_t st) {
     using namespace nope;
     const int Hh = C / 32;
-    NOPE_CHECK(ntok % 64 == 0, "attention: token count must be a multiple of 64");
-    ldm_attn_prep_kernel<<<dim3(ntok / 64, n), 256, 0, st>>>(qkv, Qp, Kp, Vt, ntok, C);
+    NOPE_CHECK(ntok % 64 == 0 && C % 64 == 0, "attention: tokens and channels must be multiples of 64");
+    ldm_attn_prep_kernel<<<dim3(ntok / 64, n), 256, 0, st>>>(qkv, Vt, ntok, C);
     NOPE_CUDA(cudaGetLastError());
     const float sl2e = 0.17677669529663687f * 1.4426950408889634f;   // 32^-1/2 * log2(e)
     const dim3 grid(n * Hh, (ntok + 127) / 128);
+    if (profile && prof_begin(st)) return -1;
     if (attn_impl == 1) {
-      ldm_attn_simt_kernel<<<grid, 128, 0, st>>>(Qp, Kp, Vt, out, ntok, Hh, C, sl2e);
+      ldm_attn_simt_kernel<<<grid, 128, 0, st>>>(qkv, Vt, out, ntok, Hh, C, sl2e);
     } else {
       static bool attr_set = false;
       if (!attr_set) {
@@ -706,16 +734,15 @@ struct nope_ldm {
       }
       AttnParams p;
       const CUtensorMap* m = nullptr;
-      if (get_map3(&m, Qp, 64, ntok, n * Hh, 64, 128)) return -1;
-      p.qmap = *m;
-      if (get_map3(&m, Kp, 64, ntok, n * Hh, 64, 128)) return -1;
-      p.kmap = *m;
+      if (get_map3(&m, qkv, 3 * C, ntok, n, 64, 128)) return -1;
+      p.qkmap = *m;
       if (get_map3(&m, Vt, ntok, 32, n * Hh, 64, 32)) return -1;
       p.vmap = *m;
       p.out = out; p.n = ntok; p.H = Hh; p.C = C; p.scale_log2e = sl2e;
       ldm_attn_tc_kernel<<<grid, 128, kAttnSmem, st>>>(p);
     }
     NOPE_CUDA(cudaGetLastError());
+    if (profile && prof_end(st, 4.0 * (double)n * ntok * (double)ntok * C, 1)) return -1;
     launches += 2;
     return 0;
   }

@@ -100,6 +100,15 @@ class UNetModelPose:
     def last_launch_count(self):
         return int(_lib.load().nope_ldm_last_launch_count(self._handle()))
 
+    def profile(self, enable):
+        _lib.check(_lib.load().nope_ldm_profile(self._handle(), 1 if enable else 0))
+
+    def profile_read(self):
+        """-> {'gemm': {...}, 'attention': {...}} with ms / flops / launches since profile(True)."""
+        ms, fl, n = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int64 * 2)()
+        _lib.check(_lib.load().nope_ldm_profile_read(self._handle(), ms, fl, n))
+        return {k: {"ms": ms[i], "flops": fl[i], "launches": n[i]} for i, k in enumerate(("gemm", "attention"))}
+
     def sweep(self, ref_latent, poses, query_latent=None, want_emb=True, want_sim=None, k=0, idx_base=0):
         """ref_latent [B,C,32,32], poses [B,N,6] (+ query_latent) -> dict(emb, sim, topv, topi)."""
         if not self._finalized:

@@ -347,3 +347,50 @@ def make_ldm_state_dict(seed=0, model_channels=256, channel_mult=(1, 2, 4), cont
     g = torch.Generator(device="cpu").manual_seed(3000 + seed)
     return OrderedDict((k, _fill_ldm(k, shp, g)) for k, shp in
                        ldm_param_shapes(model_channels, channel_mult, context_dim=context_dim).items())
+
+
+def ldm_flops_per_hyp(model_channels=256, channel_mult=(1, 2, 4), num_res_blocks=2, latent=32,
+                      in_channels=4):
+    """Algorithmic FLOPs of one UNetModelPose.forward (2 x multiply-adds): convolutions / linear
+    layers as 2*M*N*K and the self-attention contractions (QK^T and PV); the one-token
+    cross-attention and the unused time embedding are not counted."""
+    inp, mid_ch, out = ldm_block_plan(model_channels, channel_mult, num_res_blocks)
+    gemm = 0.0
+    attn = 0.0
+
+    def res(cin, cout, hw):
+        f = 2.0 * hw * cout * cin * 9 + 2.0 * hw * cout * cout * 9
+        if cin != cout:
+            f += 2.0 * hw * cout * cin
+        return f
+
+    def st(c, hw):
+        lin = 2.0 * hw * c * c * (1 + 3 + 1 + 1) + 2.0 * hw * c * 8 * c + 2.0 * hw * 4 * c * c
+        return lin, 4.0 * hw * hw * c
+
+    S = latent
+    for b in inp:
+        if b[0] == "conv":
+            gemm += 2.0 * S * S * b[2] * in_channels * 9
+        elif b[0] == "res":
+            gemm += res(b[1], b[2], S * S)
+            l, a = st(b[2], S * S)
+            gemm += l
+            attn += a
+        else:
+            S //= 2
+            gemm += 2.0 * S * S * b[2] * b[1] * 9
+    gemm += 2 * res(mid_ch, mid_ch, S * S)
+    l, a = st(mid_ch, S * S)
+    gemm += l
+    attn += a
+    for b in out:
+        gemm += res(b[1], b[2], S * S)
+        l, a = st(b[2], S * S)
+        gemm += l
+        attn += a
+        if b[4]:
+            S *= 2
+            gemm += 2.0 * S * S * b[2] * b[2] * 9
+    gemm += 2.0 * S * S * in_channels * model_channels * 9
+    return {"gemm": gemm, "attention": attn, "total": gemm + attn}
