@@ -152,10 +152,34 @@ __device__ __forceinline__ int butterfly8(float (&v)[8], int lane) {
 // EXTRAS (compile time) enables ReLU / residual add / (hi, lo) split / fp32 output: the template
 // encoder's epilogue.  The sweep instantiates EXTRAS = false so its epilogue stays minimal (the
 // extra predicates and registers cost ~10 % on the large convolutions when merely present).
+// Residual operands (high halves) of a tile, software-pipelined ONE TILE AHEAD by the epilogue
+// warps: while sub-tile cc of tile i is being combined, the loads of sub-tile cc of tile i+1 are
+// already in flight (into the registers that sub-tile just vacated).  With the loads issued next to
+// their use, their ~1-2 us latency sat in front of every tile of the short-K 1x1 layers.
+template <int BN>
+struct ResPrefetch {
+  uint4 v[BN / 64][4];
+  int next_m_tile, next_n_chan0;    // tile whose operands are fetched next; next_m_tile < 0: none
+  __device__ __forceinline__ void load_sub(const ConvParams& p, int cc, int m_tile, int n_chan0, int e, int lane) {
+    const int q = e & 3, hh = e >> 2;
+    const int grow = m_tile * kBM + q * 32 + lane;
+    if (p.res_hi && m_tile >= 0 && grow < p.m_valid) {
+      const size_t roff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[cc][j] = *reinterpret_cast<const uint4*>(p.res_hi + roff + j * 8);
+    }
+  }
+  __device__ __forceinline__ void load(const ConvParams& p, int m_tile, int n_chan0, int e, int lane) {
+#pragma unroll
+    for (int cc = 0; cc < BN / 64; ++cc) load_sub(p, cc, m_tile, n_chan0, e, lane);
+  }
+};
+
 template <int BN, bool EXTRAS>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t* out_stage,
                                                    const float* s_bias, uint32_t t_acc, int m_tile,
-                                                   int n_chan0, int e, int lane) {
+                                                   int n_chan0, int e, int lane,
+                                                   ResPrefetch<BN>* pre = nullptr) {
   const int q = e & 3, hh = e >> 2;
   const int row = q * 32 + lane;
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
@@ -176,10 +200,11 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       const size_t roff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        rh[j] = *reinterpret_cast<const uint4*>(p.res_hi + roff + j * 8);
+        rh[j] = pre ? pre->v[cc][j] : *reinterpret_cast<const uint4*>(p.res_hi + roff + j * 8);
         rl[j] = p.res_lo ? *reinterpret_cast<const uint4*>(p.res_lo + roff + j * 8) : make_uint4(0, 0, 0, 0);
       }
     }
+    if (EXTRAS && pre) pre->load_sub(p, cc, pre->next_m_tile, pre->next_n_chan0, e, lane);   // next tile, same sub-tile
     float st[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {   // 4 x 16-byte chunks of 8 channels

@@ -228,6 +228,13 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     const int etid = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
+    ResPrefetch<BN> pre;
+    if constexpr (EPI == 1) {
+      if (tile0 < num_tiles) {     // operands of this CTA's first tile (residual convs have n_par == 1)
+        const int mp0 = tile0 / p.n_tiles;
+        pre.load(p, 2 * mp0 + (int)rank, (tile0 - mp0 * p.n_tiles) * BN, e, lane);
+      }
+    }
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_pair = tile / p.n_tiles;
       const int n_tile = tile - m_pair * p.n_tiles;
@@ -237,14 +244,22 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
       if (etid < BN) s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
+      if constexpr (EPI == 1) {
+        const int nt = tile + tile_step;
+        const int nmp = nt / p.n_tiles;
+        pre.next_m_tile = nt < num_tiles ? 2 * nmp + (int)rank : -1;
+        pre.next_n_chan0 = (nt - nmp * p.n_tiles) * BN;
+      }
       if (etid == 0) tma_store_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if constexpr (EPI == 2)
         conv_epilogue_geglu(out_stage, s_bias, tmem_base + acc * BN, e, lane);
+      else if constexpr (EPI == 1)
+        conv_epilogue_tile<BN, true>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane, &pre);
       else
-        conv_epilogue_tile<BN, EPI == 1>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
+        conv_epilogue_tile<BN, false>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       // this CTA's accumulator half is drained: tell the leader's MMA warp
       tc_fence_before();
       __syncwarp();

@@ -722,7 +722,7 @@ struct nope_ldm {
     ldm_attn_prep_kernel<<<dim3(ntok / 64, n), 256, 0, st>>>(qkv, Vt, ntok, C);
     NOPE_CUDA(cudaGetLastError());
     const float sl2e = 0.17677669529663687f * 1.4426950408889634f;   // 32^-1/2 * log2(e)
-    const dim3 grid(n * Hh, (ntok + 127) / 128);
+    const dim3 grid((unsigned)(n * Hh) * (unsigned)((ntok + 127) / 128));
     if (profile && prof_begin(st)) return -1;
     if (attn_impl == 1) {
       ldm_attn_simt_kernel<<<grid, 128, 0, st>>>(qkv, Vt, out, ntok, Hh, C, sl2e);

@@ -371,9 +371,11 @@ __global__ void __launch_bounds__(128, 2) ldm_attn_tc_kernel(const __grid_consta
   uint64_t* bar_o = bar_q + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 8);
 
-  const int bh = blockIdx.x, qb = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // query blocks of one (image, head) are adjacent CTAs: they run together and share K / V^T in L2
+  // (with the head-major order of the first version every query block re-read them from DRAM)
   const int nblk = (p.n + 127) / 128;
+  const int bh = blockIdx.x / nblk, qb = blockIdx.x - bh * nblk;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int img = bh / p.H, head = bh - img * p.H;
   const int qc0 = (head >> 1) * 64, kc0 = p.C + qc0;      // channel of the head pair's 64-wide box
   const uint32_t kstep0 = (head & 1) * 4;                   // descriptor offset (>>4) of this head's 32 channels
@@ -578,7 +580,8 @@ ldm_attn_simt_kernel(const __half* __restrict__ qkv, const __half* __restrict__ 
                      __half* __restrict__ out, int n, int H, int C, float scale_log2e) {
   __shared__ float sK[64][33];
   __shared__ float sVt[32][65];
-  const int bh = blockIdx.x, qb = blockIdx.y, tid = threadIdx.x;
+  const int nqb = (n + 127) / 128;
+  const int bh = blockIdx.x / nqb, qb = blockIdx.x - bh * nqb, tid = threadIdx.x;
   const int q_row = qb * 128 + tid;
   float q[32], O[32];
 #pragma unroll
