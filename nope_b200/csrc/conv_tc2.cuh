@@ -107,7 +107,10 @@ struct Conv2Smem {
   static constexpr int kBBytes = (BN / 2) * kBK * 2;      // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = (BN / 64) * kBM * 128;
-  static constexpr int kBarOffset = STAGES * kStageBytes + kOutBytes;
+  // narrow tiles double-buffer the output staging: the TMA store of tile i drains while the
+  // epilogue of tile i+1 fills the other buffer (the short-K 1x1 layers are epilogue bound)
+  static constexpr int kOutBufs = BN <= 128 ? 2 : 1;
+  static constexpr int kBarOffset = STAGES * kStageBytes + kOutBufs * kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
   static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;
 };
@@ -228,8 +231,10 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     const int etid = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
-    ResPrefetch<BN> pre;
-    if constexpr (EPI == 1) {
+    int obuf = 0;
+    constexpr bool kPrefetchRes = EPI == 1 && BN <= 128;   // 32 registers; wider tiles load in place
+    ResPrefetch<kPrefetchRes ? BN : 64> pre;
+    if constexpr (kPrefetchRes) {
       if (tile0 < num_tiles) {     // operands of this CTA's first tile (residual convs have n_par == 1)
         const int mp0 = tile0 / p.n_tiles;
         pre.load(p, 2 * mp0 + (int)rank, (tile0 - mp0 * p.n_tiles) * BN, e, lane);
@@ -244,22 +249,28 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       int b0, y0;
       conv_tile_coords(p, m_tile, b0, y0);
       if (etid < BN) s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
-      if constexpr (EPI == 1) {
+      if constexpr (kPrefetchRes) {
         const int nt = tile + tile_step;
         const int nmp = nt / p.n_tiles;
         pre.next_m_tile = nt < num_tiles ? 2 * nmp + (int)rank : -1;
         pre.next_n_chan0 = (nt - nmp * p.n_tiles) * BN;
       }
-      if (etid == 0) tma_store_wait_read0();
+      uint8_t* ost = out_stage + obuf * S::kOutBytes;
+      if (etid == 0) {       // the store that last used this staging buffer has read it
+        if constexpr (S::kOutBufs == 2) tma_store_wait_read1();
+        else tma_store_wait_read0();
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if constexpr (EPI == 2)
-        conv_epilogue_geglu(out_stage, s_bias, tmem_base + acc * BN, e, lane);
+        conv_epilogue_geglu(ost, s_bias, tmem_base + acc * BN, e, lane);
+      else if constexpr (kPrefetchRes)
+        conv_epilogue_tile<BN, true>(p, ost, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane, &pre);
       else if constexpr (EPI == 1)
-        conv_epilogue_tile<BN, true>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane, &pre);
+        conv_epilogue_tile<BN, true>(p, ost, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       else
-        conv_epilogue_tile<BN, false>(p, out_stage, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
+        conv_epilogue_tile<BN, false>(p, ost, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       // this CTA's accumulator half is drained: tell the leader's MMA warp
       tc_fence_before();
       __syncwarp();
@@ -271,14 +282,15 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (etid == 0) {
         if constexpr (EPI == 2) {
-          tma_store_4d(&p.omap[0], out_stage, n_chan0 / 2, 0, y0, b0);
+          tma_store_4d(&p.omap[0], ost, n_chan0 / 2, 0, y0, b0);
         } else {
 #pragma unroll 1
           for (int cc = 0; cc < BN / 64; ++cc)
-            tma_store_4d(&p.omap[par], out_stage + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
+            tma_store_4d(&p.omap[par], ost + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
         }
         tma_store_commit();
       }
+      obuf ^= S::kOutBufs - 1;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -311,13 +323,18 @@ inline int launch_conv_tc2(const ConvParams& p, int bn, int num_sms, cudaStream_
   const bool ex = conv_needs_extras(p);
   if (p.geglu) {
     if (bn != 128 || ex || p.stats || p.n_par != 1) return fail("launch_conv_tc2: GEGLU epilogue needs BN = 128, no extras");
-    return launch_conv_tc2_t<128, 7, 2>(p, num_sms, stream);
+    return launch_conv_tc2_t<128, 6, 2>(p, num_sms, stream);
   }
   switch (bn) {
+    // 256-wide tiles (LDM variant: every width is a multiple of 256): per K-step a CTA reads
+    // 16 KB of A + 16 KB of B for 128 tensor-core clocks, against 16 + 8 KB for 64 clocks at
+    // BN = 128, which sits exactly on the 128 B/clk shared-memory read limit
+    case 256: return ex ? launch_conv_tc2_t<256, 5, 1>(p, num_sms, stream)
+                        : launch_conv_tc2_t<256, 5, 0>(p, num_sms, stream);
     case 192: return ex ? launch_conv_tc2_t<192, 6, 1>(p, num_sms, stream)
                         : launch_conv_tc2_t<192, 6, 0>(p, num_sms, stream);
-    case 128: return ex ? launch_conv_tc2_t<128, 7, 1>(p, num_sms, stream)
-                        : launch_conv_tc2_t<128, 7, 0>(p, num_sms, stream);
+    case 128: return ex ? launch_conv_tc2_t<128, 6, 1>(p, num_sms, stream)
+                        : launch_conv_tc2_t<128, 6, 0>(p, num_sms, stream);
     case 64: return ex ? launch_conv_tc2_t<64, 8, 1>(p, num_sms, stream)
                        : launch_conv_tc2_t<64, 8, 0>(p, num_sms, stream);
   }

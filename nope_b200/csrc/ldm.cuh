@@ -35,7 +35,9 @@ namespace nope {
 
 struct LdmConv {
   int mode = 0;   // 0: 3x3 pad 1, 1: 1x1 / linear, 3: nearest-x2 + 3x3 (folded), 4: 3x3 stride 2 pad 1
-  int cin = 0, cout = 0, K = 0, bn = 0;
+  int cin = 0, cout = 0, K = 0;
+  int bn = 0;              // tile width of the 2-CTA kernel (up to 256)
+  int bn1 = 0;             // tile width of the 1-CTA kernel (up to 192)
   int skip_c = 0;          // channels of a folded 1x1 skip_connection (extra K columns)
   bool geglu = false;      // rows permuted to (64 x | 64 gate) tiles; the epilogue emits x * gelu(gate)
   __half* w = nullptr;     // [rows][K] fp16
@@ -68,6 +70,7 @@ struct nope_ldm {
   bool finalized = false;
   int conv_impl = 2;   // 2: tcgen05 CTA pairs (default), 0: tcgen05 1-CTA tiles
   int attn_impl = 0;   // 0: tcgen05 attention, 1: CUDA-core twin
+  bool wide_tiles = true;   // 256-channel tiles on the 2-CTA kernel where Cout % 256 == 0 (set before finalize)
   bool hoist = true;        // pose-independent prefix once per reference (prestage)
   bool fuse_geglu = true;   // GEGLU in the projection's epilogue (2-CTA kernel); false: separate kernel
   int chunk = 256;
@@ -292,10 +295,11 @@ struct nope_ldm {
   }
   int finish_conv(const std::string& name, nope::LdmConv& L, int rows, const std::vector<float>& bias) {
     using namespace nope;
-    L.bn = pick_bn(L.cout);
+    L.bn1 = pick_bn(L.cout);
+    L.bn = (!L.geglu && L.cout % 256 == 0 && wide_tiles) ? 256 : L.bn1;
     NOPE_CHECK(L.bn != 0 && L.K % 64 == 0, name + ": channel counts must be multiples of 64");
     if (!bias.empty() && upload(bias, &L.bias)) return -1;
-    if (make_weight_map(&L.wmap, L.w, rows, L.K, L.bn)) return -1;
+    if (make_weight_map(&L.wmap, L.w, rows, L.K, L.bn1)) return -1;
     if (make_weight_map(&L.wmap_half, L.w, rows, L.K, L.bn / 2)) return -1;
     convs[name] = L;
     return 0;
@@ -649,7 +653,8 @@ struct nope_ldm {
     p.nseg = nseg;
     p.ksteps = ksteps;
     p.m_tiles = geom_m_tiles(g, n_img);
-    p.n_tiles_par = L.cout / L.bn;
+    const int bn = conv_impl == 2 ? L.bn : L.bn1;
+    p.n_tiles_par = L.cout / bn;
     p.n_tiles = p.n_tiles_par * p.n_par;
     p.tiles_per_img = g.tiles_per_img;
     p.h_cnt = g.h_cnt;
@@ -657,7 +662,7 @@ struct nope_ldm {
     NOPE_CHECK(nseg <= kMaxSeg && ksteps * 64 == L.K, "conv: K mismatch");
     NOPE_CHECK(!((stats || res) && L.mode == 3), "upsample conv has no fused statistics / residual");
     if (profile && prof_begin(st)) return -1;
-    const int rc = conv_impl == 2 ? launch_conv_tc2(p, L.bn, num_sms, st) : launch_conv_tc(p, L.bn, num_sms, st);
+    const int rc = conv_impl == 2 ? launch_conv_tc2(p, bn, num_sms, st) : launch_conv_tc(p, bn, num_sms, st);
     // executed FLOPs (the folded upsample runs 4 parity GEMMs of K = 4 Cin over the source pixels)
     if (profile && prof_end(st, 2.0 * (double)n_img * g.H * g.W * (double)(L.mode == 3 ? 4 * L.cout : L.cout) * (double)L.K, 0))
       return -1;
@@ -692,7 +697,8 @@ struct nope_ldm {
          cudaStream_t st, const int* src_img = nullptr) {
     using namespace nope;
     const long long ntok = (long long)n * S * S;
-    const unsigned grid = (unsigned)((ntok + 7) / 8);
+    const int tpw = 1024 / C;                               // tokens per warp (ldm_ln_kernel)
+    const unsigned grid = (unsigned)((ntok + 8 * tpw - 1) / (8 * tpw));
     switch (C) {
       case 256: ldm_ln_kernel<1><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S, src_img); break;
       case 512: ldm_ln_kernel<2><<<grid, 256, 0, st>>>(x, xout, cbp, cb_width, N.gamma, N.beta, y, ntok, S * S, src_img); break;

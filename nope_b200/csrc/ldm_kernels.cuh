@@ -181,63 +181,74 @@ ldm_ln_kernel(const __half* __restrict__ x, __half* __restrict__ xout, const flo
               int cb_stride, const float* __restrict__ gamma, const float* __restrict__ beta,
               __half* __restrict__ y, long long n_tok, int tok_per_img, const int* __restrict__ src_img) {
   constexpr int C = 256 * NV;
-  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int TPW = 4 / NV;      // tokens in flight per warp: 1024 channels = 4 x 16-byte loads per lane
+  const long long tok0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * TPW;
   const int lane = threadIdx.x & 31;
-  if (tok >= n_tok) return;
-  float f[NV][8];
+  if (tok0 >= n_tok) return;
+  float f[TPW][NV][8];
+  long long img[TPW];
   // src_img: x holds one image per REFERENCE (pose-independent prefix); hypothesis i reads image
   // src_img[i] of it.  Outputs are always per hypothesis.
-  const long long img = tok / tok_per_img;
-  const long long src_tok = src_img ? (long long)src_img[img] * tok_per_img + (tok - img * tok_per_img) : tok;
-  const __half* xp = x + src_tok * C;
 #pragma unroll
-  for (int j = 0; j < NV; ++j)
-    unpack8(*reinterpret_cast<const uint4*>(xp + (j * 32 + lane) * 8), f[j]);
-  if (cb) {
-    const float* cp = cb + (size_t)img * cb_stride;
+  for (int t = 0; t < TPW; ++t) {
+    const long long tok = tok0 + t < n_tok ? tok0 + t : n_tok - 1;    // clamp: tail tokens recompute the last one
+    img[t] = tok / tok_per_img;
+    const long long src_tok = src_img ? (long long)src_img[img[t]] * tok_per_img + (tok - img[t] * tok_per_img) : tok;
+    const __half* xp = x + src_tok * C;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      unpack8(*reinterpret_cast<const uint4*>(xp + (j * 32 + lane) * 8), f[t][j]);
+  }
+#pragma unroll
+  for (int t = 0; t < TPW; ++t) {
+    const long long tok = tok0 + t;
+    if (tok >= n_tok) break;
+    if (cb) {
+      const float* cp = cb + (size_t)img[t] * cb_stride;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 c0 = *reinterpret_cast<const float4*>(cp + (j * 32 + lane) * 8);
+        const float4 c1 = *reinterpret_cast<const float4*>(cp + (j * 32 + lane) * 8 + 4);
+        f[t][j][0] += c0.x; f[t][j][1] += c0.y; f[t][j][2] += c0.z; f[t][j][3] += c0.w;
+        f[t][j][4] += c1.x; f[t][j][5] += c1.y; f[t][j][6] += c1.z; f[t][j][7] += c1.w;
+        const uint4 w = pack8(f[t][j]);
+        *reinterpret_cast<uint4*>(xout + tok * C + (j * 32 + lane) * 8) = w;
+        unpack8(w, f[t][j]);     // normalise what is stored (the residual the next layer adds)
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[t][j][i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = f[t][j][i] - mean;
+        q = fmaf(d, d, q);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const float4 c0 = *reinterpret_cast<const float4*>(cp + (j * 32 + lane) * 8);
-      const float4 c1 = *reinterpret_cast<const float4*>(cp + (j * 32 + lane) * 8 + 4);
-      f[j][0] += c0.x; f[j][1] += c0.y; f[j][2] += c0.z; f[j][3] += c0.w;
-      f[j][4] += c1.x; f[j][5] += c1.y; f[j][6] += c1.z; f[j][7] += c1.w;
-      const uint4 w = pack8(f[j]);
-      *reinterpret_cast<uint4*>(xout + tok * C + (j * 32 + lane) * 8) = w;
-      unpack8(w, f[j]);     // normalise what is stored (the residual the next layer adds)
+      const int c = (j * 32 + lane) * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] = fmaf((f[t][j][i] - mean) * rstd, gm[i], bt[i]);
+      *reinterpret_cast<uint4*>(y + tok * C + c) = pack8(o8);
     }
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < NV; ++j)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += f[j][i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.f / C);
-  float q = 0.f;
-#pragma unroll
-  for (int j = 0; j < NV; ++j)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float d = f[j][i] - mean;
-      q = fmaf(d, d, q);
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int c = (j * 32 + lane) * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c);
-    const float4 g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(beta + c + 4);
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float o8[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o8[i] = fmaf((f[j][i] - mean) * rstd, gm[i], bt[i]);
-    *reinterpret_cast<uint4*>(y + tok * C + c) = pack8(o8);
   }
 }
 
