@@ -182,7 +182,10 @@ int nope_ldm_set_impl(nope_ldm_t* m, int conv_impl, int attn_impl);
 /* Named switches (bring-up / A-B measurements): "fuse_geglu" (default 1: GEGLU runs in the
  * epilogue of its projection GEMM; 0: separate elementwise kernel), "hoist" (default 1: the
  * pose-independent prefix -- input conv, first ResBlock, first transformer up to its
- * self-attention -- runs once per reference instead of once per hypothesis). */
+ * self-attention -- runs once per reference instead of once per hypothesis); before
+ * nope_ldm_finalize only: "wide_tiles" (default 1: 256-channel GEMM tiles on the CTA-pair kernel),
+ * "fold_residual" (default 1: residual adds ride in the GEMM as identity K-segments fed by TMA;
+ * 0: added in the epilogue from global memory). */
 int nope_ldm_set_option(nope_ldm_t* m, const char* name, int value);
 int nope_ldm_sweep(nope_ldm_t* m, const float* ref_latent, const float* poses, int B, int N,
                    const float* query_latent, float* out_emb, float* out_sim, int k,

@@ -38,7 +38,8 @@ struct LdmConv {
   int cin = 0, cout = 0, K = 0;
   int bn = 0;              // tile width of the 2-CTA kernel (up to 256)
   int bn1 = 0;             // tile width of the 1-CTA kernel (up to 192)
-  int skip_c = 0;          // channels of a folded 1x1 skip_connection (extra K columns)
+  int skip_c = 0;          // channels of a folded 1x1 skip_connection / identity residual (extra K columns)
+  int k_alg = 0;           // K without identity-residual columns (algorithmic FLOP count)
   bool geglu = false;      // rows permuted to (64 x | 64 gate) tiles; the epilogue emits x * gelu(gate)
   __half* w = nullptr;     // [rows][K] fp16
   float* bias = nullptr;
@@ -70,6 +71,7 @@ struct nope_ldm {
   bool finalized = false;
   int conv_impl = 2;   // 2: tcgen05 CTA pairs (default), 0: tcgen05 1-CTA tiles
   int attn_impl = 0;   // 0: tcgen05 attention, 1: CUDA-core twin
+  bool fold_residual = true;   // residual adds as identity K-segments of the GEMM (set before finalize)
   bool wide_tiles = true;   // 256-channel tiles on the 2-CTA kernel where Cout % 256 == 0 (set before finalize)
   bool hoist = true;        // pose-independent prefix once per reference (prestage)
   bool fuse_geglu = true;   // GEGLU in the projection's epilogue (2-CTA kernel); false: separate kernel
@@ -295,6 +297,7 @@ struct nope_ldm {
   }
   int finish_conv(const std::string& name, nope::LdmConv& L, int rows, const std::vector<float>& bias) {
     using namespace nope;
+    if (L.k_alg == 0) L.k_alg = L.K;
     L.bn1 = pick_bn(L.cout);
     L.bn = (!L.geglu && L.cout % 256 == 0 && wide_tiles) ? 256 : L.bn1;
     NOPE_CHECK(L.bn != 0 && L.K % 64 == 0, name + ": channel counts must be multiples of 64");
@@ -332,6 +335,35 @@ struct nope_ldm {
     }
     return finish_conv(name, L, rows, bias);
   }
+  // [c][c] identity as a host "weight": a residual add rides in the GEMM as one more K-segment
+  // (out = W x + I r).  The product of an fp16 value with 1.0 is exact and accumulates in fp32, so
+  // this is the same arithmetic as adding r in the epilogue -- but r arrives through TMA like any
+  // other operand instead of through per-row global loads in the epilogue (which stalled the short
+  // 1x1 layers on long-scoreboard waits), the plain epilogue and the 256-wide tiles apply, and the
+  // extra MMAs land on a tensor pipe that idles in these layers anyway.
+  static HostT identity(int c) {
+    HostT t;
+    t.first = {c, c};
+    t.second.assign((size_t)c * c, 0.f);
+    for (int i = 0; i < c; ++i) t.second[(size_t)i * c + i] = 1.f;
+    return t;
+  }
+  // linear layer (1x1) whose output gets a residual of `cout` channels added
+  int make_lin_res(const std::string& name, const std::string& wkey, const std::string& bkey) {
+    if (!fold_residual) return make_conv(name, wkey, bkey, 1);
+    const HostT& W = H(wkey);
+    nope::LdmConv L;
+    L.mode = 1;
+    L.cout = (int)W.first[0];
+    L.cin = (int)W.first[1];
+    L.skip_c = L.cout;
+    L.K = L.cin + L.skip_c;
+    L.k_alg = L.cin;
+    if (alloc_w(L, L.cout)) return -1;
+    if (pack_into(L.w, L.K, 0, 0, W, L.cout, L.cin, 1) || pack_into(L.w, L.K, 0, L.cin, identity(L.cout), L.cout, L.cout, 1))
+      return -1;
+    return finish_conv(name, L, L.cout, H(bkey).second);
+  }
   int make_norm(const std::string& name, const std::string& prefix) {
     nope::LdmNorm n;
     n.C = (int)H(prefix + ".weight").first[0];
@@ -360,11 +392,15 @@ struct nope_ldm {
       const auto& bs = H(p + ".skip_connection.bias").second;
       for (size_t i = 0; i < bias.size(); ++i) bias[i] += bs[i];
     }
+    const bool id_skip = !has_skip && fold_residual;      // identity skip as an identity K-segment
+    if (id_skip) L.skip_c = L.cout;
     L.K = 9 * L.cin + L.skip_c;
+    if (id_skip) L.k_alg = 9 * L.cin;
     if (alloc_w(L, L.cout)) return -1;
     if (pack_into(L.w, L.K, 0, 0, W2, L.cout, L.cin, 9)) return -1;
     if (has_skip && pack_into(L.w, L.K, 0, 9 * L.cin, H(p + ".skip_connection.weight"), L.cout, L.skip_c, 1))
       return -1;
+    if (id_skip && pack_into(L.w, L.K, 0, 9 * L.cin, identity(L.cout), L.cout, L.cout, 1)) return -1;
     return finish_conv(p + ".c2", L, L.cout, bias);
   }
   int make_st(const std::string& p) {
@@ -372,8 +408,8 @@ struct nope_ldm {
     const int c = (int)H(p + ".norm.weight").first[0];
     if (make_norm(p + ".norm", p + ".norm")) return -1;
     if (make_conv(p + ".proj_in", p + ".proj_in.weight", p + ".proj_in.bias", 1)) return -1;
-    if (make_conv(p + ".proj_out", p + ".proj_out.weight", p + ".proj_out.bias", 1)) return -1;
-    if (make_conv(p + ".to_out", t + ".attn1.to_out.0.weight", t + ".attn1.to_out.0.bias", 1)) return -1;
+    if (make_lin_res(p + ".proj_out", p + ".proj_out.weight", p + ".proj_out.bias")) return -1;
+    if (make_lin_res(p + ".to_out", t + ".attn1.to_out.0.weight", t + ".attn1.to_out.0.bias")) return -1;
     if (make_conv(p + ".ff1", t + ".ff.net.0.proj.weight", t + ".ff.net.0.proj.bias", 1)) return -1;
     {  // the same projection with GEGLU fused into the epilogue (2-CTA kernel): tile t of 128 rows =
        // x rows 64t..64t+63 followed by gate rows inner+64t..inner+64t+63
@@ -403,7 +439,7 @@ struct nope_ldm {
         return -1;
       NOPE_CHECK(convs.at(p + ".ff1g").bn == 128, "GEGLU projection must tile by 128");
     }
-    if (make_conv(p + ".ff2", t + ".ff.net.2.weight", t + ".ff.net.2.bias", 1)) return -1;
+    if (make_lin_res(p + ".ff2", t + ".ff.net.2.weight", t + ".ff.net.2.bias")) return -1;
     {  // q | k | v of the self-attention as one GEMM (no bias, ldm/attention.py:160-162)
       nope::LdmConv L;
       L.mode = 1;
@@ -614,7 +650,7 @@ struct nope_ldm {
       }
     }
     if (L.skip_c) {
-      NOPE_CHECK(L.mode == 0 && sk0 && skc0 % 64 == 0 && skc1 % 64 == 0, "conv: bad skip sources");
+      NOPE_CHECK((L.mode == 0 || L.mode == 1) && sk0 && skc0 % 64 == 0 && skc1 % 64 == 0, "conv: bad skip sources");
       if (get_map(&m, sk0, skc0, g, -1)) return -1;
       p.amap[nmaps] = *m;
       p.seg[nseg++] = ConvSeg{(int16_t)nmaps, 0, 0, (int16_t)(skc0 / 64)};
@@ -664,9 +700,16 @@ struct nope_ldm {
     if (profile && prof_begin(st)) return -1;
     const int rc = conv_impl == 2 ? launch_conv_tc2(p, bn, num_sms, st) : launch_conv_tc(p, bn, num_sms, st);
     // executed FLOPs (the folded upsample runs 4 parity GEMMs of K = 4 Cin over the source pixels)
-    if (profile && prof_end(st, 2.0 * (double)n_img * g.H * g.W * (double)(L.mode == 3 ? 4 * L.cout : L.cout) * (double)L.K, 0))
+    if (profile && prof_end(st, 2.0 * (double)n_img * g.H * g.W * (double)(L.mode == 3 ? 4 * L.cout : L.cout) * (double)L.k_alg, 0))
       return -1;
     return rc;
+  }
+
+  // out = L(in) + res: residual as an identity K-segment (fold_residual) or in the epilogue
+  int lin_res(const nope::LdmConv& L, const __half* in, __half* out, const __half* res, int C, int S, int n,
+              cudaStream_t st) {
+    if (L.skip_c) return conv(L, in, out, S, n, st, nullptr, nullptr, res, C);
+    return conv(L, in, out, S, n, st, nullptr, res);
   }
 
   static int parts_of(int S) { return S * S < 32 ? 1 : S * S / 32; }
@@ -775,7 +818,7 @@ struct nope_ldm {
     if (gn(norms.at(p + ".n2"), T2, c1.cout, nullptr, 0, S_mid, S, n, T3, true, 1e-5f, st)) return -1;
     if (c2.skip_c) return conv(c2, T3, out, S, n, st, S_out, nullptr, x0, C0, x1, C1);
     NOPE_CHECK(x1 == nullptr && C0 == c2.cout, "resblock: identity skip needs Cin == Cout");
-    return conv(c2, T3, out, S, n, st, S_out, x0);
+    return conv(c2, T3, out, S, n, st, S_out, x0);    // epilogue add (fold_residual off)
   }
 
   // SpatialTransformer.forward (ldm/attention.py:264-277) with one BasicTransformerBlock
@@ -787,7 +830,7 @@ struct nope_ldm {
     if (ln(norms.at(p + ".ln1"), PI, nullptr, nullptr, XN, C, S, n, st)) return -1;
     if (conv(convs.at(p + ".qkv"), XN, QKV, S, n, st)) return -1;
     if (attention(QKV, AO, C, S * S, n, st)) return -1;
-    return conv(convs.at(p + ".to_out"), AO, xs, S, n, st, nullptr, PI);
+    return lin_res(convs.at(p + ".to_out"), AO, xs, PI, C, S, n, st);
   }
   // st_post: x = attn2(norm2(x), context) + x -- the one-token cross-attention is the
   // per-hypothesis vector cb (see make_cross), added by the LayerNorm kernel, which also applies
@@ -806,8 +849,8 @@ struct nope_ldm {
       NOPE_CUDA(cudaGetLastError());
       ++launches;
     }
-    if (conv(convs.at(p + ".ff2"), GG, PI, S, n, st, nullptr, PJ)) return -1;
-    return conv(convs.at(p + ".proj_out"), PI, out, S, n, st, nullptr, x_in);
+    if (lin_res(convs.at(p + ".ff2"), GG, PI, PJ, C, S, n, st)) return -1;
+    return lin_res(convs.at(p + ".proj_out"), PI, out, x_in, C, S, n, st);
   }
   int transformer(const std::string& p, const __half* x_in, __half* out, int C, int S, int n, const float* cbp,
                   cudaStream_t st) {

@@ -1293,6 +1293,11 @@ int nope_ldm_set_option(nope_ldm_t* m, const char* name, int value) {
   NOPE_CHECK(m && name, "null argument");
   if (std::strcmp(name, "fuse_geglu") == 0) { m->fuse_geglu = value != 0; return 0; }
   if (std::strcmp(name, "hoist") == 0) { m->hoist = value != 0; return 0; }
+  if (std::strcmp(name, "fold_residual") == 0) {
+    NOPE_CHECK(!m->finalized, "fold_residual must be set before finalize");
+    m->fold_residual = value != 0;
+    return 0;
+  }
   if (std::strcmp(name, "wide_tiles") == 0) {
     NOPE_CHECK(!m->finalized, "wide_tiles must be set before finalize");
     m->wide_tiles = value != 0;

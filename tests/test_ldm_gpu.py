@@ -198,6 +198,21 @@ def test_hoisted_prefix_is_bitwise_neutral(ldm_model, golden):
     assert torch.equal(a["emb"], b["emb"]) and torch.equal(a["sim"], b["sim"])
 
 
+def test_epilogue_residual_and_narrow_tiles(ldm_sd, oracle_taps, golden):
+    """the alternative GEMM configuration (residuals added in the epilogue, 128-wide tiles) against
+    the oracle and against the default engine"""
+    from nope_b200.ldm import UNetModelPose
+    m = UNetModelPose(device="cuda:0", chunk=4)
+    m.set_option("fold_residual", 0)
+    m.set_option("wide_tiles", 0)
+    m.load_state_dict(ldm_sd)
+    ref = torch.from_numpy(golden["ref_latent"])
+    emb = m(ref.expand(N_HYP, -1, -1, -1), oracle_taps["poses"])
+    e = rel_l2(emb, oracle_taps["emb"])
+    log("ldm_alt_gemm_config", emb_rel_l2=e)
+    assert e < EMB_TOL
+
+
 def test_rejects_bad_input(ldm_model):
     from nope_b200 import _lib
     with pytest.raises(_lib.NopeError):
