@@ -49,3 +49,50 @@ def test_one_token_cross_attention_is_a_vector(ldm_sd):
     vec = (ctx[:, 0] @ ldm_sd[p + ".to_v.weight"].t()) @ ldm_sd[p + ".to_out.0.weight"].t() \
         + ldm_sd[p + ".to_out.0.bias"]
     assert rel_l2(out, vec[:, None, :].expand_as(out)) < 1e-6
+
+
+def test_block_plan_matches_reference_module_list():
+    """ldm_block_plan() against the module list UNetModel.__init__ builds for vae_cin_ldm.yaml
+    (recorded from the reference: input/output block widths and the skip widths popped per block)."""
+    from nope_b200.synth_weights import ldm_block_plan, ldm_flops_per_hyp
+    inp, mid, out = ldm_block_plan()
+    assert [b[0] for b in inp] == ["conv", "res", "res", "down", "res", "res", "down", "res", "res"]
+    assert [b[2] for b in inp] == [256, 256, 256, 256, 512, 512, 512, 1024, 1024]
+    assert mid == 1024
+    assert [(b[1], b[2], b[3], b[4]) for b in out] == [
+        (2048, 1024, 1024, False), (2048, 1024, 1024, False), (1536, 1024, 512, True),
+        (1536, 512, 512, False), (1024, 512, 512, False), (768, 512, 256, True),
+        (768, 256, 256, False), (512, 256, 256, False), (512, 256, 256, False)]
+    f = ldm_flops_per_hyp()
+    assert abs(f["total"] / 1e9 - 109.73) < 0.05 and abs(f["attention"] / 1e9 - 6.14) < 0.01
+
+
+def test_mirror_rejects_unsupported_configurations():
+    """only the shipped vae_cin_ldm.yaml configuration resolves; no CUDA needed to find out"""
+    from nope_b200.ldm import UNetModelPose
+    UNetModelPose(device="cuda:0")                      # constructing does not touch the library
+    for bad in (dict(channel_mult=(1, 2, 4, 8)), dict(injecting_condition_twice=True),
+                dict(pose_mlp_name="two_layers"), dict(num_head_channels=64), dict(transformer_depth=2),
+                dict(use_scale_shift_norm=True), dict(attention_resolutions=(4, 2))):
+        with pytest.raises(ValueError):
+            UNetModelPose(**bad)
+
+
+def test_gemm_schedule_count():
+    """tools/ldm_conv_table.py replays nope_ldm::forward_chunk's GEMM launches: 135 per chunk with the
+    pose-independent prefix hoisted (bench.py --variant ldm reports the same count)."""
+    import importlib.util
+    import os
+    import sys
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "ldm_conv_table.py")
+    src = open(path).read().split("rows = list(csv.reader")[0]
+    argv = sys.argv
+    sys.argv = ["ldm_conv_table.py", "unused", "128"]
+    try:
+        ns = {"__file__": path, "__name__": "ldm_conv_table"}
+        exec(compile(src, path, "exec"), ns)
+    finally:
+        sys.argv = argv
+    sched = ns["schedule"](128)
+    assert len(sched) == 135
+    assert sum(1 for s in sched if s[0].endswith(".ff1g")) == 16
