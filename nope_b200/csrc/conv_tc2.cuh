@@ -10,6 +10,13 @@
 // 1-CTA kernel (77 FLOP/B at BN=192) drops by 30 % (110 FLOP/B), and the smaller stage
 // buys a 6-deep ring.
 //
+// Tile widths: 192 (the default UNet: every width is a multiple of 192), 256 (the LDM variant:
+// multiples of 256; a 128-wide tile reads 16 KB of A + 8 KB of B per 64 tensor-core clocks,
+// exactly the 128 B/clk shared-memory limit, a 256-wide one 32 KB per 128), 128 / 64 (template
+// encoder, GEGLU).  Tiles of <= 128 columns double-buffer the output staging.  EPI selects the
+// epilogue at compile time: 0 plain (+ GroupNorm partial sums), 1 extras (ReLU, residual add,
+// (hi, lo) split, fp32 store: template encoder, LDM out conv), 2 GEGLU (conv_tc.cuh).
+//
 // Protocol (per CTA unless noted; barriers live at identical smem offsets in both CTAs):
 //   full[s]   leader only, count 2: leader's arrive.expect_tx(bytes of BOTH CTAs) + the
 //             peer producer's remote arrive; both CTAs' TMA loads complete_tx on it

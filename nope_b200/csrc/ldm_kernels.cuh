@@ -8,7 +8,8 @@
 //   * LayerNorm over channels (+ the cross-attention term, see ldm_ln_kernel),
 //   * multi-head self-attention: QK^T and PV on tcgen05 (S and O accumulators in TMEM, softmax
 //     in registers, P staged in shared memory as a swizzled K-major operand),
-//   * GEGLU, the 3x3 output convolution fused with the reference's l2 score.
+//   * the stand-alone GEGLU kernel (A/B switch; the default path fuses GEGLU into the GEMM
+//     epilogue, conv_tc.cuh), the l2 score of the (tensor-core) output convolution.
 // Activations are NHWC fp16 (tokens = pixels, so "b (h w) c" is the same memory); statistics,
 // softmax, LayerNorm and scores are fp32.
 #pragma once
