@@ -309,16 +309,26 @@ def main_ldm(args):
     from nope_b200.ldm import UNetModelPose
     from nope_b200.poses import synthetic_pose_batch
     from nope_b200.synth_weights import ldm_flops_per_hyp, make_ldm_state_dict
+    import torch.distributed as dist
+    from nope_b200.dist import ShardedSweep
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    assert int(os.environ.get("WORLD_SIZE", "1")) == 1, "--variant ldm is a single-GPU line"
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    n = args.poses
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sharded = ShardedSweep() if world > 1 else None
+    n_local = args.poses
+    n = n_local * world                      # weak scaling: one grid per GPU shard
     chunk = min(args.chunk, 642)
     m = UNetModelPose(device=str(dev), chunk=chunk)
     m.load_state_dict(make_ldm_state_dict(seed=0))
     Q = args.queries
-    poses, _ = synthetic_pose_batch(n, Q)
+    poses, _ = synthetic_pose_batch(n_local, Q)
+    poses = poses.repeat(1, world, 1)
     g = torch.Generator().manual_seed(0)
     ref_h = torch.randn(Q, 4, 32, 32, generator=g).pin_memory()
     qry_h = torch.randn(Q, 4, 32, 32, generator=g).pin_memory()
@@ -327,17 +337,29 @@ def main_ldm(args):
     h2d = (ref_h.numel() + qry_h.numel() + poses_h.numel()) * 4
     d2h = Q * (5 * 8 + n * 4)
 
+    def run(ref, pz, qry):
+        if sharded is not None:
+            sim, topi, _ = sharded.sweep(m, ref, pz, qry, k=5, want_emb=False)
+            return {"sim": sim, "topi": topi}
+        return m.sweep(ref, pz, qry, want_emb=False, k=5)
+
     def step_resident():
-        return m.sweep(ref_d, poses_d, qry_d, want_emb=False, k=5)
+        return run(ref_d, poses_d, qry_d)
 
     def step_e2e():
-        out = m.sweep(ref_h.to(dev, non_blocking=True), poses_h.to(dev, non_blocking=True),
-                      qry_h.to(dev, non_blocking=True), want_emb=False, k=5)
+        out = run(ref_h.to(dev, non_blocking=True), poses_h.to(dev, non_blocking=True),
+                  qry_h.to(dev, non_blocking=True))
         return out["topi"].cpu(), out["sim"].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
+        torch.cuda.synchronize()
+        barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -345,13 +367,20 @@ def main_ldm(args):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps
+        barrier()
+        t = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tt = torch.tensor([t], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt)
+        return t
 
-    sampler = ClockSampler(0)
-    sampler.start()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     ms = timed(step_resident, args.steps, max(args.warmup, 3))
     launches = m.last_launch_count
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
     m.profile(True)
     step_resident()
@@ -363,15 +392,20 @@ def main_ldm(args):
     attn_tf = at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0
     fl = ldm_flops_per_hyp()
     value = Q * n / (ms * 1e-3)
-    cpu = None if args.no_cpu_baseline else ldm_cpu_baseline()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    cpu = None if (args.no_cpu_baseline or world > 1) else ldm_cpu_baseline()
     line = {
-        "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": 1, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
         "config": {
             "workload": f"LDM variant (SURVEY.md 8 f2): UNetModelPose of configs/model/vae_cin_ldm.yaml on 4x32x32 "
-                        f"latents, {n}-pose grid, batch={Q} query, fp16 storage / fp32 accumulate, l2 score + top-5",
-            "poses_per_gpu": n, "queries": Q, "chunk": chunk,
+                        f"latents, {n_local}-pose grid per GPU, batch={Q} query, fp16 storage / fp32 accumulate, "
+                        "l2 score + top-5",
+            "poses_per_gpu": n_local, "global_poses": n, "queries": Q, "chunk": chunk,
+            "parallelism": f"pose grid sharded {world}-way, all-gather of top-k" if world > 1 else "1 GPU",
             "weights": "seeded random init, reference state_dict schema (395.0 M params)",
             "gflop_per_hyp": fl["total"] / 1e9,
             "encoder": "none: the diffusers VAE of this variant is not in the reference tree; inputs are latents",
@@ -397,6 +431,8 @@ def main_ldm(args):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -109,8 +109,13 @@ class UNetModelPose:
         _lib.check(_lib.load().nope_ldm_profile_read(self._handle(), ms, fl, n))
         return {k: {"ms": ms[i], "flops": fl[i], "launches": n[i]} for i, k in enumerate(("gemm", "attention"))}
 
-    def sweep(self, ref_latent, poses, query_latent=None, want_emb=True, want_sim=None, k=0, idx_base=0):
-        """ref_latent [B,C,32,32], poses [B,N,6] (+ query_latent) -> dict(emb, sim, topv, topi)."""
+    def sweep(self, ref_latent, poses, query_latent=None, want_emb=True, want_sim=None, k=0, idx_base=0,
+              query_feat=None):
+        """ref_latent [B,C,32,32], poses [B,N,6] (+ query_latent) -> dict(emb, sim, topv, topi).
+        `query_feat` is an alias of `query_latent` (the keyword nope_b200.unet.UNet.sweep and
+        nope_b200.dist.ShardedSweep use), so the pose grid shards across GPUs the same way."""
+        if query_feat is not None:
+            query_latent = query_feat
         if not self._finalized:
             raise _lib.NopeError("load_state_dict() must be called before the sweep")
         lib = _lib.load()
