@@ -13,6 +13,10 @@
  *   embeddings        fp32 [B, N, C, 32, 32]             (pred_feat_templates)
  *   similarity        fp32 [B, N]; nearest_idx int64 [B, k]
  * Inside the library activations are NHWC fp16 and weights are repacked K-major fp16.
+ *
+ * ABI version 2 (round 2): nope_unet_set_option / get_option, caller-owned workspace
+ * (nope_unet_workspace_bytes / nope_unet_set_workspace), nope_unet_profile_read reports executed and
+ * algorithmic FLOPs, nope_op_conv_gn_fused, nope_topk_merge, nope_score_topk metric 2.
  */
 #ifndef NOPE_B200_H
 #define NOPE_B200_H
@@ -47,9 +51,10 @@ void nope_unet_destroy(nope_unet_t* u);
 /* Hand one tensor of the reference state_dict to the engine, by its reference key
  * (e.g. "downs.0.0.block1.proj.weight").  `data` is a HOST fp32 pointer,
  * contiguous, with `ndim` sizes in `shape`.  Unknown keys are rejected; encoder.* keys
- * are not accepted here (the encoder stays a host-framework module in this round).
- * Replaces nn.Module.load_state_dict for the UNet (src/utils/weight.py:6-37 semantics:
- * shape-checked). */
+ * are not accepted here (they go to nope_encoder_load_tensor below).
+ * Replaces nn.Module.load_state_dict for the UNet; the shape-filtered partial load of
+ * src/utils/weight.py:6-37 (skip keys whose shape does not match) is done by the Python mirror
+ * (nope_b200.unet.load_checkpoint), this call rejects a mismatching shape. */
 int nope_unet_load_tensor(nope_unet_t* u, const char* key, const float* data,
                           const int64_t* shape, int ndim);
 
@@ -62,6 +67,26 @@ int nope_unet_finalize(nope_unet_t* u);
  * twin, 2 = tcgen05 with CTA pairs (cta_group::2, 256-pixel tiles; default). */
 int nope_unet_set_chunk(nope_unet_t* u, int hyps_per_chunk);
 int nope_unet_set_conv_impl(nope_unet_t* u, int impl);
+/* Named options:
+ *   "precision" (before nope_unet_finalize): 0 = fp16 operands (default; embeddings ~1.3e-3 rel-L2 of the
+ *       fp32 reference, u_net.py:160-198), 1 = exact weights: every weight is an fp16 pair W_hi + W_lo and
+ *       each convolution accumulates A W_hi + A W_lo (2x the tensor-core work), 2 = split precision:
+ *       exact weights and activations carried as fp16 pairs, A_hi W_hi + A_hi W_lo + A_lo W_hi (3x;
+ *       the "parity" mode that meets the 1e-3 embedding tolerance with margin);
+ *   "fuse_gn" (default 1): GroupNorm + SiLU + pose bias + residual run in the epilogue of the producing
+ *       convolution (Block.forward / ResnetBlock.forward, model_utils.py:237-279); 0 = separate
+ *       gn_apply pass (round-1 schedule; also what conv_impl 0 / 1 use);
+ *   "conv_impl": as nope_unet_set_conv_impl. */
+int nope_unet_set_option(nope_unet_t* u, const char* name, int value);
+int nope_unet_get_option(const nope_unet_t* u, const char* name, int* value);
+
+/* Workspace ownership.  By default the engine owns one device slab and grows it on demand (a growth
+ * synchronises the device and calls cudaMalloc).  A host framework that wants every byte to come from
+ * its own allocator asks for the size and hands a buffer over; the sweep then never allocates and
+ * fails if the buffer is too small.  hyps = min(chunk, B*N) hypotheses per chunk, refs = B,
+ * scores = B*N (0 when no query is scored).  The buffer must stay alive while the engine uses it. */
+int64_t nope_unet_workspace_bytes(nope_unet_t* u, int hyps, int refs, int scores);
+int nope_unet_set_workspace(nope_unet_t* u, void* device_ptr, int64_t bytes, int hyps, int refs, int scores);
 
 /* ---- the hot path -----------------------------------------------------------------
  * Sweep over the pose grid.  Replaces the Python loop of
@@ -87,10 +112,12 @@ int64_t nope_unet_last_launch_count(const nope_unet_t* u);
 /* Profiling hook for bench.py's roofline: when enabled, every tensor-core convolution
  * launch of subsequent sweeps is bracketed by CUDA events on the launching stream.
  * nope_unet_profile_read synchronises the device and returns the summed launch time
- * (ms), the summed algorithmic FLOPs (2*M*N*K per launch), the launch count and the best
- * single-launch TFLOP/s.  Enabling/disabling clears the recorded events. */
+ * (ms), the summed EXECUTED FLOPs (2*M*N*K' per launch, K' counting the extra split-precision
+ * K-segments), the summed ALGORITHMIC FLOPs (2*M*N*K of the layer, what the reference computes),
+ * the launch count and the best single-launch executed TFLOP/s.  Enabling/disabling clears the
+ * recorded events. */
 int nope_unet_profile(nope_unet_t* u, int enable);
-int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops,
+int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops, double* conv_alg_flops,
                            int64_t* conv_launches, double* max_launch_tflops);
 
 /* ---- template encoder ----------------------------------------------------------------
@@ -138,6 +165,16 @@ int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, i
 int nope_op_conv_gn(int impl, int mode, const float* x0, int C0, const float* x1, int C1,
                     const float* weight, const float* bias, const float* gamma, const float* beta,
                     int G, int silu, float* out, int n_img, int H, int W, int Cout, void* stream);
+/* The sweep's fused layer (conv_impl 2): out = [SiLU](GroupNorm_G(conv(x) + bias)) + chan_bias[n, c] +
+ * residual[n / res_div] with everything after the convolution applied in its epilogue
+ * (ResnetBlock.forward, model_utils.py:271-279; G = 0: no normalisation).  mode 0..2 as nope_op_conv.
+ * precision as nope_unet_set_option.  chan_bias [n, Cout], residual [ceil(n / res_div), Cout, H, W]
+ * (res_div 0: one residual image per input image), emit_out (optional) [n, 2] receives the sum and the
+ * sum of squares of the stored output (the GroupNorm(1) statistics handed to a following pre-norm). */
+int nope_op_conv_gn_fused(int mode, int precision, const float* x0, int C0, const float* x1, int C1,
+                          const float* weight, const float* bias, const float* gamma, const float* beta,
+                          int G, int silu, const float* chan_bias, const float* residual, int res_div,
+                          float* out, float* emit_out, int n_img, int H, int W, int Cout, void* stream);
 /* y = [SiLU](GroupNorm_G(x)) + chan_bias[n, c] + residual   (model_utils.py:237-253,271-279) */
 int nope_op_groupnorm(const float* x, const float* gamma, const float* beta, int G, int silu,
                       const float* chan_bias, const float* residual, float* out, int n_img,

@@ -26,7 +26,14 @@ SIGNATURES = {
     "nope_unet_last_launch_count": (C.c_int64, [C.c_void_p]),
     "nope_unet_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "nope_unet_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
-                                         C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "nope_unet_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "nope_unet_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]),
+    "nope_unet_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "nope_unet_set_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "nope_op_conv_gn_fused": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, c_f32p, c_f32p,
+                                        c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p, C.c_int, c_f32p,
+                                        c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nope_encoder_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "nope_encoder_destroy": (None, [C.c_void_p]),
     "nope_encoder_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_f32p, C.POINTER(C.c_int64), C.c_int]),
@@ -68,6 +75,8 @@ SIGNATURES = {
                                       C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
 }
 
+EXPECTED_ABI = 2     # include/nope_b200.h "ABI version"; a stale build with other signatures must not bind
+
 _lib = None
 
 
@@ -80,20 +89,28 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) and LIB_PATH == _DEFAULT_LIB_PATH and \
-            not os.environ.get("NOPE_NO_AUTOBUILD"):
+    if LIB_PATH == _DEFAULT_LIB_PATH and not os.environ.get("NOPE_NO_AUTOBUILD"):
         # the library is built in-tree by `python -m nope_b200.build` / __graft_entry__.build();
-        # on a fresh checkout compile it now (nvcc, sm_100a) -- still the CUDA path, never a fallback
-        try:
-            from . import build as _build
-            _build.build()
-        except Exception as exc:
-            raise NopeError(f"{LIB_PATH} is missing and building it failed: {exc}") from exc
+        # on a fresh checkout, or when a source file is newer than the binary, compile it now
+        # (nvcc, sm_100a) -- still the CUDA path, never a fallback.  A box without nvcc keeps the
+        # shipped binary (its ABI version is checked below).
+        from . import build as _build
+        if not os.path.exists(LIB_PATH) or (_build.is_stale() and _build.have_nvcc()):
+            try:
+                _build.build()
+            except Exception as exc:
+                if not os.path.exists(LIB_PATH):
+                    raise NopeError(f"{LIB_PATH} is missing and building it failed: {exc}") from exc
     if not os.path.exists(LIB_PATH):
         raise NopeError(
             f"{LIB_PATH} is missing: build it with `python -m nope_b200.build` "
             "(nope_b200 has no CPU or PyTorch fallback)")
     lib = C.CDLL(LIB_PATH)
+    lib.nope_abi_version.restype = C.c_int
+    abi = lib.nope_abi_version()
+    if abi != EXPECTED_ABI:
+        raise NopeError(f"{LIB_PATH} has ABI version {abi}, this package binds version {EXPECTED_ABI}: "
+                        "rebuild with `python -m nope_b200.build --force`")
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError if the export is missing
         fn.restype = res

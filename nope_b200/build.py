@@ -22,20 +22,40 @@ def nvcc_path():
     return p
 
 
+def have_nvcc():
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+
+
+STAMP = OUT + ".srchash"
+
+
+def source_hash():
+    """Content hash of every source the library is built from (mtimes do not survive a copy of the
+    tree to another box, contents do)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in DEPS:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
     if not force and not is_stale():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
+    tmp = f"{OUT}.{os.getpid()}.tmp"       # several ranks may build at once: private temp, atomic rename
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3",
            "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
-           "-o", OUT + ".tmp", SRC]
+           "-o", tmp, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -44,7 +64,10 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libnope_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    os.replace(OUT + ".tmp", OUT)
+    os.replace(tmp, OUT)
+    with open(f"{STAMP}.{os.getpid()}.tmp", "w") as f:
+        f.write(source_hash())
+    os.replace(f"{STAMP}.{os.getpid()}.tmp", STAMP)
     return OUT
 
 

@@ -11,6 +11,8 @@
 
 namespace nope {
 
+constexpr int kMaxDevices = 64;   // per-device launch state (shared-memory opt-in, resident clusters)
+
 // ----------------------------------------------------------------------------
 // host-side error plumbing (C-ABI returns int codes; message kept thread-local)
 // ----------------------------------------------------------------------------

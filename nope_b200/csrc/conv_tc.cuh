@@ -32,7 +32,7 @@ namespace nope {
 
 constexpr int kBM = 128;         // pixels per tile (UMMA M)
 constexpr int kBK = 64;          // channels per K-step (one 128-byte swizzle row)
-constexpr int kMaxSeg = 32;      // 9 taps x 2 sources, or 9 taps x 3 split-precision products
+constexpr int kMaxSeg = 64;      // 9 taps x 2 sources x 3 split-precision products
 constexpr int kMaxAMaps = 8;     // 4 stride-2 lattices x (hi, lo)
 constexpr int kConvThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
@@ -41,6 +41,45 @@ struct ConvSeg {
   int16_t map;      // index into amap[]
   int16_t dy, dx;   // tap offset in pixels
   int16_t nchunks;  // channels / 64 in this segment
+  int32_t wcol1;    // 0: weight columns continue where the previous segment ended; else first column + 1
+                    // (split precision re-reads the W_hi columns for the A_lo product)
+};
+
+// GroupNorm applied in the epilogue of the producing convolution (2-CTA kernel, EPI == 3):
+//   y = [SiLU]((acc - mean) * rstd * gamma + beta) + pose_bias[img, c] + residual[pixel, c]
+// (Block.forward / ResnetBlock.forward, model_utils.py:237-253, 271-279; PreNorm / to_out[1] of
+// LinearAttention, model_utils.py:230, 401).  The statistics of an image are spread over the CTA
+// tiles that hold its pixels (and, for groups wider than one tile, its channels): every such tile
+// publishes its partial sums, then waits for the `expected` tiles of its sync group (all resident:
+// the kernel is persistent with one CTA per SM).  Partials are combined in slot order, so results
+// do not depend on launch size or timing.
+struct GnFuse {
+  const float* gamma;    // [n_total]; G == 0: no normalisation (residual / pose-bias epilogue only)
+  const float* beta;
+  int G;                 // groups (0, 1 or 8)
+  int cpg;               // channels per group
+  int gpt;               // groups per N-tile            = max(1, BN / cpg)
+  int tpg;               // N-tiles per group            = max(1, cpg / BN)
+  int mt;                // M-tiles per image            = max(1, H*W / 128)
+  int ipt;               // images per M-tile            = max(1, 128 / (H*W))
+  int expected;          // tiles per sync group         = mt * tpg
+  int hw_shift;          // log2(H*W)
+  float inv_cnt;         // 1 / (H*W * cpg)
+  float eps;
+  int silu;
+  const __half* pb;      // per-image channel bias added after the activation (pose projection) or nullptr
+  int pb_stride, pb_off;
+  int has_res;           // residual tile arrives through ConvParams::rmap (TMA) into the output staging
+  int res_div, res_base; // res_div > 0: residual image index = (res_base + img) / res_div (hoisted prefix)
+  int n_img;             // valid images
+  float2* xpart;         // [sync group][slot][ipt * gpt] partial (sum, sum of squares)
+  unsigned* xcnt;        // [sync group] arrival counters, monotone (+expected per launch), private per layer
+  float2* emit;          // optional: GroupNorm(1, C) partial sums of the stored output,
+  int emit_parts;        //   emit[img * emit_parts + (m_in_img * n_tiles + n_tile)], emit_parts = mt * n_tiles
+  // split precision (activations carried as fp16 hi + lo): remainder of the output, [pixel][n_total],
+  // and of the residual (same layout; the residual image mapping of res_div applies)
+  __half* out_lo;
+  const __half* res_lo;
 };
 
 struct ConvParams {
@@ -49,6 +88,8 @@ struct ConvParams {
   CUtensorMap bmap;
   CUtensorMap bmap_half;  // box of BN/2 weight rows: the 2-CTA kernel (conv_tc2.cuh)
   CUtensorMap omap[4];  // one per output parity class when n_par == 4, else omap[0]
+  CUtensorMap rmap;     // residual tensor (output geometry), EPI == 3 with gn.has_res
+  GnFuse gn;            // EPI == 3
   const float* bias;  // [n_total] or nullptr
   // Sub-pixel ("parity") decomposition of nearest-x2-upsample + conv3x3 (HardUpsample,
   // model_utils.py:161-165): n_par == 4 makes n_tile enumerate (parity, channel tile); parity
@@ -56,6 +97,7 @@ struct ConvParams {
   // stores through omap[parity] (the stride-2 sub-lattice of the 2H x 2W output).
   int n_par;          // 1 or 4
   int n_tiles_par;    // channel tiles per parity (== n_tiles when n_par == 1)
+  int src_w, src_hw;  // n_par == 4: width / pixels of one SOURCE image (out_lo addressing)
   // Optional epilogue extras (template encoder: folded BatchNorm = bias, ReLU, residual add and
   // fp32-accurate activations stored as an fp16 (hi, lo) pair).  All [pixel][n_total] row-major;
   // not available together with n_par == 4.
@@ -179,12 +221,18 @@ template <int BN, bool EXTRAS>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t* out_stage,
                                                    const float* s_bias, uint32_t t_acc, int m_tile,
                                                    int n_chan0, int e, int lane,
-                                                   ResPrefetch<BN>* pre = nullptr) {
+                                                   ResPrefetch<BN>* pre = nullptr, int par = 0) {
   const int q = e & 3, hh = e >> 2;
   const int row = q * 32 + lane;
   const uint32_t t_row = t_acc + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
   const int grow = m_tile * kBM + row;                                // linear pixel index
   const bool row_ok = grow < p.m_valid;
+  size_t opix = (size_t)grow;                                         // output pixel (EXTRAS stores)
+  if (EXTRAS && p.n_par == 4) {       // parity class (py, px) of the 2H x 2W output
+    const int img = grow / p.src_hw, r = grow - img * p.src_hw;
+    const int yy = r / p.src_w, xx = r - yy * p.src_w;
+    opix = (size_t)img * 4 * p.src_hw + (size_t)(2 * yy + (par >> 1)) * (2 * p.src_w) + 2 * xx + (par & 1);
+  }
   uint32_t va[32], vb[32];
   tmem_ld_32x32(t_row, va);
 #pragma unroll
@@ -220,7 +268,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       f[6] = __uint_as_float(v[j * 8 + 6]) + b1.z;
       f[7] = __uint_as_float(v[j * 8 + 7]) + b1.w;
       if (EXTRAS) {
-        const size_t goff = (size_t)grow * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
+        const size_t goff = opix * p.n_total + n_chan0 + cc * 64 + hh * 32 + j * 8;
         if (p.res_hi && row_ok) {
           const __half2* h2 = reinterpret_cast<const __half2*>(&rh[j]);
           const __half2* l2 = reinterpret_cast<const __half2*>(&rl[j]);
@@ -388,6 +436,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
       for (int s = 0; s < p.nseg; ++s) {
         const ConvSeg sg = p.seg[s];
         const CUtensorMap* am = &p.amap[sg.map];
+        if (sg.wcol1) kcol = sg.wcol1 - 1;
         for (int ch = 0; ch < sg.nchunks; ++ch) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
@@ -579,11 +628,14 @@ inline bool conv_needs_extras(const ConvParams& p) {
 template <int BN, int STAGES, bool EXTRAS>
 inline int launch_conv_tc_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using S = ConvSmem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices];     // the opt-in is per device
+  int dev = 0;
+  NOPE_CUDA(cudaGetDevice(&dev));
+  NOPE_CHECK(dev >= 0 && dev < kMaxDevices, "device index out of range");
+  if (!attr_set[dev]) {
     NOPE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, EXTRAS>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;

@@ -15,7 +15,9 @@
 // exactly the 128 B/clk shared-memory limit, a 256-wide one 32 KB per 128), 128 / 64 (template
 // encoder, GEGLU).  Tiles of <= 128 columns double-buffer the output staging.  EPI selects the
 // epilogue at compile time: 0 plain (+ GroupNorm partial sums), 1 extras (ReLU, residual add,
-// (hi, lo) split, fp32 store: template encoder, LDM out conv), 2 GEGLU (conv_tc.cuh).
+// (hi, lo) split, fp32 store: template encoder, LDM out conv), 2 GEGLU (conv_tc.cuh), 3 GroupNorm
+// fused (GnFuse, conv_tc.cuh): the default UNet's Block / ResnetBlock / to_out epilogues -- the
+// normalised, activated tensor is the only thing that reaches HBM.
 //
 // Protocol (per CTA unless noted; barriers live at identical smem offsets in both CTAs):
 //   full[s]   leader only, count 2: leader's arrive.expect_tx(bytes of BOTH CTAs) + the
@@ -108,7 +110,7 @@ __device__ __forceinline__ void umma_commit_2cta_mc(uint64_t* bar, uint16_t mask
       : "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI = 0>
 struct Conv2Smem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / 2) * kBK * 2;      // this CTA's half of the weight tile
@@ -119,14 +121,348 @@ struct Conv2Smem {
   static constexpr int kOutBufs = BN <= 128 ? 2 : 1;
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBufs * kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
-  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024;
+  // EPI == 3 (GroupNorm fused): gamma | beta (fp32 [BN] each) | pose bias (fp16 [8][BN]) |
+  // segment partial sums (fp32 [8][BN/8][2]) | (mean, rstd) [64] | octet -> group table [BN/8] | emit scratch
+  static constexpr int kGnOffset = kBiasOffset + BN * 4;
+  static constexpr int kGnBytes = EPI == 3 ? (2 * BN * 4 + 8 * BN * 2 + 8 * (BN / 8) * 8 + 64 * 8 + (BN / 8) * 4 + 16 * 8) : 0;
+  static constexpr int kTotal = kGnOffset + kGnBytes + 1024;
 };
+
+// ld / st that bypass L1 (cross-CTA partial sums live in L2)
+__device__ __forceinline__ float2 ld_cg_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_cg_f2(float2* p, float2 v) {
+  asm volatile("st.global.cg.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned r;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EPI == 3: the whole epilogue loop of a CTA with GroupNorm fused (GnFuse, conv_tc.cuh).
+// Per tile, the 8 epilogue warps
+//   1. start the residual tile's TMA load into the output staging buffer (if any), stage
+//      bias / gamma / beta / pose-bias rows in shared memory;
+//   2. pull the accumulator out of TMEM into registers (+bias) and hand the TMEM buffer straight
+//      back to the MMA warp -- the mainloop of the next-but-one tile never waits for this epilogue;
+//   3. reduce per-(image, group) sums over the tile (butterfly over pixel rows, fixed order over
+//      row segments and channel octets), publish them and wait for the other tiles of the sync group
+//      (skipped when the tile holds whole images and whole groups);
+//   4. normalise, activate, add pose bias / residual in place in the swizzled staging buffer, TMA-store.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8_t* smem, uint32_t tmem_base,
+                                                      uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar,
+                                                      int tile0, int tile_step, int num_tiles, uint32_t rank) {
+  using S = Conv2Smem<BN, STAGES, 3>;
+  constexpr int kOct = BN / 8;
+  uint8_t* out_stage = smem + STAGES * S::kStageBytes;
+  float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
+  float* s_gamma = reinterpret_cast<float*>(smem + S::kGnOffset);
+  float* s_beta = s_gamma + BN;
+  __half* s_pb = reinterpret_cast<__half*>(s_beta + BN);                 // [8][BN]
+  float* s_part = reinterpret_cast<float*>(s_pb + 8 * BN);               // [8 segs][kOct][2]
+  float2* s_mr = reinterpret_cast<float2*>(s_part + 8 * kOct * 2);       // [ipt * gpt] (mean, rstd)
+  int* s_og = reinterpret_cast<int*>(s_mr + 64);                         // [kOct] octet -> group in tile
+  float2* s_em = reinterpret_cast<float2*>(s_og + kOct);                 // [2][8] emit scratch
+
+  const GnFuse& g = p.gn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = warp - 4, etid = threadIdx.x - 128;
+  const int q = e & 3, hh = e >> 2;
+  const int row = q * 32 + lane;
+  const bool leader = rank == 0;
+  const int hw = p.stats_hw;
+  const bool small = hw < 32;                       // 4x4 images: 16-row segments, two per warp
+  const int it = hw < kBM ? (row >> g.hw_shift) : 0;    // image of this thread's row inside the tile
+  const int npairs = g.ipt * g.gpt;
+  if (etid < kOct) s_og[etid] = (g.G > 0 && g.cpg < BN) ? (etid * 8) / g.cpg : 0;
+
+  int acc = 0, obuf = 0;
+  uint32_t acc_phase = 0, res_phase = 0;
+  for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    const int m_pair = tile / p.n_tiles;
+    const int n_tile = tile - m_pair * p.n_tiles;
+    const int m_tile = 2 * m_pair + (int)rank;
+    const int n_chan0 = n_tile * BN;
+    const bool live = m_tile < p.m_tiles;          // the peer of an odd last pair owns a phantom tile
+    int b0, y0;
+    conv_tile_coords(p, m_tile, b0, y0);
+    const int img0 = p.tiles_per_img > 0 ? m_tile / g.mt : m_tile * g.ipt;   // first image of the tile
+    uint8_t* ost = out_stage + obuf * S::kOutBytes;
+    if (etid == 0) {
+      if constexpr (S::kOutBufs == 2) tma_store_wait_read1();
+      else tma_store_wait_read0();
+      if (g.has_res && live) {     // residual tile -> staging buffer (same box / swizzle as the store)
+        const int rb = g.res_div > 0 ? (g.res_base + b0) / g.res_div : b0;
+        mbar_expect_tx(res_bar, S::kOutBytes);
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 64; ++cc)
+          tma_load_4d(ost + cc * (kBM * 128), &p.rmap, res_bar, n_chan0 + cc * 64, 0, y0, rb);
+      }
+    }
+    if (etid < BN) {
+      s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
+      if (g.G > 0) {
+        s_gamma[etid] = __ldg(g.gamma + n_chan0 + etid);
+        s_beta[etid] = __ldg(g.beta + n_chan0 + etid);
+      }
+    }
+    if (g.pb) {
+      for (int i = etid; i < g.ipt * kOct; i += 256) {
+        const int ii = i / kOct, o8 = i - ii * kOct;
+        const int img = img0 + ii;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (img < g.n_img)
+          v = *reinterpret_cast<const uint4*>(g.pb + (size_t)img * g.pb_stride + g.pb_off + n_chan0 + o8 * 8);
+        *reinterpret_cast<uint4*>(s_pb + ii * BN + o8 * 8) = v;
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+
+    // ---- pass 1: TMEM -> registers, free the accumulator, per-octet partial sums
+    uint32_t a[BN / 64][32];
+    {
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
+#pragma unroll
+      for (int cc = 0; cc < BN / 64; ++cc) tmem_ld_32x32(t_row + cc * 64, a[cc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_remote(&tempty_bar[acc], 0);
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const float* bs = s_bias + cc * 64 + hh * 32;
+        float st[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 c0 = *reinterpret_cast<const float4*>(bs + j * 8);
+          const float4 c1 = *reinterpret_cast<const float4*>(bs + j * 8 + 4);
+          const float bb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[i] = __uint_as_float(a[cc][j * 8 + i]) + bb[i];
+            a[cc][j * 8 + i] = __float_as_uint(f[i]);
+          }
+          float sm = (f[0] + f[1]) + (f[2] + f[3]) + ((f[4] + f[5]) + (f[6] + f[7]));
+          float q2 = f[0] * f[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) q2 = fmaf(f[i], f[i], q2);
+          st[2 * j] = sm;
+          st[2 * j + 1] = q2;
+        }
+        if (g.G > 0) {
+          const int idx = small ? butterfly8<16>(st, lane) : butterfly8<32>(st, lane);
+          const bool writer = small ? ((lane & 1) == 0) : ((lane & 3) == 0);
+          const int segi = small ? (q * 2 + (lane >> 4)) : q;
+          if (writer) s_part[(segi * kOct + cc * 8 + hh * 4) * 2 + idx] = st[0];   // idx = octet * 2 + {sum, sumsq}
+        }
+      }
+      if (g.G > 0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float Sx = 0.f, Qx = 0.f;
+        if (etid < npairs) {
+          const int ii = etid / g.gpt, gl = etid - ii * g.gpt;
+          const int spi = hw >= kBM ? 4 : (small ? 1 : (hw >> 5));   // row segments of this image in the tile
+          const int s0 = hw >= kBM ? 0 : ii * spi;
+          const int opg = (g.cpg < BN ? g.cpg : BN) >> 3;
+          const int o0 = gl * opg;
+          for (int sgm = s0; sgm < s0 + spi; ++sgm)
+            for (int o = o0; o < o0 + opg; ++o) {
+              Sx += s_part[(sgm * kOct + o) * 2];
+              Qx += s_part[(sgm * kOct + o) * 2 + 1];
+            }
+        }
+        if (g.expected > 1) {
+          // publish, then wait for the other tiles of this (image, group-set)
+          const int sg = (m_tile / g.mt) * (p.n_tiles / g.tpg) + n_tile / g.tpg;
+          const int slot = (m_tile % g.mt) * g.tpg + (n_tile % g.tpg);
+          float2* xp = g.xpart + (size_t)sg * g.expected * npairs;
+          if (etid < npairs) st_cg_f2(xp + slot * npairs + etid, make_float2(Sx, Qx));
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (etid == 0) {
+            __threadfence();
+            const unsigned old = atomicAdd(g.xcnt + sg, 1u);
+            const unsigned target = (old / (unsigned)g.expected + 1u) * (unsigned)g.expected;
+            if ((int)(ld_volatile_u32(g.xcnt + sg) - target) < 0) {
+              const long long t0 = clock64();
+              while ((int)(ld_volatile_u32(g.xcnt + sg) - target) < 0) {
+                if (clock64() - t0 > 4000000000LL) {
+                  printf("nope_b200: GroupNorm tile sync timed out (block %d tile %d)\n", (int)blockIdx.x, tile);
+                  __trap();
+                }
+              }
+            }
+            __threadfence();
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (etid < npairs) {
+            Sx = 0.f; Qx = 0.f;
+            for (int sl = 0; sl < g.expected; ++sl) {
+              const float2 t = ld_cg_f2(xp + sl * npairs + etid);
+              Sx += t.x;
+              Qx += t.y;
+            }
+          }
+        }
+        if (etid < npairs) {
+          const float mean = Sx * g.inv_cnt;
+          const float var = fmaxf(Qx * g.inv_cnt - mean * mean, 0.f);
+          s_mr[etid] = make_float2(mean, rsqrtf(var + g.eps));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+
+      // ---- pass 2: normalise / activate / add, in place in the swizzled staging tile
+      if (g.has_res) mbar_wait(res_bar, res_phase);
+      float e1 = 0.f, e2 = 0.f;
+      const float2* mrp = s_mr + it * g.gpt;
+      const __half* pbp = s_pb + it * BN;
+      const int grow = m_tile * kBM + row;            // linear output pixel
+      const bool row_ok = grow < p.m_valid;
+      // residual pixel under the hoisted-prefix image mapping (32x32 images: one image per tile)
+      const long long rpix = g.res_div > 0
+          ? (long long)((g.res_base + b0) / g.res_div) * hw + (m_tile % g.mt) * kBM + row
+          : (long long)grow;
+#pragma unroll
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        uint8_t* srow = ost + cc * (kBM * 128) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int lc = cc * 64 + hh * 32 + j * 8;
+          uint4* sp = reinterpret_cast<uint4*>(srow + (((hh * 4 + j) ^ (row & 7)) << 4));
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(a[cc][j * 8 + i]);
+          if (g.G > 0) {
+            const float2 mr = mrp[s_og[lc >> 3]];
+            const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + lc);
+            const float4 g1 = *reinterpret_cast<const float4*>(s_gamma + lc + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(s_beta + lc);
+            const float4 h1 = *reinterpret_cast<const float4*>(s_beta + lc + 4);
+            const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bt[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] - mr.x, mr.y * gm[i], bt[i]);
+          }
+          if (g.silu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
+          }
+          if (g.pb) {
+            const uint4 pv = *reinterpret_cast<const uint4*>(pbp + lc);
+            const __half2* hp = reinterpret_cast<const __half2*>(&pv);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float2 t = __half22float2(hp[k2]);
+              f[2 * k2] += t.x;
+              f[2 * k2 + 1] += t.y;
+            }
+          }
+          if (g.has_res) {
+            const uint4 rv = *sp;
+            const __half2* hr = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float2 t = __half22float2(hr[k2]);
+              f[2 * k2] += t.x;
+              f[2 * k2 + 1] += t.y;
+            }
+            if (g.res_lo && row_ok) {
+              const uint4 rl = *reinterpret_cast<const uint4*>(g.res_lo + rpix * p.n_total + n_chan0 + lc);
+              const __half2* hl = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float2 t = __half22float2(hl[k2]);
+                f[2 * k2] += t.x;
+                f[2 * k2 + 1] += t.y;
+              }
+            }
+          }
+          uint4 w;
+          w.x = pack_half2(f[0], f[1]);
+          w.y = pack_half2(f[2], f[3]);
+          w.z = pack_half2(f[4], f[5]);
+          w.w = pack_half2(f[6], f[7]);
+          *sp = w;
+          if (g.out_lo && row_ok) {
+            const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+            uint4 wl;
+            uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float2 t = __half22float2(hw2[k2]);
+              pl[k2] = pack_half2(f[2 * k2] - t.x, f[2 * k2 + 1] - t.y);
+            }
+            *reinterpret_cast<uint4*>(g.out_lo + (size_t)grow * p.n_total + n_chan0 + lc) = wl;
+          }
+          if (g.emit) {       // statistics of the values as stored (what the consumer reads)
+            const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float2 t = __half22float2(hw2[k2]);
+              e1 += t.x + t.y;
+              e2 = fmaf(t.x, t.x, e2);
+              e2 = fmaf(t.y, t.y, e2);
+            }
+          }
+        }
+      }
+      if (g.has_res) res_phase ^= 1;
+      if (g.emit) {
+        // 16-row segments: every image is a whole number of them at every resolution
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) {
+          e1 += __shfl_xor_sync(0xffffffffu, e1, off);
+          e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+        }
+        if ((lane & 15) == 0) s_em[hh * 8 + (row >> 4)] = make_float2(e1, e2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (etid < g.ipt && img0 + etid < g.n_img) {
+          const int r16 = hw >= kBM ? 8 : (hw >> 4);
+          float s1 = 0.f, s2 = 0.f;
+          for (int h2 = 0; h2 < 2; ++h2)
+            for (int r = etid * r16; r < (etid + 1) * r16; ++r) {
+              s1 += s_em[h2 * 8 + r].x;
+              s2 += s_em[h2 * 8 + r].y;
+            }
+          g.emit[(size_t)(img0 + etid) * g.emit_parts + (m_tile % g.mt) * p.n_tiles + n_tile] = make_float2(s1, s2);
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (etid == 0) {
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 64; ++cc)
+          tma_store_4d(&p.omap[0], ost + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
+        tma_store_commit();
+      }
+    }
+    obuf ^= S::kOutBufs - 1;
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (etid == 0) tma_store_wait_all();
+}
 
 // EPI: 0 = plain epilogue (the sweep), 1 = extras (ReLU / residual / hi-lo / fp32), 2 = GEGLU
 template <int BN, int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ ConvParams p) {
-  using S = Conv2Smem<BN, STAGES>;
+  using S = Conv2Smem<BN, STAGES, EPI>;
   constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64");
 
@@ -139,6 +475,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);     // EPI == 3: residual tile landed
   float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
 
   const int warp = threadIdx.x >> 5;
@@ -163,6 +500,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 2 * kEpiWarps);
     }
+    mbar_init(res_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_2cta<kTmemCols>(tmem_slot);
@@ -187,6 +525,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       for (int s = 0; s < p.nseg; ++s) {
         const ConvSeg sg = p.seg[s];
         const CUtensorMap* am = &p.amap[sg.map];
+        if (sg.wcol1) kcol = sg.wcol1 - 1;
         for (int ch = 0; ch < sg.nchunks; ++ch) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
@@ -232,6 +571,11 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+  } else if (warp >= 4 && EPI == 3) {
+    // ===================== epilogue with GroupNorm fused =====================
+    if constexpr (EPI == 3)
+      conv_gn_epilogue_loop<BN, STAGES>(p, smem, tmem_base, tfull_bar, tempty_bar, res_bar, tile0, tile_step,
+                                        num_tiles, rank);
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows, 8 warps) =====================
     const int e = warp - 4;
@@ -275,7 +619,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       else if constexpr (kPrefetchRes)
         conv_epilogue_tile<BN, true>(p, ost, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane, &pre);
       else if constexpr (EPI == 1)
-        conv_epilogue_tile<BN, true>(p, ost, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
+        conv_epilogue_tile<BN, true>(p, ost, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane, nullptr, par);
       else
         conv_epilogue_tile<BN, false>(p, ost, s_bias, tmem_base + acc * BN, m_tile, n_chan0, e, lane);
       // this CTA's accumulator half is drained: tell the leader's MMA warp
@@ -311,19 +655,53 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
 
 template <int BN, int STAGES, int EPI>
 inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
-  using S = Conv2Smem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  using S = Conv2Smem<BN, STAGES, EPI>;
+  // the shared-memory opt-in and the resident-cluster count are per device
+  static int max_clusters_of[kMaxDevices];      // 0: not initialised on this device yet
+  int dev = 0;
+  NOPE_CUDA(cudaGetDevice(&dev));
+  NOPE_CHECK(dev >= 0 && dev < kMaxDevices, "device index out of range");
+  if (max_clusters_of[dev] == 0) {
     NOPE_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, EPI>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
+    int mc = num_sms / 2;
+    if (EPI == 3) {
+      // tiles of one image wait for each other: every cluster of the grid must be resident
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(num_sms, 1, 1);
+      cfg.blockDim = dim3(kConvThreads, 1, 1);
+      cfg.dynamicSmemBytes = S::kTotal;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      NOPE_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc2_kernel<BN, STAGES, EPI>, &cfg));
+      NOPE_CHECK(n >= 1, "conv_tc2_kernel: no resident cluster fits on this device");
+      if (n < mc) mc = n;
+    }
+    max_clusters_of[dev] = mc;
   }
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
-  const int max_clusters = num_sms / 2;
+  const int max_clusters = max_clusters_of[dev];
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
   conv_tc2_kernel<BN, STAGES, EPI><<<2 * clusters, kConvThreads, S::kTotal, stream>>>(p);
   NOPE_CUDA(cudaGetLastError());
   return 0;
+}
+
+// GroupNorm-fused epilogue (GnFuse in p.gn)
+inline int launch_conv_gn(const ConvParams& p, int bn, int num_sms, cudaStream_t stream) {
+  if (p.n_par != 1 || p.geglu || conv_needs_extras(p) || p.stats)
+    return fail("launch_conv_gn: the fused GroupNorm epilogue takes a plain convolution");
+  switch (bn) {
+    case 192: return launch_conv_tc2_t<192, 6, 3>(p, num_sms, stream);
+    case 128: return launch_conv_tc2_t<128, 6, 3>(p, num_sms, stream);
+    case 64: return launch_conv_tc2_t<64, 8, 3>(p, num_sms, stream);
+  }
+  return fail("launch_conv_gn: unsupported BN");
 }
 
 inline int launch_conv_tc2(const ConvParams& p, int bn, int num_sms, cudaStream_t stream) {

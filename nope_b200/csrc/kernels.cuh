@@ -15,17 +15,22 @@ namespace nope {
 // src fp32 [Cout][Cin][T] (OIHW with T = KH*KW, or the [Cout][Cin*4] weight of the
 // 1x1 after pixel-unshuffle, whose input channel index is c*4 + p1*2 + p2,
 // model_utils.py:168-172) -> dst fp16 [Cout][T][Cin]  (K-major for the GEMM).
+// lo_off > 0 additionally writes the fp16 remainder W - fp16(W) at column lo_off + (t*cin + c):
+// the "exact weights" K-segments of the split-precision modes (22 significant bits per weight).
 __global__ void pack_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst,
                                    int cout, int cin, int taps, int dst_row_stride,
-                                   int dst_col_off) {
+                                   int dst_col_off, int lo_off = 0) {
   const long long total = (long long)cout * cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cin);
     const int t = (int)((i / cin) % taps);
     const int o = (int)(i / ((long long)cin * taps));
-    dst[(long long)o * dst_row_stride + dst_col_off + t * cin + c] =
-        __float2half_rn(src[((long long)o * cin + c) * taps + t]);
+    const float w = src[((long long)o * cin + c) * taps + t];
+    const __half hi = __float2half_rn(w);
+    __half* d = dst + (long long)o * dst_row_stride + dst_col_off + t * cin + c;
+    d[0] = hi;
+    if (lo_off > 0) d[lo_off] = __float2half_rn(w - __half2float(hi));
   }
 }
 
@@ -83,7 +88,7 @@ __global__ void pose_embed_kernel(const float* __restrict__ poses, const float* 
 // ----------------------------------------------------------------------------
 __global__ void init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ bias, __half* __restrict__ out, int B,
-                                 int Cl, int H, int W, int Cout) {
+                                 int Cl, int H, int W, int Cout, __half* __restrict__ out_lo = nullptr) {
   const long long total = (long long)B * H * W * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -103,7 +108,9 @@ __global__ void init_conv_kernel(const float* __restrict__ x, const float* __res
                      w[((o * Cl + c) * 3 + ky) * 3 + kx], acc);
         }
       }
-    out[i] = __float2half_rn(acc);
+    const __half hi = __float2half_rn(acc);
+    out[i] = hi;
+    if (out_lo) out_lo[i] = __float2half_rn(acc - __half2float(hi));
   }
 }
 
@@ -113,9 +120,12 @@ __global__ void init_conv_kernel(const float* __restrict__ x, const float* __res
 // applied to the hoisted pose-independent block1 output).
 // out[h, p, c] = src[ref_of[h], p, c] + pb[h, pb_off + c]
 // ----------------------------------------------------------------------------
+// With src_lo / out_lo (split precision) the sum src_hi + src_lo + pb is re-split into (hi, lo).
 __global__ void bcast_add_kernel(const __half* __restrict__ src, const int* __restrict__ ref_of,
                                  const __half* __restrict__ pb, int pb_stride, int pb_off,
-                                 __half* __restrict__ out, int n_hyp, int hw, int C) {
+                                 __half* __restrict__ out, int n_hyp, int hw, int C,
+                                 const __half* __restrict__ src_lo = nullptr,
+                                 __half* __restrict__ out_lo = nullptr) {
   const int octs = C / 8;
   const long long total = (long long)n_hyp * hw * octs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -125,6 +135,49 @@ __global__ void bcast_add_kernel(const __half* __restrict__ src, const int* __re
     const int h = (int)(i / ((long long)octs * hw));
     const int r = ref_of[h];
     uint4 v = *reinterpret_cast<const uint4*>(src + ((long long)r * hw + p) * C + o * 8);
+    if (out_lo) {
+      float f[8];
+      const __half2* vv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 x = __half22float2(vv[q]);
+        f[2 * q] = x.x;
+        f[2 * q + 1] = x.y;
+      }
+      if (src_lo) {
+        const uint4 l = *reinterpret_cast<const uint4*>(src_lo + ((long long)r * hw + p) * C + o * 8);
+        const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 x = __half22float2(ll[q]);
+          f[2 * q] += x.x;
+          f[2 * q + 1] += x.y;
+        }
+      }
+      if (pb) {
+        const uint4 a = *reinterpret_cast<const uint4*>(pb + (long long)h * pb_stride + pb_off + o * 8);
+        const __half2* aa = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 x = __half22float2(aa[q]);
+          f[2 * q] += x.x;
+          f[2 * q + 1] += x.y;
+        }
+      }
+      uint4 wh, wl;
+      uint32_t* ph = reinterpret_cast<uint32_t*>(&wh);
+      uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __half2 hh2 = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+        const float2 back = __half22float2(hh2);
+        ph[q] = *reinterpret_cast<const uint32_t*>(&hh2);
+        pl[q] = pack_half2(f[2 * q] - back.x, f[2 * q + 1] - back.y);
+      }
+      *reinterpret_cast<uint4*>(out + ((long long)h * hw + p) * C + o * 8) = wh;
+      *reinterpret_cast<uint4*>(out_lo + ((long long)h * hw + p) * C + o * 8) = wl;
+      continue;
+    }
     if (pb) {
       const uint4 a = *reinterpret_cast<const uint4*>(pb + (long long)h * pb_stride + pb_off + o * 8);
       __half2* vv = reinterpret_cast<__half2*>(&v);
@@ -692,7 +745,8 @@ __global__ void __launch_bounds__(kFinalThreads)
 final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ w,
                         const float* __restrict__ bias, float* __restrict__ emb,
                         const float* __restrict__ query, const int* __restrict__ ref_of,
-                        float* __restrict__ partial, int hw, int C, int Cl) {
+                        float* __restrict__ partial, int hw, int C, int Cl,
+                        const __half* __restrict__ x_lo = nullptr) {
   extern __shared__ float s_w[];  // [Cl][C]
   __shared__ float s_part[kFinalThreads / 32];
   const int slab = blockIdx.x, h = blockIdx.y, nslab = gridDim.x;
@@ -705,6 +759,7 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
   float dist = 0.f;
   if (p < hw) {
     const __half* xp = x + ((long long)h * hw + p) * C;
+    const __half* xl = x_lo ? x_lo + ((long long)h * hw + p) * C : nullptr;
     for (int k0 = 0; k0 < C; k0 += 8) {
       const uint4 v = *reinterpret_cast<const uint4*>(xp + k0);
       const __half2* hv = reinterpret_cast<const __half2*>(&v);
@@ -714,6 +769,16 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
         const float2 t = __half22float2(hv[q]);
         f[2 * q] = t.x;
         f[2 * q + 1] = t.y;
+      }
+      if (xl) {
+        const uint4 l = *reinterpret_cast<const uint4*>(xl + k0);
+        const __half2* hl = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 t = __half22float2(hl[q]);
+          f[2 * q] += t.x;
+          f[2 * q + 1] += t.y;
+        }
       }
 #pragma unroll
       for (int c = 0; c < kMaxLatent; ++c)
@@ -928,25 +993,30 @@ __global__ void conv_simt_kernel(const SimtConvArgs a) {
 
 // fp32 NCHW <-> fp16 NHWC helpers for the per-op test entry points
 __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y,
-                                            int n_img, int C, int hw) {
+                                            int n_img, int C, int hw, __half* __restrict__ y_lo = nullptr) {
   const long long total = (long long)n_img * C * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const int p = (int)((i / C) % hw);
     const int b = (int)(i / ((long long)C * hw));
-    y[i] = __float2half_rn(x[((long long)b * C + c) * hw + p]);
+    const float v = x[((long long)b * C + c) * hw + p];
+    const __half hi = __float2half_rn(v);
+    y[i] = hi;
+    if (y_lo) y_lo[i] = __float2half_rn(v - __half2float(hi));
   }
 }
 __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y,
-                                            int n_img, int C, int hw) {
+                                            int n_img, int C, int hw,
+                                            const __half* __restrict__ x_lo = nullptr) {
   const long long total = (long long)n_img * C * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % hw);
     const int c = (int)((i / hw) % C);
     const int b = (int)(i / ((long long)C * hw));
-    y[i] = __half2float(x[((long long)b * hw + p) * C + c]);
+    const long long j = ((long long)b * hw + p) * C + c;
+    y[i] = __half2float(x[j]) + (x_lo ? __half2float(x_lo[j]) : 0.f);
   }
 }
 

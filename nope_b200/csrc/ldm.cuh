@@ -776,10 +776,13 @@ struct nope_ldm {
     if (attn_impl == 1) {
       ldm_attn_simt_kernel<<<grid, 128, 0, st>>>(qkv, Vt, out, ntok, Hh, C, sl2e);
     } else {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static bool attr_set[kMaxDevices];     // the shared-memory opt-in is per device
+      int dev = 0;
+      NOPE_CUDA(cudaGetDevice(&dev));
+      NOPE_CHECK(dev >= 0 && dev < kMaxDevices, "device index out of range");
+      if (!attr_set[dev]) {
         NOPE_CUDA(cudaFuncSetAttribute(ldm_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        attr_set = true;
+        attr_set[dev] = true;
       }
       AttnParams p;
       const CUtensorMap* m = nullptr;

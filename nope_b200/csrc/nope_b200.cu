@@ -25,7 +25,7 @@ using namespace nope;
 
 namespace {
 
-constexpr int kAbiVersion = 1;
+constexpr int kAbiVersion = 2;
 constexpr int kHeadsHidden = 128;  // 4 heads x 32 (model_utils.py:368,394)
 
 struct HostTensor {
@@ -36,11 +36,13 @@ struct HostTensor {
 struct ConvLayer {
   int mode = 0;  // 0: 3x3 pad1, 1: 1x1, 2: unshuffle+1x1, 3: nearest-x2 upsample + 3x3 (folded)
   int cin = 0, cout = 0, K = 0, bn = 0;
-  __half* w = nullptr;    // [cout][K] fp16
+  int Kp = 0;             // packed row length: K (fp16 weights) or 2K (W_hi | W_lo, precision >= 1)
+  __half* w = nullptr;    // [rows][Kp] fp16
   float* bias = nullptr;  // [cout] fp32 or nullptr
   CUtensorMap wmap;
   CUtensorMap wmap_half;  // BN/2-row box for the 2-CTA kernel
   bool has_map = false;
+  int id = -1;            // index of the layer's private tile-sync counters (fused GroupNorm)
 };
 
 struct NormLayer {
@@ -49,10 +51,35 @@ struct NormLayer {
   int C = 0, G = 1;
 };
 
-struct Act {  // NHWC fp16 activation [n_img, S, S, C]
-  __half* p = nullptr;
+// NHWC fp16 activation [n_img, S, S, C]; `lo` carries the fp16 remainder x - fp16(x) in the
+// split-precision mode (nullptr otherwise)
+struct Act {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
   int C = 0;
-  int S = 0;  // spatial side
+  Act() {}
+  Act(__half* h, int c, __half* l = nullptr) : hi(h), lo(l), C(c) {}
+};
+
+// what the fused epilogue applies after the convolution (ResnetBlock / Block / to_out)
+struct GnSpec {
+  const NormLayer* norm = nullptr;   // nullptr: no normalisation
+  bool silu = false;
+  int pb_offset = -1;                // pose-projection columns of this block, -1: none
+  Act res;                           // residual (hi == nullptr: none)
+  int res_div = 0, res_base = 0;     // residual image = (res_base + img) / res_div (hoisted prefix)
+  float2* emit = nullptr;            // GroupNorm(1) partial sums of the output for a following pre-norm
+};
+
+// bump allocator over one device slab (base == nullptr: size computation only)
+struct Bump {
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  template <typename T> void take(T** out, size_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    if (base) *out = reinterpret_cast<T*>(base + off);     // size-only passes leave the engine untouched
+    off += n * sizeof(T);
+  }
 };
 
 }  // namespace
@@ -62,6 +89,10 @@ struct nope_unet {
   int dims[5] = {0, 0, 0, 0, 0};
   bool finalized = false;
   int conv_impl = 2;   // 0: tcgen05 1-CTA tiles, 1: SIMT debug twin, 2: tcgen05 CTA pairs (default)
+  bool fuse_gn = true; // GroupNorm / SiLU / pose bias / residual in the conv epilogue (conv_impl 2 only)
+  // 0: fp16 operands; 1: exact weights (W_hi + W_lo K-segments, 2x the MMA work); 2: split precision
+  // (exact weights + activations carried as hi + lo: A_hi W_hi + A_hi W_lo + A_lo W_hi, 3x)
+  int precision = 0;
   int chunk = 642;
   int64_t launches = 0;
 
@@ -72,25 +103,31 @@ struct nope_unet {
   std::map<std::string, NormLayer> norms;
   std::map<std::string, int> pb_off;
   int P = 0;  // total pose-projection width
+  int n_layers = 0;
   ConvLayer poseproj;
   float *pose_w = nullptr, *pose_b = nullptr, *init_w = nullptr, *init_b = nullptr,
         *final_w = nullptr, *final_b = nullptr;
-  std::vector<void*> owned;  // every cudaMalloc'd pointer
+  std::vector<void*> owned;  // every cudaMalloc'd weight pointer
 
-  // workspace
+  // workspace: one slab, either caller-provided (nope_unet_set_workspace) or owned
   int cap = 0, cap_ref = 0;
+  uint8_t* ws_base = nullptr;
+  size_t ws_bytes = 0;
+  bool ws_external = false;
+  bool ws_fresh = false;            // counters not zeroed yet
   Act sk[4][2];
-  __half *TA = nullptr, *TB = nullptr, *TC = nullptr, *TD = nullptr, *XA = nullptr, *XB = nullptr,
-         *RB = nullptr, *cs = nullptr, *pb = nullptr;
-  __half *x0 = nullptr, *g1 = nullptr, *pt = nullptr;  // per-reference pre-stage
+  Act TA, TB, TC, TD, XA, XB, RB;
+  __half *cs = nullptr, *pb = nullptr;
+  Act x0, g1;                       // per-reference pre-stage
+  __half* pt = nullptr;
   float2* gn_partial = nullptr;   // gn_stats_kernel output (per-op test path only)
-  float2 *SA = nullptr, *SB = nullptr;   // fused statistics: conv epilogue / gn_apply emit
+  float2 *SA = nullptr, *SB = nullptr;   // unfused statistics: conv epilogue / gn_apply emit; SB also fused emit
+  float2* xpart = nullptr;        // fused GroupNorm: cross-tile partial sums
+  unsigned* xcnt = nullptr;       // fused GroupNorm: per-layer arrival counters [n_layers][xcnt_per_layer]
+  size_t xcnt_per_layer = 0, xcnt_total = 0;
   int* ref_of = nullptr;
   float* score_partial = nullptr;
-  size_t score_partial_cap = 0;
   float* sim_buf = nullptr;
-  size_t sim_buf_cap = 0;
-  std::vector<void*> ws_owned;
 
   std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;
 
@@ -108,11 +145,11 @@ struct nope_unet {
 
   ~nope_unet() {
     for (void* p : owned) cudaFree(p);
-    for (void* p : ws_owned) cudaFree(p);
-    if (score_partial) cudaFree(score_partial);
-    if (sim_buf) cudaFree(sim_buf);
+    if (ws_base && !ws_external) cudaFree(ws_base);
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   }
+  bool fused() const { return fuse_gn && conv_impl == 2; }
+  bool split() const { return precision == 2 && fused(); }
 
   // ------------------------------------------------------------------ schema
   void expect(const std::string& k, std::vector<int64_t> s) { expected[k] = std::move(s); }
@@ -203,6 +240,7 @@ struct nope_unet {
   }
   // pack one conv weight (+ bias) into a ConvLayer.  mode 3 (nearest-x2 upsample + conv3x3,
   // HardUpsample) first folds the 3x3 kernel into four 2x2 parity kernels (fold_upconv_kernel).
+  // precision >= 1 appends the fp16 remainders as a second K-block: rows are [W_hi (K) | W_lo (K)].
   int make_conv(const std::string& name, const std::string& wkey, const std::string& bkey, int mode) {
     auto it = host.find(wkey);
     NOPE_CHECK(it != host.end(), "missing tensor " + wkey);
@@ -214,6 +252,7 @@ struct nope_unet {
     const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
     L.cin = mode == 2 ? (int)sh[1] / 4 : (int)sh[1];
     L.K = L.cin * taps;
+    L.Kp = precision >= 1 ? 2 * L.K : L.K;
     NOPE_CHECK(L.cin % 64 == 0, wkey + ": input channels must be a multiple of 64");
     L.bn = pick_bn(L.cout);
     NOPE_CHECK(L.bn != 0, wkey + ": output channels must be a multiple of 64");
@@ -221,18 +260,19 @@ struct nope_unet {
     const size_t n = it->second.data.size();
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), n * sizeof(float)));
     NOPE_CUDA(cudaMemcpy(tmp, it->second.data.data(), n * sizeof(float), cudaMemcpyHostToDevice));
-    const size_t npack = (size_t)rows * L.K;
+    const size_t npack = (size_t)rows * L.Kp;
     const float* src = tmp;
     if (mode == 3) {
       NOPE_CHECK(sh.size() == 4 && sh[2] == 3 && sh[3] == 3, wkey + ": expected a 3x3 kernel");
-      NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&folded), npack * sizeof(float)));
+      NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&folded), (size_t)rows * L.K * sizeof(float)));
       fold_upconv_kernel<<<ew_grid((long long)4 * L.cout * L.cin), 256>>>(tmp, folded, L.cout, L.cin);
       NOPE_CUDA(cudaGetLastError());
       src = folded;
     }
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w), npack * sizeof(__half)));
     owned.push_back(L.w);
-    pack_weight_kernel<<<ew_grid((long long)npack), 256>>>(src, L.w, rows, L.cin, taps, L.K, 0);
+    pack_weight_kernel<<<ew_grid((long long)rows * L.K), 256>>>(src, L.w, rows, L.cin, taps, L.Kp, 0,
+                                                                precision >= 1 ? L.K : 0);
     NOPE_CUDA(cudaGetLastError());
     NOPE_CUDA(cudaDeviceSynchronize());
     NOPE_CUDA(cudaFree(tmp));
@@ -240,9 +280,10 @@ struct nope_unet {
     if (!bkey.empty()) {
       if (upload_f32(bkey, &L.bias)) return -1;
     }
-    if (make_weight_map(&L.wmap, L.w, rows, L.K, L.bn)) return -1;
-    if (make_weight_map(&L.wmap_half, L.w, rows, L.K, L.bn / 2)) return -1;
+    if (make_weight_map(&L.wmap, L.w, rows, L.Kp, L.bn)) return -1;
+    if (make_weight_map(&L.wmap_half, L.w, rows, L.Kp, L.bn / 2)) return -1;
     L.has_map = true;
+    L.id = n_layers++;
     convs[name] = L;
     return 0;
   }
@@ -311,6 +352,7 @@ struct nope_unet {
     NOPE_CHECK(!finalized, "already finalized");
     for (const auto& kv : expected)
       NOPE_CHECK(host.count(kv.first), "state_dict is missing " + kv.first);
+    NOPE_CHECK(precision == 0 || conv_impl != 1, "the SIMT debug convolution only runs fp16 weights");
     NOPE_CUDA(cudaSetDevice(device));
     if (upload_f32("pose_mlp.0.weight", &pose_w) || upload_f32("pose_mlp.0.bias", &pose_b) ||
         upload_f32("init_conv.weight", &init_w) || upload_f32("init_conv.bias", &init_b) ||
@@ -347,50 +389,101 @@ struct nope_unet {
   }
 
   // ------------------------------------------------------------------ workspace
-  int ws_alloc_half(__half** p, size_t n) {
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(__half)));
-    ws_owned.push_back(*p);
-    return 0;
+  // One slab carved by a bump allocator: ~6 MB per hypothesis (12 MB in the split-precision mode).
+  // layout(b) assigns every buffer for capacities (c hypotheses, r references).
+  void take_act(Bump& b, Act* a, size_t n, int C, bool with_lo) {
+    if (b.base) {
+      a->C = C;
+      a->lo = nullptr;
+    }
+    b.take(&a->hi, n);
+    if (with_lo) b.take(&a->lo, n);
   }
-  int ensure_workspace(int need_cap, int need_ref) {
-    if (need_cap <= cap && need_ref <= cap_ref) return 0;
-    NOPE_CUDA(cudaDeviceSynchronize());
-    for (void* p : ws_owned) cudaFree(p);
-    ws_owned.clear();
-    tmaps.clear();
-    cap = std::max(cap, need_cap);
-    cap_ref = std::max(cap_ref, need_ref);
-    const size_t c = (size_t)cap;
+  size_t layout(Bump& b, int c_hyp, int c_ref, int n_total_scores) {
+    const size_t c = (size_t)c_hyp, r = (size_t)c_ref;
+    const bool lo = precision == 2;
     // temporaries hold the widest full-resolution tensor: a concat-conv output (<= 2*dim
     // channels) or the attention qkv tensor (3 x 128 channels, independent of dim)
     const size_t big = (size_t)S0 * S0 * std::max(dim * 2, 3 * kHeadsHidden);
     const size_t xsz = (size_t)S0 * S0 * dim;      // one full-resolution feature map
     for (int i = 0; i < 4; ++i) {
       const int s = S0 >> i;
-      for (int b = 0; b < 2; ++b) {
-        sk[i][b].C = dims[i];
-        sk[i][b].S = s;
-        if (ws_alloc_half(&sk[i][b].p, c * s * s * dims[i])) return -1;
-      }
+      for (int k = 0; k < 2; ++k) take_act(b, &sk[i][k], c * s * s * dims[i], dims[i], lo);
     }
-    if (ws_alloc_half(&TA, c * big) || ws_alloc_half(&TB, c * big) || ws_alloc_half(&TC, c * big) ||
-        ws_alloc_half(&TD, c * big) || ws_alloc_half(&XA, c * xsz) ||
-        ws_alloc_half(&XB, c * xsz) || ws_alloc_half(&RB, c * xsz) ||
-        ws_alloc_half(&cs, c * cemb) || ws_alloc_half(&pb, c * P))
-      return -1;
-    const size_t r = (size_t)cap_ref;
-    if (ws_alloc_half(&x0, r * xsz) || ws_alloc_half(&g1, r * xsz) || ws_alloc_half(&pt, r * xsz))
-      return -1;
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&gn_partial),
-                         (size_t)std::max(cap, cap_ref) * 8 * 8 * sizeof(float2)));
-    ws_owned.push_back(gn_partial);
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&ref_of), (size_t)std::max(cap, cap_ref) * sizeof(int)));
-    ws_owned.push_back(ref_of);
-    const size_t st_per_img = (size_t)S0 * S0 * dim / 256;   // (hw/32) x (C/8) at the top level
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&SA), (size_t)std::max(cap, cap_ref) * st_per_img * sizeof(float2)));
-    ws_owned.push_back(SA);
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&SB), (size_t)std::max(cap, cap_ref) * 8 * sizeof(float2)));
-    ws_owned.push_back(SB);
+    take_act(b, &TA, c * big, 0, false);
+    take_act(b, &TB, c * big, 0, lo);
+    take_act(b, &TC, c * big, 0, lo);
+    take_act(b, &TD, c * big, 0, false);
+    take_act(b, &XA, c * xsz, 0, lo);
+    take_act(b, &XB, c * xsz, 0, lo);
+    take_act(b, &RB, c * xsz, dim, lo);
+    b.take(&cs, c * cemb);
+    b.take(&pb, c * (size_t)P);
+    take_act(b, &x0, r * xsz, dim, lo);
+    take_act(b, &g1, r * xsz, dim, lo);
+    b.take(&pt, r * xsz);
+    const size_t m = std::max(c, r);
+    b.take(&gn_partial, m * 8 * 8);
+    b.take(&ref_of, m);
+    b.take(&SA, m * ((size_t)S0 * S0 * dim / 256));   // (hw/32) x (C/8) at the top level
+    b.take(&SB, m * 8);
+    b.take(&xpart, (m + 8) * 64);
+    const size_t per_layer = m * 8, cnt_total = per_layer * (size_t)std::max(n_layers, 1);
+    if (b.base) {
+      xcnt_per_layer = per_layer;
+      xcnt_total = cnt_total;
+    }
+    b.take(&xcnt, cnt_total);
+    const int nslab = (S0 * S0 + kFinalThreads - 1) / kFinalThreads;
+    b.take(&score_partial, (size_t)n_total_scores * nslab);
+    b.take(&sim_buf, (size_t)n_total_scores);
+    return b.off;
+  }
+  size_t workspace_bytes(int c_hyp, int c_ref, int n_scores) {
+    Bump b;
+    return layout(b, c_hyp, c_ref, n_scores) + 256;
+  }
+  int scores_cap = 0;
+  int ensure_workspace(int need_cap, int need_ref, int need_scores = 0) {
+    if (need_cap <= cap && need_ref <= cap_ref && need_scores <= scores_cap) return 0;
+    NOPE_CHECK(!ws_external, "the caller-provided workspace is too small for this sweep "
+                             "(nope_unet_workspace_bytes / nope_unet_set_workspace)");
+    NOPE_CUDA(cudaDeviceSynchronize());
+    if (ws_base) cudaFree(ws_base);
+    ws_base = nullptr;
+    const int c = std::max(cap, need_cap), r = std::max(cap_ref, need_ref), sc = std::max(scores_cap, need_scores);
+    const size_t bytes = workspace_bytes(c, r, sc);
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws_base), bytes));
+    ws_bytes = bytes;
+    return adopt(c, r, sc);
+  }
+  int adopt(int c, int r, int sc) {
+    tmaps.clear();
+    cap = c; cap_ref = r; scores_cap = sc;
+    Bump b;
+    b.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws_base) + 255) & ~static_cast<uintptr_t>(255));
+    layout(b, c, r, sc);
+    ws_fresh = true;
+    return 0;
+  }
+  int set_workspace(void* ptr, size_t bytes, int c, int r, int sc) {
+    NOPE_CHECK(ptr && c >= 1 && r >= 1, "bad workspace arguments");
+    NOPE_CHECK(bytes >= workspace_bytes(c, r, sc), "workspace buffer smaller than nope_unet_workspace_bytes");
+    if (ws_base && !ws_external) {
+      NOPE_CUDA(cudaDeviceSynchronize());
+      cudaFree(ws_base);
+    }
+    ws_base = static_cast<uint8_t*>(ptr);
+    ws_bytes = bytes;
+    ws_external = true;
+    return adopt(c, r, sc);
+  }
+  // the tile-sync counters start at zero (and stay multiples of `expected` between launches)
+  int prepare_stream(cudaStream_t st) {
+    if (ws_fresh) {
+      NOPE_CUDA(cudaMemsetAsync(xcnt, 0, xcnt_total * sizeof(unsigned), st));
+      ws_fresh = false;
+    }
     return 0;
   }
 
@@ -411,14 +504,18 @@ struct nope_unet {
   }
 
   // ------------------------------------------------------------------ op launchers
-  // out[n_img, So, So, cout] = conv(L, in0 (++ in1))
-  int conv(const ConvLayer& L, const __half* in0, int c0, const __half* in1, int c1, __half* out,
-           int So, int n_img, int cap_img, cudaStream_t st, float2* stats = nullptr) {
+  // out[n_img, So, So, cout] = conv(L, in0 (++ in1)).  The K loop walks, per filter tap and source
+  // tensor, up to three products: A_hi W_hi, A_hi W_lo (precision >= 1), A_lo W_hi (sources that
+  // carry a remainder).  `gs` selects the fused GroupNorm epilogue; `stats` the unfused partial sums.
+  int conv(const ConvLayer& L, const Act& in0, const Act& in1, const Act& out, int So, int n_img, int cap_img,
+           cudaStream_t st, float2* stats = nullptr, const GnSpec* gs = nullptr) {
+    const int c0 = in0.C, c1 = in1.hi ? in1.C : 0;
     NOPE_CHECK(c0 + c1 == L.cin, "conv: channel mismatch");
     ++launches;
     if (conv_impl == 1) {
+      NOPE_CHECK(!gs && L.Kp == L.K, "the SIMT debug convolution has no fused epilogue / split weights");
       SimtConvArgs a;
-      a.src0 = in0; a.src1 = in1; a.C0 = c0; a.C1 = c1; a.w = L.w; a.bias = L.bias; a.out = out;
+      a.src0 = in0.hi; a.src1 = in1.hi; a.C0 = c0; a.C1 = c1; a.w = L.w; a.bias = L.bias; a.out = out.hi;
       a.n_img = n_img; a.H = So; a.W = So; a.Cout = L.cout; a.K = L.K; a.mode = L.mode;
       conv_simt_kernel<<<ew_grid((long long)n_img * So * So * L.cout, 256, 148 * 32), 256, 0, st>>>(a);
       NOPE_CUDA(cudaGetLastError());
@@ -426,7 +523,7 @@ struct nope_unet {
         // the SIMT twin has no fused statistics: produce them in the conv-epilogue format
         // (parts = max(1, hw/32), noct = C/8) with a plain reduction kernel
         const int hw = So * So;
-        stats_ref_kernel<<<dim3(hw < 32 ? 1 : hw / 32, n_img), 256, 0, st>>>(out, stats, hw, L.cout);
+        stats_ref_kernel<<<dim3(hw < 32 ? 1 : hw / 32, n_img), 256, 0, st>>>(out.hi, stats, hw, L.cout);
         NOPE_CUDA(cudaGetLastError());
       }
       return 0;
@@ -436,60 +533,85 @@ struct nope_unet {
     ConvParams p;
     memset(&p, 0, sizeof p);
     const CUtensorMap* m = nullptr;
-    int nseg = 0, ksteps = 0;
     p.n_par = 1;
-    p.n_amaps = 4;
+    const bool wlo = L.Kp > L.K;                       // packed rows carry W_lo at column K + ...
+    const bool alo0 = in0.lo != nullptr, alo1 = in1.hi && in1.lo != nullptr;
+    // taps: (dy, dx, lattice) ; sources: (hi map, lo map, channels, weight column offset inside a tap)
+    struct Tap { int dy, dx, lat; };
+    std::vector<Tap> taps;
+    int n_lat = 1;
     if (L.mode == 3) {
       // So is the OUTPUT side (2x the source side); tiles and input maps use the source geometry
-      NOPE_CHECK(in1 == nullptr && So % 2 == 0, "upsample conv takes one source");
+      NOPE_CHECK(in1.hi == nullptr && So % 2 == 0, "upsample conv takes one source");
       if (make_geom(So / 2, So / 2, &g)) return -1;
-      if (get_map(&m, in0, cap_img, c0, g, -1)) return -1;
-      for (int t = 0; t < 4; ++t) p.amap[t] = *m;
       for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-          p.seg[nseg++] = ConvSeg{0, (int16_t)(a - 1), (int16_t)(b - 1), (int16_t)(c0 / 64)};
-          ksteps += c0 / 64;
-        }
+        for (int b = 0; b < 2; ++b) taps.push_back(Tap{a - 1, b - 1, 0});
       p.n_par = 4;
     } else if (L.mode == 2) {
-      NOPE_CHECK(in1 == nullptr, "unshuffle conv takes one source");
-      for (int t = 0; t < 4; ++t) {
-        if (get_map(&m, in0, cap_img, c0, g, t)) return -1;
-        p.amap[t] = *m;
-        p.seg[nseg++] = ConvSeg{(int16_t)t, 0, 0, (int16_t)(c0 / 64)};
-        ksteps += c0 / 64;
-      }
+      NOPE_CHECK(in1.hi == nullptr, "unshuffle conv takes one source");
+      for (int t = 0; t < 4; ++t) taps.push_back(Tap{0, 0, t});
+      n_lat = 4;
+    } else if (L.mode == 0) {
+      for (int t = 0; t < 9; ++t) taps.push_back(Tap{t / 3 - 1, t % 3 - 1, 0});
     } else {
-      if (get_map(&m, in0, cap_img, c0, g, -1)) return -1;
-      p.amap[0] = *m;
-      if (in1) {
-        if (get_map(&m, in1, cap_img, c1, g, -1)) return -1;
-        p.amap[1] = *m;
-      } else {
-        p.amap[1] = p.amap[0];
-      }
-      p.amap[2] = p.amap[0];
-      p.amap[3] = p.amap[0];
-      const int taps = L.mode == 0 ? 9 : 1;
-      for (int t = 0; t < taps; ++t) {
-        const int dy = L.mode == 0 ? t / 3 - 1 : 0, dx = L.mode == 0 ? t % 3 - 1 : 0;
-        p.seg[nseg++] = ConvSeg{0, (int16_t)dy, (int16_t)dx, (int16_t)(c0 / 64)};
-        ksteps += c0 / 64;
-        if (in1) {
-          p.seg[nseg++] = ConvSeg{1, (int16_t)dy, (int16_t)dx, (int16_t)(c1 / 64)};
-          ksteps += c1 / 64;
+      taps.push_back(Tap{0, 0, 0});
+    }
+    // activation maps: index = lattice + n_lat * (source + 2 * is_lo)
+    auto map_index = [&](int lat, int src, int lo) { return lat + n_lat * (src + 2 * lo); };
+    int max_map = 0;
+    bool map_set[kMaxAMaps] = {false};
+    for (int lat = 0; lat < n_lat; ++lat)
+      for (int src = 0; src < (in1.hi ? 2 : 1); ++src)
+        for (int lo = 0; lo < 2; ++lo) {
+          const Act& a = src ? in1 : in0;
+          const __half* base = lo ? a.lo : a.hi;
+          if (!base) continue;
+          // unshuffle with a remainder: 4 lattices x (hi, lo) of ONE source = maps 0..3, 4..7
+          const int idx = (n_lat == 4) ? lat + 4 * lo : map_index(lat, src, lo);
+          NOPE_CHECK(idx < kMaxAMaps, "conv: activation map table overflow");
+          if (get_map(&m, base, cap_img, a.C, g, L.mode == 2 ? lat : -1)) return -1;
+          p.amap[idx] = *m;
+          map_set[idx] = true;
+          max_map = std::max(max_map, idx);
         }
+    p.n_amaps = max_map + 1;
+    for (int i = 1; i < p.n_amaps; ++i)      // unused slots: any valid descriptor (they are only prefetched)
+      if (!map_set[i]) p.amap[i] = p.amap[0];
+    int nseg = 0, ksteps = 0;
+    auto add_seg = [&](int map, const Tap& t, int nch, int wcol) {
+      p.seg[nseg++] = ConvSeg{(int16_t)map, (int16_t)t.dy, (int16_t)t.dx, (int16_t)nch, wcol + 1};
+      ksteps += nch;
+    };
+    const int n_products = 1 + (wlo ? 1 : 0) + ((alo0 || alo1) ? 1 : 0);
+    NOPE_CHECK((int)taps.size() * (in1.hi ? 2 : 1) * n_products <= kMaxSeg, "conv: segment table overflow");
+    for (size_t ti = 0; ti < taps.size(); ++ti) {
+      const Tap& t = taps[ti];
+      const int wbase = (int)ti * L.cin;
+      const int mh0 = (n_lat == 4) ? t.lat : map_index(0, 0, 0);
+      const int ml0 = (n_lat == 4) ? t.lat + 4 : map_index(0, 0, 1);
+      // A_hi W_hi
+      add_seg(mh0, t, c0 / 64, wbase);
+      if (in1.hi) add_seg(map_index(0, 1, 0), t, c1 / 64, wbase + c0);
+      // A_hi W_lo
+      if (wlo) {
+        add_seg(mh0, t, c0 / 64, L.K + wbase);
+        if (in1.hi) add_seg(map_index(0, 1, 0), t, c1 / 64, L.K + wbase + c0);
       }
+      // A_lo W_hi
+      if (alo0) add_seg(ml0, t, c0 / 64, wbase);
+      if (alo1) add_seg(map_index(0, 1, 1), t, c1 / 64, wbase + c0);
     }
     p.bmap = L.wmap;
     p.bmap_half = L.wmap_half;
     if (L.mode == 3) {
       for (int t = 0; t < 4; ++t) {
-        if (get_map(&m, out, cap_img, L.cout, g, t)) return -1;   // stride-2 sub-lattice (py, px)
+        if (get_map(&m, out.hi, cap_img, L.cout, g, t)) return -1;   // stride-2 sub-lattice (py, px)
         p.omap[t] = *m;
       }
+      p.src_w = g.W;
+      p.src_hw = g.H * g.W;
     } else {
-      if (get_map(&m, out, cap_img, L.cout, g, -1)) return -1;
+      if (get_map(&m, out.hi, cap_img, L.cout, g, -1)) return -1;
       for (int t = 0; t < 4; ++t) p.omap[t] = *m;
     }
     p.bias = L.bias;
@@ -497,7 +619,7 @@ struct nope_unet {
     p.stats_hw = So * So;
     p.stats_noct = L.cout / 8;
     p.n_total = L.cout;
-    p.m_valid = n_img * So * So;
+    p.m_valid = n_img * g.H * g.W;     // rows of the GEMM (source pixels for the folded upsample conv)
     p.nseg = nseg;
     p.ksteps = ksteps;
     p.m_tiles = geom_m_tiles(g, n_img);
@@ -506,9 +628,68 @@ struct nope_unet {
     p.tiles_per_img = g.tiles_per_img;
     p.h_cnt = g.h_cnt;
     p.b_cnt = g.b_cnt;
-    NOPE_CHECK(ksteps * 64 == L.K, "conv: K mismatch");
     NOPE_CHECK(!(stats && L.mode == 3), "fused statistics are not available on the upsample conv");
+    if (gs) {
+      NOPE_CHECK(conv_impl == 2 && L.mode != 3 && !stats, "fused GroupNorm epilogue: CTA-pair kernel, no upsample");
+      GnFuse& f = p.gn;
+      const int hw = So * So;
+      f.G = gs->norm ? gs->norm->G : 0;
+      if (gs->norm) {
+        NOPE_CHECK(gs->norm->C == L.cout, "fused GroupNorm: channel mismatch");
+        f.gamma = gs->norm->gamma;
+        f.beta = gs->norm->beta;
+        f.cpg = L.cout / f.G;
+        NOPE_CHECK(f.cpg % 8 == 0 && (f.cpg >= L.bn ? f.cpg % L.bn == 0 : L.bn % f.cpg == 0),
+                   "fused GroupNorm: groups must tile the channel tiles");
+      } else {
+        f.cpg = L.cout;
+      }
+      f.gpt = std::max(1, L.bn / f.cpg);
+      f.tpg = std::max(1, f.cpg / L.bn);
+      f.mt = std::max(1, g.tiles_per_img);
+      f.ipt = g.tiles_per_img > 0 ? 1 : g.b_cnt;
+      f.expected = f.G > 0 ? f.mt * f.tpg : 1;
+      int sh = 0;
+      while ((1 << sh) < hw) ++sh;
+      NOPE_CHECK((1 << sh) == hw, "fused GroupNorm: H*W must be a power of two");
+      f.hw_shift = sh;
+      f.inv_cnt = 1.0f / ((float)hw * (float)f.cpg);
+      f.eps = 1e-5f;
+      f.silu = gs->silu ? 1 : 0;
+      f.pb = gs->pb_offset >= 0 ? pb : nullptr;
+      f.pb_stride = P;
+      f.pb_off = std::max(gs->pb_offset, 0);
+      f.n_img = n_img;
+      if (gs->res.hi) {
+        NOPE_CHECK(gs->res.C == L.cout, "fused residual: channel mismatch");
+        NOPE_CHECK(gs->res_div == 0 || g.tiles_per_img > 0, "residual image mapping needs >= 128-pixel images");
+        if (get_map(&m, gs->res.hi, gs->res_div > 0 ? cap_ref : cap_img, L.cout, g, -1)) return -1;
+        p.rmap = *m;
+        f.has_res = 1;
+        f.res_lo = gs->res.lo;
+      } else {
+        p.rmap = p.omap[0];
+      }
+      f.res_div = gs->res_div;
+      f.res_base = gs->res_base;
+      f.out_lo = out.lo;
+      f.emit = gs->emit;
+      f.emit_parts = f.mt * p.n_tiles;
+      NOPE_CHECK(f.ipt * f.gpt <= 64 && f.ipt <= 8, "fused GroupNorm: tile holds too many (image, group) pairs");
+      if (f.expected > 1) {
+        const size_t n_sg = (size_t)(p.m_tiles / f.mt + 1) * (p.n_tiles / f.tpg);
+        NOPE_CHECK(L.id >= 0 && L.id < std::max(n_layers, 1) && n_sg <= xcnt_per_layer && xpart && xcnt,
+                   "fused GroupNorm: workspace for the tile sync is missing");
+        NOPE_CHECK(n_sg * f.expected * f.ipt * f.gpt <= (size_t)std::max(cap, cap_ref) * 64 + 64 * 8,
+                   "fused GroupNorm: partial-sum buffer too small");
+        f.xpart = xpart;
+        f.xcnt = xcnt + (size_t)L.id * xcnt_per_layer;
+      }
+    } else if (out.lo) {
+      p.out_lo = out.lo;                // extras epilogue writes the remainder
+    }
     auto launch = [&]() {
+      if (gs) return launch_conv_gn(p, L.bn, num_sms, st);
       return conv_impl == 2 ? launch_conv_tc2(p, L.bn, num_sms, st) : launch_conv_tc(p, L.bn, num_sms, st);
     };
     if (!profile) return launch();
@@ -520,10 +701,13 @@ struct nope_unet {
     NOPE_CUDA(cudaEventRecord(e1, st));
     prof_ev.push_back(e0);
     prof_ev.push_back(e1);
-    // executed FLOPs: mode 3 runs 4 parity GEMMs of K = 4 Cin over the source-resolution pixels
-    prof_flops.push_back(2.0 * (double)n_img * So * So * (double)L.cout * (double)L.K);
+    // executed FLOPs: mode 3 runs 4 parity GEMMs of K = 4 Cin over the source-resolution pixels;
+    // the split-precision modes execute 2x / 3x the K-steps of the fp16 mode
+    prof_flops.push_back(2.0 * (double)n_img * So * So * (double)L.cout * (double)ksteps * 64.0);
+    prof_alg.push_back(2.0 * (double)n_img * So * So * (double)L.cout * (double)L.K);
     return rc;
   }
+  std::vector<double> prof_alg;     // algorithmic (fp16-mode) FLOPs of the same launches
 
   // pixel slabs per image for the GroupNorm kernels: as few as keep >= ~4 CTAs per SM in
   // flight (every CTA pays a fixed statistics prologue), at most 8, and >= 32 pixels each
@@ -573,86 +757,144 @@ struct nope_unet {
   // fixed number of sub-slabs per image for statistics emitted by gn_apply (<= 8, >= 32 pixels
   // each): independent of the number of images, so results do not depend on chunk / shard size
   static int emit_parts_of(int hw) { return hw >= 256 ? 8 : (hw >= 32 ? hw / 32 : 1); }
+  // partial sums per image emitted by the fused epilogue: one per (M-tile of the image, N-tile)
+  static int fused_emit_parts(int S, int C) {
+    return std::max(1, S * S / kBM) * (C / pick_bn(C));
+  }
 
-  int tap(const char* name, const __half* buf, int C, int S, int n, cudaStream_t st) {
+  int tap(const char* name, const Act& buf, int C, int S, int n, cudaStream_t st) {
     if (tap_out == nullptr || tap_name != name || tap_hit) return 0;
     NOPE_CHECK((int64_t)n * C * S * S <= tap_cap, "debug tap: output buffer too small");
-    nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * C * S * S), 256, 0, st>>>(buf, tap_out, n, C, S * S);
+    nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * C * S * S), 256, 0, st>>>(buf.hi, tap_out, n, C, S * S,
+                                                                                   buf.lo);
     NOPE_CUDA(cudaGetLastError());
     tap_C = C; tap_S = S; tap_hit = true;
     return 0;
   }
 
-  // ResnetBlock.forward (model_utils.py:271-279) on NHWC fp16.  GroupNorm statistics ride on
-  // the conv epilogues (SA); `emit_g1` makes the last apply also emit the GroupNorm(1, C)
-  // statistics of the block output into SB for a following attention pre-norm.
-  int resblock(const std::string& p, const __half* in0, int c0, const __half* in1, int c1,
-               __half* out, int S, int n, bool pose, cudaStream_t st, bool emit_g1 = false) {
+  // ResnetBlock.forward (model_utils.py:271-279) on NHWC fp16.
+  // Fused schedule: conv1 [GN8 + SiLU + pose bias] -> h ; (res_conv) ; conv2 [GN8 + SiLU + residual] -> out:
+  // two or three launches, no tensor is written un-normalised.  `emit_g1` makes conv2's epilogue also
+  // emit the GroupNorm(1, C) statistics of the block output into SB for a following attention pre-norm.
+  // Unfused schedule (conv_impl 0 / 1 or fuse_gn off): GroupNorm statistics ride on the conv epilogues
+  // (SA) and gn_apply_kernel normalises in a separate pass.
+  int resblock(const std::string& p, const Act& in0, const Act& in1, const Act& out, int S, int n, bool pose,
+               cudaStream_t st, bool emit_g1 = false, int res_div = 0, int res_base = 0, const Act* hoisted_h = nullptr) {
     const ConvLayer& b1 = convs.at(p + ".block1");
     const ConvLayer& b2 = convs.at(p + ".block2");
     const int co = b1.cout;
     const int parts = st_parts_of(S);
-    if (conv(b1, in0, c0, in1, c1, TA, S, n, cap, st, SA)) return -1;
-    if (gn(&norms.at(p + ".norm1"), TA, TB, S, co, n, true, pose ? pb_off.at(p) : -1, nullptr, nullptr, st,
+    auto it = convs.find(p + ".res");
+    if (fused()) {
+      Act h(TB.hi, co, split() ? TB.lo : nullptr);
+      if (hoisted_h) {
+        h = *hoisted_h;
+      } else {
+        GnSpec s1;
+        s1.norm = &norms.at(p + ".norm1");
+        s1.silu = true;
+        s1.pb_offset = pose ? pb_off.at(p) : -1;
+        if (conv(b1, in0, in1, h, S, n, cap, st, nullptr, &s1)) return -1;
+      }
+      GnSpec s2;
+      s2.norm = &norms.at(p + ".norm2");
+      s2.silu = true;
+      if (it != convs.end()) {
+        Act r(TC.hi, co, split() ? TC.lo : nullptr);
+        if (conv(it->second, in0, in1, r, S, n, cap, st)) return -1;
+        s2.res = r;
+      } else {
+        NOPE_CHECK(in1.hi == nullptr && in0.C == co, "resblock: identity residual needs Cin == Cout");
+        s2.res = in0;
+        s2.res_div = res_div;
+        s2.res_base = res_base;
+      }
+      s2.emit = emit_g1 ? SB : nullptr;
+      return conv(b2, h, Act(), out, S, n, cap, st, nullptr, &s2);
+    }
+    NOPE_CHECK(!hoisted_h && res_div == 0, "resblock: hoisting arguments belong to the fused schedule");
+    if (conv(b1, in0, in1, Act(TA.hi, co), S, n, cap, st, SA)) return -1;
+    if (gn(&norms.at(p + ".norm1"), TA.hi, TB.hi, S, co, n, true, pose ? pb_off.at(p) : -1, nullptr, nullptr, st,
            SA, parts, co / 8))
       return -1;
-    if (conv(b2, TB, co, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
-    const __half* res = in0;
-    auto it = convs.find(p + ".res");
+    if (conv(b2, Act(TB.hi, co), Act(), Act(TA.hi, co), S, n, cap, st, SA)) return -1;
+    const __half* res = in0.hi;
     if (it != convs.end()) {
-      if (conv(it->second, in0, c0, in1, c1, TC, S, n, cap, st)) return -1;
-      res = TC;
+      if (conv(it->second, in0, in1, Act(TC.hi, co), S, n, cap, st)) return -1;
+      res = TC.hi;
     } else {
-      NOPE_CHECK(in1 == nullptr && c0 == co, "resblock: identity residual needs Cin == Cout");
+      NOPE_CHECK(in1.hi == nullptr && in0.C == co, "resblock: identity residual needs Cin == Cout");
     }
-    return gn(&norms.at(p + ".norm2"), TA, out, S, co, n, true, -1, res, nullptr, st, SA, parts, co / 8,
+    return gn(&norms.at(p + ".norm2"), TA.hi, out.hi, S, co, n, true, -1, res, nullptr, st, SA, parts, co / 8,
               emit_g1 ? SB : nullptr);
   }
 
   // Residual(PreNorm(LinearAttention)) (model_utils.py:393-418).  x's GroupNorm(1) statistics
-  // were emitted into SB by the producer of x; to_out[1]'s come from the to_out conv epilogue.
-  int linattn(const std::string& p, const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
-    if (gn(&norms.at(p + ".prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
-           emit_parts_of(S * S), 1))
+  // were emitted into SB by the producer of x; to_out[1] (GroupNorm(1)) + the residual add run in the
+  // to_out convolution's epilogue (fused) or come from its epilogue statistics (unfused).
+  int linattn(const std::string& p, const Act& x, const Act& out, int C, int S, int n, cudaStream_t st) {
+    const int eparts = fused() ? fused_emit_parts(S, C) : emit_parts_of(S * S);
+    if (gn(&norms.at(p + ".prenorm"), x.hi, TB.hi, S, C, n, false, -1, nullptr, nullptr, st, SB, eparts, 1))
       return -1;
-    if (conv(convs.at(p + ".qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
-    linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD, TC, S * S);
+    if (conv(convs.at(p + ".qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
+    linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD.hi, TC.hi, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
-    if (conv(convs.at(p + ".out"), TC, kHeadsHidden, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
-    return gn(&norms.at(p + ".outnorm"), TA, out, S, C, n, false, -1, x, nullptr, st, SA, st_parts_of(S),
+    if (fused()) {
+      GnSpec s;
+      s.norm = &norms.at(p + ".outnorm");
+      s.res = x;
+      return conv(convs.at(p + ".out"), Act(TC.hi, kHeadsHidden), Act(), out, S, n, cap, st, nullptr, &s);
+    }
+    if (conv(convs.at(p + ".out"), Act(TC.hi, kHeadsHidden), Act(), Act(TA.hi, C), S, n, cap, st, SA)) return -1;
+    return gn(&norms.at(p + ".outnorm"), TA.hi, out.hi, S, C, n, false, -1, x.hi, nullptr, st, SA, st_parts_of(S),
               C / 8);
   }
 
   // Residual(PreNorm(Attention)) (model_utils.py:367-390)
-  int midattn(const __half* x, __half* out, int C, int S, int n, cudaStream_t st) {
+  int midattn(const Act& x, const Act& out, int C, int S, int n, cudaStream_t st) {
     NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
-    if (gn(&norms.at("mid_attn.prenorm"), x, TB, S, C, n, false, -1, nullptr, nullptr, st, SB,
-           emit_parts_of(S * S), 1))
+    const int eparts = fused() ? fused_emit_parts(S, C) : emit_parts_of(S * S);
+    if (gn(&norms.at("mid_attn.prenorm"), x.hi, TB.hi, S, C, n, false, -1, nullptr, nullptr, st, SB, eparts, 1))
       return -1;
-    if (conv(convs.at("mid_attn.qkv"), TB, C, nullptr, 0, TD, S, n, cap, st)) return -1;
-    midattn_kernel<<<n, 128, 0, st>>>(TD, TC, S * S);
+    if (conv(convs.at("mid_attn.qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
+    midattn_kernel<<<n, 128, 0, st>>>(TD.hi, TC.hi, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
-    if (conv(convs.at("mid_attn.out"), TC, kHeadsHidden, nullptr, 0, TA, S, n, cap, st)) return -1;
-    return gn(nullptr, TA, out, S, C, n, false, -1, x, nullptr, st);
+    if (fused()) {
+      GnSpec s;                // no normalisation: out = to_out(attn) + x
+      s.res = x;
+      return conv(convs.at("mid_attn.out"), Act(TC.hi, kHeadsHidden), Act(), out, S, n, cap, st, nullptr, &s);
+    }
+    if (conv(convs.at("mid_attn.out"), Act(TC.hi, kHeadsHidden), Act(), Act(TA.hi, C), S, n, cap, st)) return -1;
+    return gn(nullptr, TA.hi, out.hi, S, C, n, false, -1, x.hi, nullptr, st);
   }
 
   // pose-independent prefix, once per reference image: x0 = init_conv(ref),
   // g1 = SiLU(GN(downs.0.0.block1.proj(x0)))   (u_net.py:161; model_utils.py:272)
   int prestage(const float* ref_feat, int B, cudaStream_t st) {
-    init_conv_kernel<<<ew_grid((long long)B * S0 * S0 * dim), 256, 0, st>>>(ref_feat, init_w, init_b, x0,
-                                                                            B, Cl, S0, S0, dim);
+    init_conv_kernel<<<ew_grid((long long)B * S0 * S0 * dim), 256, 0, st>>>(ref_feat, init_w, init_b, x0.hi,
+                                                                            B, Cl, S0, S0, dim, split() ? x0.lo : nullptr);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
-    if (conv(convs.at("downs.0.0.block1"), x0, dim, nullptr, 0, pt, S0, B, cap_ref, st, SA)) return -1;
-    return gn(&norms.at("downs.0.0.norm1"), pt, g1, S0, dim, B, true, -1, nullptr, nullptr, st, SA,
+    const Act xin(x0.hi, dim, split() ? x0.lo : nullptr);
+    if (fused()) {
+      GnSpec s;
+      s.norm = &norms.at("downs.0.0.norm1");
+      s.silu = true;
+      return conv(convs.at("downs.0.0.block1"), xin, Act(), Act(g1.hi, dim, split() ? g1.lo : nullptr), S0, B,
+                  cap_ref, st, nullptr, &s);
+    }
+    if (conv(convs.at("downs.0.0.block1"), xin, Act(), Act(pt, dim), S0, B, cap_ref, st, SA)) return -1;
+    return gn(&norms.at("downs.0.0.norm1"), pt, g1.hi, S0, dim, B, true, -1, nullptr, nullptr, st, SA,
               st_parts_of(S0), dim / 8);
   }
 
   // UNet.forward for hypotheses [hyp0, hyp0 + n) of the flattened (b, pose) list
   int forward_chunk(const float* poses, int hyp0, int n, int N, const float* query_feat,
                     float* out_emb, float* score_part, cudaStream_t st) {
+    const bool sp = split();
+    auto A = [&](const Act& buf, int C) { return Act(buf.hi, C, sp ? buf.lo : nullptr); };
     // hypothesis -> reference image
     iota_div(ref_of, hyp0, N, n, st);
     // pose embedding + all 19 pose projections in one GEMM
@@ -665,84 +907,86 @@ struct nope_unet {
     // r (= init_conv output) and the hoisted block1 output, broadcast per hypothesis
     const int hw0 = S0 * S0;
     bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-        x0, ref_of, nullptr, 0, 0, RB, n, hw0, dim);
+        x0.hi, ref_of, nullptr, 0, 0, RB.hi, n, hw0, dim, sp ? x0.lo : nullptr, sp ? RB.lo : nullptr);
     bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-        g1, ref_of, pb, P, pb_off.at("downs.0.0"), TB, n, hw0, dim);
+        g1.hi, ref_of, pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, sp ? g1.lo : nullptr, sp ? TB.lo : nullptr);
     NOPE_CUDA(cudaGetLastError());
     launches += 2;
-    if (tap("init_conv", RB, dim, S0, n, st)) return -1;
+    if (tap("init_conv", A(RB, dim), dim, S0, n, st)) return -1;
 
     // ---- downs
-    __half* cur = nullptr;
+    Act cur;
     int S = S0;
     for (int i = 0; i < 4; ++i) {
       const int C = dims[i];
       const std::string p = "downs." + std::to_string(i);
+      const Act s0 = A(sk[i][0], C), s1 = A(sk[i][1], C);
       if (i == 0) {
         // block 0 with its block1 half hoisted: TB already holds SiLU(GN(conv(x0))) + pose bias
-        if (conv(convs.at(p + ".0.block2"), TB, C, nullptr, 0, TA, S, n, cap, st, SA)) return -1;
-        if (gn(&norms.at(p + ".0.norm2"), TA, sk[0][0].p, S, C, n, true, -1, x0, ref_of, st, SA,
-               st_parts_of(S), C / 8))
-          return -1;
+        if (fused()) {
+          const Act h = A(TB, C);
+          if (resblock(p + ".0", A(x0, C), Act(), s0, S, n, true, st, false, N, hyp0, &h)) return -1;
+        } else {
+          if (conv(convs.at(p + ".0.block2"), Act(TB.hi, C), Act(), Act(TA.hi, C), S, n, cap, st, SA)) return -1;
+          if (gn(&norms.at(p + ".0.norm2"), TA.hi, s0.hi, S, C, n, true, -1, x0.hi, ref_of, st, SA,
+                 st_parts_of(S), C / 8))
+            return -1;
+        }
       } else {
-        if (resblock(p + ".0", cur, C, nullptr, 0, sk[i][0].p, S, n, true, st)) return -1;
+        if (resblock(p + ".0", cur, Act(), s0, S, n, true, st)) return -1;
       }
-      if (tap((p + ".0").c_str(), sk[i][0].p, C, S, n, st)) return -1;
-      if (resblock(p + ".1", sk[i][0].p, C, nullptr, 0, XA, S, n, true, st, true)) return -1;
-      if (tap((p + ".1").c_str(), XA, C, S, n, st)) return -1;
-      if (linattn(p + ".2", XA, sk[i][1].p, C, S, n, st)) return -1;
-      if (tap((p + ".2").c_str(), sk[i][1].p, C, S, n, st)) return -1;
+      if (tap((p + ".0").c_str(), s0, C, S, n, st)) return -1;
+      if (resblock(p + ".1", s0, Act(), A(XA, C), S, n, true, st, true)) return -1;
+      if (tap((p + ".1").c_str(), A(XA, C), C, S, n, st)) return -1;
+      if (linattn(p + ".2", A(XA, C), s1, C, S, n, st)) return -1;
+      if (tap((p + ".2").c_str(), s1, C, S, n, st)) return -1;
       if (i < 3) S >>= 1;
-      if (conv(convs.at(p + ".3"), sk[i][1].p, C, nullptr, 0, XB, S, n, cap, st)) return -1;
-      if (tap((p + ".3").c_str(), XB, dims[i + 1], S, n, st)) return -1;
-      cur = XB;
+      if (conv(convs.at(p + ".3"), s1, Act(), A(XB, dims[i + 1]), S, n, cap, st)) return -1;
+      if (tap((p + ".3").c_str(), A(XB, dims[i + 1]), dims[i + 1], S, n, st)) return -1;
+      cur = A(XB, dims[i + 1]);
     }
     // ---- mid, twice with shared weights (u_net.py:177-183)
     const int Cm = dims[4];
+    Act xa = XA, xb = XB;
     for (int rep = 0; rep < 2; ++rep) {
-      if (resblock("mid_block1", XB, Cm, nullptr, 0, XA, S, n, true, st, true)) return -1;
-      if (midattn(XA, XB, Cm, S, n, st)) return -1;
-      if (resblock("mid_block2", XB, Cm, nullptr, 0, XA, S, n, true, st)) return -1;
-      if (tap(rep == 0 ? "mid.0" : "mid.1", XA, Cm, S, n, st)) return -1;
-      std::swap(XA, XB);
+      if (resblock("mid_block1", A(xb, Cm), Act(), A(xa, Cm), S, n, true, st, true)) return -1;
+      if (midattn(A(xa, Cm), A(xb, Cm), Cm, S, n, st)) return -1;
+      if (resblock("mid_block2", A(xb, Cm), Act(), A(xa, Cm), S, n, true, st)) return -1;
+      if (tap(rep == 0 ? "mid.0" : "mid.1", A(xa, Cm), Cm, S, n, st)) return -1;
+      std::swap(xa, xb);
     }
-    cur = XB;
-    __half* oth = XA;
+    Act curb = xb, othb = xa;     // buffers (channel counts vary per level)
     // ---- ups
+    int ccur = Cm;
     for (int j = 0; j < 4; ++j) {
       const int din = dims[3 - j], dout = dims[4 - j];
       const std::string p = "ups." + std::to_string(j);
-      if (resblock(p + ".0", cur, dout, sk[3 - j][1].p, din, oth, S, n, true, st)) return -1;
-      std::swap(cur, oth);
-      if (tap((p + ".0").c_str(), cur, dout, S, n, st)) return -1;
-      if (resblock(p + ".1", cur, dout, sk[3 - j][0].p, din, oth, S, n, true, st, true)) return -1;
-      std::swap(cur, oth);
-      if (linattn(p + ".2", cur, oth, dout, S, n, st)) return -1;
-      std::swap(cur, oth);
-      if (tap((p + ".2").c_str(), cur, dout, S, n, st)) return -1;
-      if (j < 3) {
-        S <<= 1;   // folded nearest-x2 + conv3x3: reads `cur` at S/2, writes `oth` at S
-        if (conv(convs.at(p + ".3"), cur, dout, nullptr, 0, oth, S, n, cap, st)) return -1;
-      } else {
-        if (conv(convs.at(p + ".3"), cur, dout, nullptr, 0, oth, S, n, cap, st)) return -1;
-      }
-      std::swap(cur, oth);
-      if (tap((p + ".3").c_str(), cur, din, S, n, st)) return -1;
+      if (resblock(p + ".0", A(curb, dout), A(sk[3 - j][1], din), A(othb, dout), S, n, true, st)) return -1;
+      std::swap(curb, othb);
+      if (tap((p + ".0").c_str(), A(curb, dout), dout, S, n, st)) return -1;
+      if (resblock(p + ".1", A(curb, dout), A(sk[3 - j][0], din), A(othb, dout), S, n, true, st, true)) return -1;
+      std::swap(curb, othb);
+      if (linattn(p + ".2", A(curb, dout), A(othb, dout), dout, S, n, st)) return -1;
+      std::swap(curb, othb);
+      if (tap((p + ".2").c_str(), A(curb, dout), dout, S, n, st)) return -1;
+      if (j < 3) S <<= 1;   // folded nearest-x2 + conv3x3: reads `cur` at S/2, writes `oth` at S
+      if (conv(convs.at(p + ".3"), A(curb, dout), Act(), A(othb, din), S, n, cap, st)) return -1;
+      std::swap(curb, othb);
+      ccur = din;
+      if (tap((p + ".3").c_str(), A(curb, din), din, S, n, st)) return -1;
     }
     // ---- head
-    if (resblock("final_res_block", cur, dim, RB, dim, oth, S, n, true, st)) return -1;
-    std::swap(cur, oth);
-    if (tap("final_res_block", cur, dim, S, n, st)) return -1;
-    if (resblock("final_conv.0", cur, dim, nullptr, 0, oth, S, n, false, st)) return -1;
-    std::swap(cur, oth);
-    if (tap("final_conv.0", cur, dim, S, n, st)) return -1;
-    XA = cur;  // keep the ping-pong pair consistent for the next chunk
-    XB = oth;
+    if (resblock("final_res_block", A(curb, ccur), A(RB, dim), A(othb, dim), S, n, true, st)) return -1;
+    std::swap(curb, othb);
+    if (tap("final_res_block", A(curb, dim), dim, S, n, st)) return -1;
+    if (resblock("final_conv.0", A(curb, dim), Act(), A(othb, dim), S, n, false, st)) return -1;
+    std::swap(curb, othb);
+    if (tap("final_conv.0", A(curb, dim), dim, S, n, st)) return -1;
     const int hw = S * S;
     const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
     final_conv_score_kernel<<<dim3(nslab, n), kFinalThreads, (size_t)Cl * dim * sizeof(float), st>>>(
-        cur, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat, ref_of,
-        score_part ? score_part + (size_t)hyp0 * nslab : nullptr, hw, dim, Cl);
+        curb.hi, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat, ref_of,
+        score_part ? score_part + (size_t)hyp0 * nslab : nullptr, hw, dim, Cl, sp ? curb.lo : nullptr);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     return 0;
@@ -751,7 +995,7 @@ struct nope_unet {
   int iota_div(int* r, int h0, int N, int n, cudaStream_t st);
   int conv_pose(int n, cudaStream_t st) {
     // pb[n, P] = cs[n, cemb] @ Wp^T + bp : the 1x1 "image" geometry of the conv kernel
-    return conv(poseproj, cs, cemb, nullptr, 0, pb, 1, n, cap, st);
+    return conv(poseproj, Act(cs, cemb), Act(), Act(pb, P), 1, n, cap, st);
   }
 };
 
@@ -778,14 +1022,17 @@ struct Scratch {
     return 0;
   }
 };
-int to_nhwc(const float* x, __half** out, Scratch& s, int n, int C, int hw, cudaStream_t st) {
+int to_nhwc(const float* x, __half** out, Scratch& s, int n, int C, int hw, cudaStream_t st,
+            __half** out_lo = nullptr) {
   if (s.get(out, (size_t)n * C * hw)) return -1;
-  nchw_f32_to_nhwc_f16_kernel<<<ew_grid((long long)n * C * hw), 256, 0, st>>>(x, *out, n, C, hw);
+  if (out_lo && s.get(out_lo, (size_t)n * C * hw)) return -1;
+  nchw_f32_to_nhwc_f16_kernel<<<ew_grid((long long)n * C * hw), 256, 0, st>>>(x, *out, n, C, hw,
+                                                                              out_lo ? *out_lo : nullptr);
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }
-int to_nchw(const __half* x, float* out, int n, int C, int hw, cudaStream_t st) {
-  nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * C * hw), 256, 0, st>>>(x, out, n, C, hw);
+int to_nchw(const __half* x, float* out, int n, int C, int hw, cudaStream_t st, const __half* x_lo = nullptr) {
+  nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * C * hw), 256, 0, st>>>(x, out, n, C, hw, x_lo);
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -859,34 +1106,75 @@ int nope_unet_set_chunk(nope_unet_t* u, int hyps) {
 }
 int nope_unet_set_conv_impl(nope_unet_t* u, int impl) {
   NOPE_CHECK(u && impl >= 0 && impl <= 2, "impl must be 0 (tcgen05), 1 (simt) or 2 (tcgen05 2-CTA)");
+  NOPE_CHECK(impl != 1 || u->precision == 0, "the SIMT debug convolution only runs fp16 weights");
   u->conv_impl = impl;
   return 0;
 }
+int nope_unet_set_option(nope_unet_t* u, const char* name, int value) {
+  NOPE_CHECK(u && name, "null argument");
+  if (std::strcmp(name, "fuse_gn") == 0) {
+    NOPE_CHECK(value != 0 || u->precision < 2, "split precision needs the fused GroupNorm epilogue");
+    u->fuse_gn = value != 0;
+    return 0;
+  }
+  if (std::strcmp(name, "precision") == 0) {
+    NOPE_CHECK(!u->finalized, "precision must be set before nope_unet_finalize");
+    NOPE_CHECK(value == 0 || u->conv_impl != 1, "the SIMT debug convolution only runs fp16 weights");
+    NOPE_CHECK(value >= 0 && value <= 2, "precision must be 0 (fp16), 1 (exact weights) or 2 (split)");
+    u->precision = value;
+    return 0;
+  }
+  if (std::strcmp(name, "conv_impl") == 0) return nope_unet_set_conv_impl(u, value);
+  return fail(std::string("unknown option: ") + name);
+}
+int nope_unet_get_option(const nope_unet_t* u, const char* name, int* value) {
+  NOPE_CHECK(u && name && value, "null argument");
+  if (std::strcmp(name, "fuse_gn") == 0) { *value = u->fuse_gn ? 1 : 0; return 0; }
+  if (std::strcmp(name, "precision") == 0) { *value = u->precision; return 0; }
+  if (std::strcmp(name, "conv_impl") == 0) { *value = u->conv_impl; return 0; }
+  return fail(std::string("unknown option: ") + name);
+}
 int64_t nope_unet_last_launch_count(const nope_unet_t* u) { return u ? u->launches : 0; }
+
+int64_t nope_unet_workspace_bytes(nope_unet_t* u, int hyps, int refs, int scores) {
+  if (!u || !u->finalized || hyps < 1 || refs < 1 || scores < 0) {
+    fail("nope_unet_workspace_bytes: finalized engine, hyps >= 1, refs >= 1 required");
+    return -1;
+  }
+  return (int64_t)u->workspace_bytes(hyps, refs, scores);
+}
+int nope_unet_set_workspace(nope_unet_t* u, void* ptr, int64_t bytes, int hyps, int refs, int scores) {
+  NOPE_CHECK(u && u->finalized, "engine not finalized");
+  NOPE_CUDA(cudaSetDevice(u->device));
+  return u->set_workspace(ptr, (size_t)bytes, hyps, refs, scores);
+}
 
 int nope_unet_profile(nope_unet_t* u, int enable) {
   NOPE_CHECK(u, "null engine");
   for (cudaEvent_t e : u->prof_ev) cudaEventDestroy(e);
   u->prof_ev.clear();
   u->prof_flops.clear();
+  u->prof_alg.clear();
   u->profile = enable != 0;
   return 0;
 }
 
-int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops, int64_t* conv_launches,
-                           double* max_launch_tflops) {
+int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops, double* conv_alg_flops,
+                           int64_t* conv_launches, double* max_launch_tflops) {
   NOPE_CHECK(u && conv_ms && conv_flops && conv_launches, "null argument");
   NOPE_CUDA(cudaDeviceSynchronize());
-  double ms = 0.0, fl = 0.0, best = 0.0;
+  double ms = 0.0, fl = 0.0, alg = 0.0, best = 0.0;
   for (size_t i = 0; i < u->prof_flops.size(); ++i) {
     float t = 0.f;
     NOPE_CUDA(cudaEventElapsedTime(&t, u->prof_ev[2 * i], u->prof_ev[2 * i + 1]));
     ms += t;
     fl += u->prof_flops[i];
+    alg += u->prof_alg[i];
     if (t > 0.f) best = std::max(best, u->prof_flops[i] / (t * 1e-3) / 1e12);
   }
   *conv_ms = ms;
   *conv_flops = fl;
+  if (conv_alg_flops) *conv_alg_flops = alg;
   *conv_launches = (int64_t)u->prof_flops.size();
   if (max_launch_tflops) *max_launch_tflops = best;
   return 0;
@@ -905,36 +1193,20 @@ int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, i
   u->launches = 0;
   const int total = B * N;
   const int cap = std::min(u->chunk, total);
-  if (u->ensure_workspace(cap, B)) return -1;
+  // no allocation here when the caller provided the workspace (nope_unet_set_workspace); otherwise the
+  // engine grows its own slab (device synchronisation + cudaMalloc on growth only)
+  if (u->ensure_workspace(cap, B, query_feat ? total : 0)) return -1;
+  if (u->prepare_stream(st)) return -1;
   const int hw = u->S0 * u->S0;
   const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
-  float* part = nullptr;
-  if (query_feat) {
-    const size_t need = (size_t)total * nslab;
-    if (need > u->score_partial_cap) {
-      NOPE_CUDA(cudaStreamSynchronize(st));
-      if (u->score_partial) cudaFree(u->score_partial);
-      NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->score_partial), need * sizeof(float)));
-      u->score_partial_cap = need;
-    }
-    part = u->score_partial;
-  }
+  float* part = query_feat ? u->score_partial : nullptr;
   if (u->prestage(ref_feat, B, st)) return -1;
   for (int h0 = 0; h0 < total; h0 += cap) {
     const int n = std::min(cap, total - h0);
     if (u->forward_chunk(poses, h0, n, N, query_feat, out_emb, part, st)) return -1;
   }
   if (query_feat && (out_sim || k > 0)) {
-    float* sim = out_sim;
-    if (!sim) {
-      if ((size_t)total > u->sim_buf_cap) {
-        NOPE_CUDA(cudaStreamSynchronize(st));
-        if (u->sim_buf) cudaFree(u->sim_buf);
-        NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->sim_buf), (size_t)total * sizeof(float)));
-        u->sim_buf_cap = total;
-      }
-      sim = u->sim_buf;
-    }
+    float* sim = out_sim ? out_sim : u->sim_buf;
     sim_topk_kernel<<<B, 256, 0, st>>>(part, nslab, sim, N, k, out_topv,
                                        reinterpret_cast<long long*>(out_topi), (long long)idx_base);
     NOPE_CUDA(cudaGetLastError());
@@ -1067,7 +1339,7 @@ int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, i
   NOPE_CUDA(cudaGetDeviceProperties(&prop, dev));
   eng.num_sms = prop.multiProcessorCount;
   ConvLayer L;
-  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = cin * taps; L.bn = pick_bn(Cout); L.w = wp;
+  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = cin * taps; L.Kp = L.K; L.bn = pick_bn(Cout); L.w = wp;
   float* dbias = nullptr;
   if (bias) {
     if (s.get(&dbias, Cout)) return -1;
@@ -1077,7 +1349,7 @@ int nope_op_conv(int impl, int mode, const float* x0, int C0, const float* x1, i
   if (impl != 1 && (make_weight_map(&L.wmap, wp, rows, L.K, L.bn) ||
                     make_weight_map(&L.wmap_half, wp, rows, L.K, L.bn / 2)))
     return -1;
-  if (eng.conv(L, a0, C0, a1, x1 ? C1 : 0, o, H, n_img, n_img, st)) return -1;
+  if (eng.conv(L, Act(a0, C0), x1 ? Act(a1, C1) : Act(), Act(o, Cout), H, n_img, n_img, st)) return -1;
   if (to_nchw(o, out, n_img, Cout, H * W, st)) return -1;
   NOPE_CUDA(cudaStreamSynchronize(st));
   return 0;
@@ -1111,7 +1383,7 @@ int nope_op_conv_gn(int impl, int mode, const float* x0, int C0, const float* x1
   NOPE_CUDA(cudaGetDeviceProperties(&prop, dev));
   eng.num_sms = prop.multiProcessorCount;
   ConvLayer L;
-  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = cin * taps; L.bn = pick_bn(Cout); L.w = wp;
+  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = cin * taps; L.Kp = L.K; L.bn = pick_bn(Cout); L.w = wp;
   L.bias = const_cast<float*>(bias);
   if (impl != 1 && (make_weight_map(&L.wmap, wp, Cout, L.K, L.bn) ||
                     make_weight_map(&L.wmap_half, wp, Cout, L.K, L.bn / 2)))
@@ -1119,7 +1391,7 @@ int nope_op_conv_gn(int impl, int mode, const float* x0, int C0, const float* x1
   const int parts = nope_unet::st_parts_of(H);
   float2* stats = nullptr;
   if (s.get(&stats, (size_t)n_img * parts * (Cout / 8))) return -1;
-  if (eng.conv(L, a0, C0, a1, x1 ? C1 : 0, o, H, n_img, n_img, st, stats)) return -1;
+  if (eng.conv(L, Act(a0, C0), x1 ? Act(a1, C1) : Act(), Act(o, Cout), H, n_img, n_img, st, stats)) return -1;
   NormLayer N;
   N.C = Cout; N.G = G;
   N.gamma = const_cast<float*>(gamma);
@@ -1127,6 +1399,94 @@ int nope_op_conv_gn(int impl, int mode, const float* x0, int C0, const float* x1
   if (eng.gn(&N, o, y, H, Cout, n_img, silu != 0, -1, nullptr, nullptr, st, stats, parts, Cout / 8))
     return -1;
   if (to_nchw(y, out, n_img, Cout, H * W, st)) return -1;
+  NOPE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// The sweep's fused layer: out = [SiLU](GroupNorm_G(conv(x) + bias)) + chan_bias[n, c] + residual, all in the
+// epilogue of the CTA-pair kernel (GnFuse).  precision 0 / 1 / 2 as nope_unet_set_option("precision"); with 2 the
+// inputs and the residual are split into fp16 (hi, lo) pairs and the output is the sum of its pair.
+int nope_op_conv_gn_fused(int mode, int precision, const float* x0, int C0, const float* x1, int C1,
+                          const float* weight, const float* bias, const float* gamma, const float* beta, int G,
+                          int silu, const float* chan_bias, const float* residual, int res_div, float* out,
+                          float* emit_out, int n_img, int H, int W, int Cout, void* stream) {
+  NOPE_CHECK(x0 && weight && out, "null argument");
+  NOPE_CHECK(mode >= 0 && mode <= 2 && H == W, "bad mode / non-square image");
+  NOPE_CHECK(precision >= 0 && precision <= 2, "precision must be 0..2");
+  NOPE_CHECK(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0, "channels must be multiples of 64");
+  NOPE_CHECK(G == 0 || (gamma && beta), "GroupNorm needs gamma / beta");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Scratch s;
+  const bool sp = precision == 2;
+  const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
+  const int cin = C0 + (x1 ? C1 : 0);
+  const int Hin = mode == 2 ? 2 * H : H;
+  const int hw = H * W;
+  __half *a0 = nullptr, *a0l = nullptr, *a1 = nullptr, *a1l = nullptr, *wp = nullptr, *o = nullptr, *ol = nullptr,
+         *r = nullptr, *rl = nullptr, *pbh = nullptr;
+  if (to_nhwc(x0, &a0, s, n_img, C0, Hin * Hin, st, sp ? &a0l : nullptr)) return -1;
+  if (x1 && to_nhwc(x1, &a1, s, n_img, C1, Hin * Hin, st, sp ? &a1l : nullptr)) return -1;
+  const int n_res = residual ? (res_div > 0 ? (n_img + res_div - 1) / res_div : n_img) : 0;
+  if (residual && to_nhwc(residual, &r, s, n_res, Cout, hw, st, sp ? &rl : nullptr)) return -1;
+  if (chan_bias && to_nhwc(chan_bias, &pbh, s, n_img, Cout, 1, st)) return -1;
+  const int K = cin * taps, Kp = precision >= 1 ? 2 * K : K;
+  if (s.get(&wp, (size_t)Cout * Kp) || s.get(&o, (size_t)n_img * hw * Cout)) return -1;
+  if (sp && s.get(&ol, (size_t)n_img * hw * Cout)) return -1;
+  pack_weight_kernel<<<ew_grid((long long)Cout * K), 256, 0, st>>>(weight, wp, Cout, cin, taps, Kp, 0,
+                                                                    precision >= 1 ? K : 0);
+  NOPE_CUDA(cudaGetLastError());
+  nope_unet eng;
+  eng.conv_impl = 2;
+  eng.precision = precision;
+  eng.n_layers = 1;
+  cudaDeviceProp prop;
+  int dev = 0;
+  NOPE_CUDA(cudaGetDevice(&dev));
+  NOPE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  eng.num_sms = prop.multiProcessorCount;
+  eng.device = dev;
+  if (eng.ensure_workspace(n_img, std::max(n_res, 1))) return -1;
+  if (eng.prepare_stream(st)) return -1;
+  eng.pb = pbh;
+  eng.P = Cout;
+  ConvLayer L;
+  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = K; L.Kp = Kp; L.bn = pick_bn(Cout); L.w = wp; L.id = 0;
+  L.bias = const_cast<float*>(bias);
+  if (make_weight_map(&L.wmap, wp, Cout, Kp, L.bn) || make_weight_map(&L.wmap_half, wp, Cout, Kp, L.bn / 2))
+    return -1;
+  NormLayer N;
+  N.C = Cout; N.G = std::max(G, 1);
+  N.gamma = const_cast<float*>(gamma);
+  N.beta = const_cast<float*>(beta);
+  GnSpec gs;
+  gs.norm = G > 0 ? &N : nullptr;
+  gs.silu = silu != 0;
+  gs.pb_offset = chan_bias ? 0 : -1;
+  if (residual) gs.res = Act(r, Cout, rl);
+  gs.res_div = residual ? res_div : 0;
+  float2* em = nullptr;
+  const int eparts = nope_unet::fused_emit_parts(H, Cout);
+  if (emit_out) {
+    if (s.get(&em, (size_t)n_img * eparts)) return -1;
+    gs.emit = em;
+  }
+  if (eng.conv(L, Act(a0, C0, a0l), x1 ? Act(a1, C1, a1l) : Act(), Act(o, Cout, ol), H, n_img,
+               n_img, st, nullptr, &gs))
+    return -1;
+  if (to_nchw(o, out, n_img, Cout, hw, st, ol)) return -1;
+  if (emit_out) {
+    // fold the per-tile partials on the host side of the test: [n_img][eparts] -> [n_img][2]
+    std::vector<float2> h((size_t)n_img * eparts);
+    NOPE_CUDA(cudaStreamSynchronize(st));
+    NOPE_CUDA(cudaMemcpy(h.data(), em, h.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    std::vector<float> sums((size_t)n_img * 2, 0.f);
+    for (int i = 0; i < n_img; ++i)
+      for (int e2 = 0; e2 < eparts; ++e2) {
+        sums[2 * i] += h[(size_t)i * eparts + e2].x;
+        sums[2 * i + 1] += h[(size_t)i * eparts + e2].y;
+      }
+    NOPE_CUDA(cudaMemcpy(emit_out, sums.data(), sums.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   NOPE_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1201,7 +1561,9 @@ int nope_unet_debug_tap(nope_unet_t* u, const float* ref_feat, const float* pose
   NOPE_CHECK(u && u->finalized && ref_feat && poses && tap && out, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NOPE_CHECK(N <= u->chunk, "debug tap: N must fit one chunk");
+  NOPE_CUDA(cudaSetDevice(u->device));
   if (u->ensure_workspace(N, 1)) return -1;
+  if (u->prepare_stream(st)) return -1;
   u->tap_name = tap;
   u->tap_out = out;
   u->tap_cap = out_capacity_floats;

@@ -55,6 +55,10 @@ class PoseConditional:
         self.u_net.load_state_dict(state_dict, strict=strict)
         return self
 
+    def state_dict(self):
+        """Lightning-style keys: every UNet / encoder entry under `u_net.` (model.py:33-40)."""
+        return {"u_net." + k: v for k, v in self.u_net.state_dict().items()}
+
     # ------------------------------------------------------------------ model.py:96-111
     def compute_loss(self, pred, gt):
         loss = self.loss(pred, gt, reduction="none")
@@ -165,12 +169,14 @@ def topk(sim, k, idx_base=0):
 
 
 def build_model(u_net_dim=192, descriptor_size=8, device="cuda:0", chunk=642,
-                similarity_metric="l2"):
-    """The one configuration the reference resolves: configs/model/template_base.yaml."""
+                similarity_metric="l2", precision="fp16"):
+    """The one configuration the reference resolves: configs/model/template_base.yaml.
+    precision: "fp16" (fast), "fp16_w2" (exact weights) or "parity" (split precision, meets the
+    1e-3 embedding tolerance of the fp32 reference with margin)."""
     from .encoder import FeatureExtractor
     from .unet import UNet
     enc = FeatureExtractor(descriptor_size=descriptor_size, threshold=0.2, normalize=False)
     unet = UNet(u_net_dim=u_net_dim, rot_representation_dim=6, encoder=enc,
-                pose_mlp_name="single_layer", device=device, chunk=chunk)
+                pose_mlp_name="single_layer", device=device, chunk=chunk, precision=precision)
     return PoseConditional(unet, optim_config={"loss_type": "l1"},
                            testing_config={"similarity_metric": similarity_metric}, save_dir=None)

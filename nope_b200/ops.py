@@ -54,6 +54,29 @@ def conv_gn(x0, weight, bias, gamma, beta, groups, silu=True, x1=None, mode="3x3
     return out
 
 
+def conv_gn_fused(x0, weight, bias, gamma=None, beta=None, groups=8, silu=True, x1=None, mode="3x3",
+                  precision=0, chan_bias=None, residual=None, res_div=0, want_emit=False):
+    """The sweep's fused layer on the CTA-pair kernel: [SiLU](GroupNorm(conv(x))) + chan_bias +
+    residual with everything after the convolution in its epilogue (groups=0: no normalisation).
+    precision 0 fp16 / 1 exact weights / 2 split (hi + lo operands).  -> out [, emit [n, 2]]."""
+    lib = _lib.load()
+    m = {"3x3": 0, "1x1": 1, "unshuffle": 2}[mode]
+    x0, x1, weight, bias, gamma, beta, chan_bias, residual = map(
+        _f32, (x0, x1, weight, bias, gamma, beta, chan_bias, residual))
+    n, c0, hin, win = x0.shape
+    h, w = (hin // 2, win // 2) if m == 2 else (hin, win)
+    cout = weight.shape[0]
+    out = torch.empty((n, cout, h, w), device=x0.device, dtype=torch.float32)
+    emit = torch.empty((n, 2), device=x0.device, dtype=torch.float32) if want_emit else None
+    with torch.cuda.device(x0.device):
+        _lib.check(lib.nope_op_conv_gn_fused(
+            m, precision, _lib.ptr(x0), c0, _lib.ptr(x1), 0 if x1 is None else x1.shape[1],
+            _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), groups, 1 if silu else 0,
+            _lib.ptr(chan_bias), _lib.ptr(residual), res_div, _lib.ptr(out), _lib.ptr(emit), n, h, w, cout,
+            _stream(x0.device)))
+    return (out, emit) if want_emit else out
+
+
 def groupnorm(x, gamma, beta, groups, silu=False, chan_bias=None, residual=None):
     lib = _lib.load()
     x, gamma, beta = _f32(x), _f32(gamma), _f32(beta)

@@ -1,0 +1,30 @@
+#!/bin/bash
+# One parameterised GPU script (replaces the round-1 gpu_*.sh collection).  Run under gpurun:
+#   gpurun --timeout 900 -- 'bash tools/gpu.sh <step> [<step> ...]'
+# steps: fused | unet | tests | ldmtests | time | bench | benchall | launches | ncu_conv | ncu_mem | smoke | sanitize
+# Logs land in gpurun_out/ (merged back by gpurun, < 64 MiB).
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > gpurun_out/smi.txt 2>&1
+run() { echo "== $1"; shift; timeout "$@"; echo "rc=$?"; }
+for step in "$@"; do
+case "$step" in
+  fused)    run "fused op tests" 900 python -m pytest tests/test_fused_gpu.py -m gpu -q -x --tb=short > gpurun_out/t_fused.log 2>&1; tail -15 gpurun_out/t_fused.log ;;
+  unet)     run "unet tests" 1500 python -m pytest tests/test_unet_gpu.py -m gpu -q --tb=short > gpurun_out/t_unet.log 2>&1; tail -25 gpurun_out/t_unet.log ;;
+  tests)    rm -f gpurun_out/parity_log.jsonl; run "pytest -m gpu" 2400 python -m pytest tests -m gpu -q -rA --tb=short > gpurun_out/pytest_gpu.log 2>&1; tail -8 gpurun_out/pytest_gpu.log ;;
+  dflt)     rm -f gpurun_out/parity_log.jsonl; run "pytest -m gpu (default path)" 2400 python -m pytest tests -m gpu -q --tb=short --ignore=tests/test_ldm_gpu.py > gpurun_out/pytest_dflt.log 2>&1; tail -25 gpurun_out/pytest_dflt.log ;;
+  ldmtests) run "ldm tests" 1500 python -m pytest tests/test_ldm_gpu.py -m gpu -q --tb=short > gpurun_out/t_ldm.log 2>&1; tail -5 gpurun_out/t_ldm.log ;;
+  time)     run "time_sweep" 900 python tools/time_sweep.py ${TIME_SPECS:-fp16 fp16:fuse_gn=0} --profile > gpurun_out/time_sweep.log 2>&1; cat gpurun_out/time_sweep.log ;;
+  bench)    run "bench" 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log ;;
+  smoke)    run "smoke" 900 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log ;;
+  launches) run "ncu launch list" 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_list.log 2>&1
+            python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launch_summary.txt 2>&1; head -30 gpurun_out/launch_summary.txt ;;
+  ncu_conv) run "ncu full: conv" 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc -c ${NCU_COUNT:-70} -o /tmp/prof_conv -f python tools/profile_step.py > gpurun_out/ncu_conv.log 2>&1
+            ncu -i /tmp/prof_conv.ncu-rep --page raw --csv > gpurun_out/prof_conv_raw.csv 2>/dev/null ;;
+  ncu_mem)  run "ncu full: memory-bound" 900 ncu --profile-from-start off --set full --clock-control none -k regex:'gn_|linattn|final_conv|bcast|midattn|pose_embed|topk' -c 40 -o /tmp/prof_mem -f python tools/profile_step.py > gpurun_out/ncu_mem.log 2>&1
+            ncu -i /tmp/prof_mem.ncu-rep --page raw --csv > gpurun_out/prof_mem_raw.csv 2>/dev/null ;;
+  sanitize) run "memcheck smoke" 1200 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck.log 2>&1; tail -5 gpurun_out/sanitizer_memcheck.log ;;
+  *) echo "unknown step $step" ;;
+esac
+done
+du -sh gpurun_out
