@@ -48,6 +48,15 @@ def parse():
                          "sweep on latents (SURVEY.md 8 f2), an additional line for profiles/")
     ap.add_argument("--conv-impl", default=os.environ.get("NOPE_CONV_IMPL", "tcgen05_2cta"),
                     choices=["tcgen05", "tcgen05_2cta"])
+    ap.add_argument("--precision", default=os.environ.get("NOPE_PRECISION", "fp16"),
+                    choices=["fp16", "fp16_w2", "parity"],
+                    help="engine precision of the headline number (config.precision); the other modes are timed "
+                         "beside it under `modes` at N=1")
+    ap.add_argument("--global-poses", type=int, default=0,
+                    help="strong scaling (BASELINE configs[3]): a FIXED grid of this many poses sharded over the "
+                         "GPUs (10248 = level-3 grid x 4 in-plane rotations); 0 = weak scaling, --poses per GPU")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs (other precision modes, eager-cuDNN baseline, LDM variant)")
     return ap.parse_args()
 
 
@@ -116,11 +125,13 @@ def ncu_traffic():
 
 
 def measured_peaks():
+    """(sustained bf16 TF/s, HBM GB/s, source, burst bf16 TF/s)"""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured"
-    return 1400.0, 6650.0, "fallback"     # B200_PROFILING.md fallback (sustained)
+        return (d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured",
+                d.get("bf16_tflops"))
+    return 1400.0, 6650.0, "fallback", 1590.0     # B200_PROFILING.md fallback (sustained, burst)
 
 
 # ---------------------------------------------------------------------------------------
@@ -169,108 +180,182 @@ def cpu_baseline(seconds=12.0, chunk=16):
                       f"(fastest of a probe), {dt:.1f} s"}
 
 
-def eager_gpu_baseline(dev, chunk=64, reps=3):
+def eager_gpu_baseline(dev, chunks=(64, 128, 256, 642), reps=2):
     """the reference ships no custom kernel, so the on-box GPU baseline is the same
-    module in PyTorch eager (cuDNN/cuBLAS), fp16.  /root/reference does not exist on the GPU box:
-    the oracle's torch restatement of UNet.forward runs on CUDA half tensors instead, batched
-    `chunk` hypotheses per forward.  hyp/s (UNet + l2 score only, no encoder)."""
+    module in PyTorch eager (cuDNN/cuBLAS), fp16, channels_last activations AND weights.
+    /root/reference does not exist on the GPU box: the oracle's torch restatement of UNet.forward runs
+    on CUDA half tensors instead.  The number of hypotheses per forward is swept and the best is
+    reported.  hyp/s (UNet + l2 score only, no encoder)."""
     import torch
     from oracle import unet_oracle as orc, weights
     from nope_b200.poses import synthetic_pose_batch
-    sd = {k: v.to(dev, torch.float16) for k, v in weights.make_unet_state_dict(seed=0).items()}
+    sd = {}
+    for k, v in weights.make_unet_state_dict(seed=0).items():
+        v = v.to(dev, torch.float16)
+        sd[k] = v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v
     g = torch.Generator().manual_seed(0)
     rf = (torch.randn(1, 8, 32, 32, generator=g) * 1.5).to(dev, torch.float16)
     qf = (torch.randn(1, 8, 32, 32, generator=g) * 1.5).to(dev)
     poses, _ = synthetic_pose_batch(N_POSES, 1)
     poses = poses.to(dev, torch.float16)
-    x = rf.expand(chunk, -1, -1, -1).contiguous(memory_format=torch.channels_last)
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    sweep = {}
+    try:
+        for chunk in chunks:
+            x = rf.expand(chunk, -1, -1, -1).contiguous(memory_format=torch.channels_last)
 
-    def run():
-        with torch.no_grad():
-            emb = orc.unet_forward(sd, x, poses[0, :chunk])
-            orc.l2_similarity(qf, emb.float()[None])
-    for _ in range(2):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    return {"value": chunk / (ms * 1e-3), "unit": "hyp/s", "kind": "oracle port, torch-eager CUDA fp16 "
-            "channels_last (cuDNN/cuBLAS)", "sample": f"{chunk} hypotheses per forward, {reps} forwards, "
-            "UNet + l2 score"}
+            def run():
+                with torch.no_grad():
+                    emb = orc.unet_forward(sd, x, poses[0, :chunk])
+                    orc.l2_similarity(qf, emb.float()[None])
+            try:
+                for _ in range(2):
+                    run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+                sweep[chunk] = chunk / (e0.elapsed_time(e1) / reps * 1e-3)
+            except RuntimeError as exc:          # e.g. out of memory at the largest chunk
+                sweep[chunk] = None
+                torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark = prev
+    ok = {c: v for c, v in sweep.items() if v}
+    best = max(ok, key=ok.get)
+    return {"value": ok[best], "unit": "hyp/s", "kind": "oracle port, torch-eager CUDA fp16, channels_last "
+            "activations and weights, cudnn.benchmark (cuDNN/cuBLAS)", "best_chunk": best,
+            "chunk_sweep_hyp_per_s": {str(c): (round(v, 1) if v else None) for c, v in sweep.items()},
+            "sample": f"{reps} forwards per chunk size, UNet + l2 score"}
+
+
+# what each engine precision means for parity with the fp32 reference (measured: tests/test_unet_gpu.py,
+# 642-pose level-2 golden generated by the unmodified reference)
+PRECISION_NOTES = {
+    "fp16": "fp16 operands, fp32 accumulate/statistics; GroupNorm+SiLU fused into the conv epilogue",
+    "fp16_w2": "exact weights: W = W_hi + W_lo fp16 K-segments (2x MMA work), fp16 activations",
+    "parity": "split precision: exact weights + activations as fp16 (hi, lo) pairs, 3 products per tap (3x MMA work)",
+}
+
+
+def workload_config(args, world):
+    """The `config` both arms print: same keys and values, so the driver compares like with like."""
+    strong = args.global_poses > 0
+    n_global = args.global_poses if strong else args.poses * world
+    per = (n_global + world - 1) // world
+    if strong:
+        wl = (f"configs[3]: 256x256, a FIXED {n_global}-pose grid (level-3 icosphere x 4 in-plane rotations when "
+              f"10248) sharded {world}-way, batch={args.queries} query, fp16 UNet (fp32 accumulate / statistics), "
+              "l2 score + top-5")
+    else:
+        wl = (f"configs[1]: 256x256, {args.poses}-pose icosphere grid per GPU, batch={args.queries} query, "
+              "fp16 UNet (fp32 accumulate / statistics), l2 score + top-5")
+    return {"workload": wl, "poses_per_gpu": per, "global_poses": n_global, "queries": args.queries,
+            "chunk": args.chunk, "conv_impl": args.conv_impl,
+            # engine precision of the B200 arm (the reference arm always computes fp32; its `dtype` says so)
+            "precision": f"{args.precision}: {PRECISION_NOTES[args.precision]}",
+            "weights": "seeded random init, reference state_dict schema (305.8 M params)",
+            "l2": "not flushed: each step streams 0.61 GB of fp16 weights and ~1.4 GB of "
+                  "activations per chunk, >> 126 MB L2",
+            "parallelism": f"pose grid sharded {world}-way, one all-gather of packed top-k records" if world > 1 else "1 GPU"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (its
+    unmodified modules when /root/reference is mounted, else the oracle port of them), on the same
+    workload config as our arm.  One step = the two encoder calls + the UNet sweep over a BOUNDED
+    SAMPLE of the grid + scoring; the sample is sized from a probe so that the whole
+    --steps/--warmup run ends within a few minutes.  `value` is the throughput of the FULL grid that
+    these timings imply: N / (t_encoders + N * t_unet_per_hypothesis) -- the encoder calls are paid
+    once per query, not once per sample -- and the raw sample numbers are printed beside it."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 16
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     from oracle import ref_import, unet_oracle as orc, weights
     from nope_b200.poses import synthetic_pose_batch
+    cfg = workload_config(args, world)
+    n_grid = cfg["poses_per_gpu"]                   # the reference has no sharding: one GPU's share of the grid
     poses, _ = synthetic_pose_batch(N_POSES, 1)
     g = torch.Generator().manual_seed(0)
     q = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
     r = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
     sd = weights.make_full_state_dict(seed=0)
+    batch = 16                                      # hypotheses per UNet forward (best-effort CPU batching)
     if ref_import.reference_available():
         kind = "reference"
         model = ref_import.build_reference_model()
         model.u_net.load_state_dict(sd, strict=True)
 
-        def step():
-            # the reference's retrieval path with the grid batched along dim 0 (its own
-            # modules, best-effort CPU: one encoder call per image, UNet at batch `sample`)
+        def encoders():
             with torch.no_grad():
-                qf = model.u_net.encoder.encode_image(q)
-                rf = model.u_net.encoder.encode_image(r)
-                emb = model.u_net(rf.expand(sample, -1, -1, -1), poses[0, :sample])[None]
+                return model.u_net.encoder.encode_image(q), model.u_net.encoder.encode_image(r)
+
+        def sweep(qf, rf, n):
+            # the reference's retrieval path with the grid batched along dim 0 (its own modules)
+            with torch.no_grad():
+                embs = [model.u_net(rf.expand(min(batch, n - s), -1, -1, -1), poses[0, s:min(s + batch, n)])
+                        for s in range(0, n, batch)]
+                emb = torch.cat(embs)[None]
                 d = (qf.unsqueeze(1) - emb) ** 2
-                sim = -torch.norm(d, dim=2).sum(3).sum(2)
-                sim.topk(k=5, dim=1)
+                (-torch.norm(d, dim=2).sum(3).sum(2)).topk(k=min(5, n), dim=1)
     else:
         kind = "port"
         unet_sd = {k: v for k, v in sd.items() if not k.startswith("encoder.")}
         enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
 
-        def step():
+        def encoders():
             with torch.no_grad():
-                qf = orc.encode_image(enc_sd, q)
-                rf = orc.encode_image(enc_sd, r)
-                emb = orc.generate_templates(unet_sd, rf, poses[:, :sample], chunk=sample)
-                orc.topk_lowest_index(orc.l2_similarity(qf, emb), 5)
-    with torch.no_grad():
-        small = poses[0, :4]
-        if kind == "reference":
-            rf0 = torch.randn(4, 8, 32, 32)
-            threads = pick_threads(lambda: model.u_net(rf0, small))
-        else:
-            rf0 = torch.randn(1, 8, 32, 32)
-            threads = pick_threads(lambda: orc.generate_templates(unet_sd, rf0, poses[:, :4], chunk=4))
-    for _ in range(args.warmup):
-        step()
+                return orc.encode_image(enc_sd, q), orc.encode_image(enc_sd, r)
+
+        def sweep(qf, rf, n):
+            with torch.no_grad():
+                emb = orc.generate_templates(unet_sd, rf, poses[:, :n], chunk=batch)
+                orc.topk_lowest_index(orc.l2_similarity(qf, emb), min(5, n))
+    qf, rf = encoders()
+    threads = pick_threads(lambda: sweep(qf, rf, 4))
+    # probe: how many hypotheses fit in the per-step budget?
     t0 = time.time()
+    sweep(qf, rf, batch)
+    t_probe = (time.time() - t0) / batch
+    t0 = time.time()
+    encoders()
+    t_enc_probe = time.time() - t0
+    budget = float(os.environ.get("NOPE_REF_BUDGET_S", "150")) / max(args.steps + args.warmup, 1)
+    sample = int(max(batch, min(n_grid, (budget - t_enc_probe) / max(t_probe, 1e-6))) // batch * batch)
+    sample = max(batch, min(sample, n_grid))
+    for _ in range(args.warmup):
+        sweep(*encoders(), sample)
+    t_enc = t_unet = 0.0
     for _ in range(args.steps):
-        step()
-    dt = (time.time() - t0) / args.steps
-    v = sample / dt
+        t0 = time.time()
+        qf, rf = encoders()
+        t1 = time.time()
+        sweep(qf, rf, sample)
+        t_enc += t1 - t0
+        t_unet += time.time() - t1
+    t_enc /= args.steps
+    t_hyp = t_unet / args.steps / sample
+    full_s = t_enc + n_grid * t_hyp
+    v = n_grid / full_s
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "hyp/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"configs[1]: 256x256, {N_POSES}-pose icosphere grid per GPU, batch=1 query, "
-                               "fp32 reference modules on the host CPU, l2 score + top-5",
-                   "sample": f"each step = a {sample}-pose sample of the grid + 2 encoder calls",
-                   "poses_per_step": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_s * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.global_poses else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": "hyp/s", "cores": threads, "kind": kind,
-                         "sample": f"{sample} poses + 2 encoder calls per step, {threads} of "
-                                   f"{os.cpu_count()} host threads (fastest of a probe)"},
+                         "sample": f"each step = 2 encoder calls ({t_enc * 1e3:.0f} ms) + the UNet sweep and scoring of "
+                                   f"the first {sample} of the {n_grid} poses, {batch} hypotheses per forward "
+                                   f"({t_hyp * 1e3:.1f} ms per hypothesis), fp32, {threads} of {os.cpu_count()} host "
+                                   f"threads (fastest of a probe); value = {n_grid} / (t_enc + {n_grid} t_hyp), the "
+                                   f"full-grid throughput these timings imply (sample alone: "
+                                   f"{sample / (t_enc + sample * t_hyp):.1f} hyp/s)",
+                         "sample_poses": sample, "t_encoders_ms": t_enc * 1e3, "t_per_hypothesis_ms": t_hyp * 1e3},
         "e2e": {"value": v, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -386,7 +471,7 @@ def main_ldm(args):
     step_resident()
     prof = m.profile_read()
     m.profile(False)
-    peak_tf, _, peak_src = measured_peaks()
+    peak_tf, _, peak_src, _ = measured_peaks()
     gm, at = prof["gemm"], prof["attention"]
     gemm_tf = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
     attn_tf = at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0
@@ -470,19 +555,26 @@ def main():
     from nope_b200.dist import ShardedSweep
     from nope_b200.poses import synthetic_pose_batch
 
-    n_local = args.poses
-    n_global = n_local * world
-    model = build_model(device=str(dev), chunk=args.chunk)
-    model.load_state_dict(weights.make_full_state_dict(seed=0)).eval()
+    cfg = workload_config(args, world)
+    strong = args.global_poses > 0
+    n_global = cfg["global_poses"]
+    n_local = cfg["poses_per_gpu"]
+    sd = weights.make_full_state_dict(seed=0)
+    model = build_model(device=str(dev), chunk=args.chunk, precision=args.precision)
+    model.load_state_dict(sd).eval()
     unet = model.u_net
     unet.set_conv_impl(args.conv_impl)
     if world > 1:
         model.dist = ShardedSweep()
 
-    # global grid: one icosphere-642 grid per GPU shard (pose VALUES do not affect timing)
+    # the grid: weak scaling = one icosphere grid per GPU shard (pose VALUES do not affect timing),
+    # strong scaling = ONE fixed grid split contiguously over the ranks (dist.shard_range)
     Q = args.queries
-    poses_g, tposes = synthetic_pose_batch(n_local, Q)
-    poses_g = poses_g.repeat(1, world, 1)           # [Q, n_global, 6]
+    if strong:
+        poses_g, _ = synthetic_pose_batch(n_global, Q)
+    else:
+        poses_g, _ = synthetic_pose_batch(args.poses, Q)
+        poses_g = poses_g.repeat(1, world, 1)       # [Q, n_global, 6]
     g = torch.Generator().manual_seed(0)
     q_img = (torch.rand(Q, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
     r_img = (torch.rand(Q, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
@@ -495,18 +587,24 @@ def main():
     r_feat = unet.encoder.encode_image(r_img.to(dev))
     poses_dev = poses_g.to(dev)
 
-    def step_resident():
-        if world > 1:
-            return model.dist.sweep(unet, r_feat, poses_dev, q_feat, k=5, want_emb=False)
-        out = unet.sweep(r_feat, poses_dev, query_feat=q_feat, want_emb=False, k=5)
-        return out["sim"], out["topi"], None
+    def make_steps(m):
+        u = m.u_net
 
-    def step_e2e():
-        q = q_img.to(dev, non_blocking=True)
-        r = r_img.to(dev, non_blocking=True)
-        p = poses_host.to(dev, non_blocking=True)
-        _, idx, sim = model.predict_pose(q, r, p, None, k=5)
-        return idx.cpu(), sim.cpu()                 # D2H of the step's result
+        def step_resident():
+            if world > 1:
+                return m.dist.sweep(u, r_feat, poses_dev, q_feat, k=5, want_emb=False)
+            out = u.sweep(r_feat, poses_dev, query_feat=q_feat, want_emb=False, k=5)
+            return out["sim"], out["topi"], None
+
+        def step_e2e():
+            q = q_img.to(dev, non_blocking=True)
+            r = r_img.to(dev, non_blocking=True)
+            p = poses_host.to(dev, non_blocking=True)
+            _, idx, sim = m.predict_pose(q, r, p, None, k=5)
+            return idx.cpu(), sim.cpu()             # D2H of the step's result
+        return step_resident, step_e2e
+
+    step_resident, step_e2e = make_steps(model)
 
     def barrier():
         if world > 1:
@@ -541,62 +639,144 @@ def main():
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
 
     # ---- roofline of the dominant kernel (tcgen05 convolution), CUDA events per launch
-    unet.profile(True)
-    step_resident()
-    prof = unet.profile_read()
-    unet.profile(False)
-    peak_tf, peak_hbm, peak_src = measured_peaks()
-    conv_tf = prof["conv_flops"] / (prof["conv_ms"] * 1e-3) / 1e12 if prof["conv_ms"] > 0 else 0.0
+    def conv_profile(u, step):
+        u.profile(True)
+        step()
+        pr = u.profile_read()
+        u.profile(False)
+        return pr
+    prof = conv_profile(unet, step_resident)
+    peak_tf, peak_hbm, peak_src, peak_burst = measured_peaks()
+    conv_s = prof["conv_ms"] * 1e-3
+    conv_tf = prof["conv_alg_flops"] / conv_s / 1e12 if conv_s > 0 else 0.0      # algorithmic
+    conv_exec_tf = prof["conv_flops"] / conv_s / 1e12 if conv_s > 0 else 0.0     # incl. split-precision K-segments
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    n_hyp_step = Q * n_global
+    value = n_hyp_step / (ms * 1e-3)
+    extras = world == 1 and not args.no_extras
+
+    # ---- the other precision modes, same workload, resident timing (config.precision names the headline)
+    modes = {args.precision: {"value": value, "ms_per_step": ms, "e2e": n_hyp_step / (ms_e2e * 1e-3),
+                              "conv_algorithmic_tflops": conv_tf, "conv_executed_tflops": conv_exec_tf}}
+    if extras:
+        del model, unet
+        torch.cuda.empty_cache()
+        for mode in ("fp16", "fp16_w2", "parity"):
+            if mode in modes:
+                continue
+            try:
+                m2 = build_model(device=str(dev), chunk=args.chunk, precision=mode)
+                m2.load_state_dict(sd).eval()
+                sr, se = make_steps(m2)
+                ms2 = timed(sr, max(3, args.steps // 2), 3)
+                ms2e = timed(se, max(3, args.steps // 2), 3)
+                p2 = conv_profile(m2.u_net, sr)
+                modes[mode] = {"value": n_hyp_step / (ms2 * 1e-3), "ms_per_step": ms2,
+                               "e2e": n_hyp_step / (ms2e * 1e-3),
+                               "conv_algorithmic_tflops": p2["conv_alg_flops"] / (p2["conv_ms"] * 1e-3) / 1e12,
+                               "conv_executed_tflops": p2["conv_flops"] / (p2["conv_ms"] * 1e-3) / 1e12}
+                del m2
+                torch.cuda.empty_cache()
+            except Exception as exc:                  # informational leg only
+                modes[mode] = {"unavailable": repr(exc)[:200]}
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()
     eager = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and extras:
         try:
             eager = eager_gpu_baseline(dev)
         except Exception as exc:                      # informational leg only
             eager = {"unavailable": repr(exc)[:200]}
-    value = Q * n_global / (ms * 1e-3)
+    variants = None
+    if extras and not args.no_cpu_baseline:
+        try:
+            variants = {"ldm": ldm_summary(args, dev)}
+        except Exception as exc:
+            variants = {"ldm": {"unavailable": repr(exc)[:200]}}
     line = {
         "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-        "config": {
-            "workload": f"configs[1]: 256x256, {n_local}-pose icosphere grid per GPU, batch={Q} query, "
-                        "fp16 UNet (fp32 accumulate / statistics), l2 score + top-5",
-            "poses_per_gpu": n_local, "global_poses": n_global, "queries": Q, "chunk": args.chunk,
-            "conv_impl": args.conv_impl,
-            "weights": "seeded random init, reference state_dict schema (305.8 M params)",
-            "l2": "not flushed: each step streams 0.61 GB of fp16 weights and ~1.4 GB of "
-                  "activations per chunk, >> 126 MB L2",
-            "parallelism": f"pose grid sharded {world}-way, all-gather of top-k" if world > 1 else "1 GPU",
-        },
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": cfg,
         "clocks": clocks,
-        "e2e": {"value": Q * n_global / (ms_e2e * 1e-3), "unit": "hyp/s", "ms_per_step": ms_e2e,
+        "e2e": {"value": n_hyp_step / (ms_e2e * 1e-3), "unit": "hyp/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "PoseConditional.predict_pose (pinned host images -> encoder x2 -> sweep -> top-5 -> host)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {
-            "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)",
+            "bound": "tensor", "kernel": "conv_tc2_kernel (tcgen05 implicit-GEMM conv, CTA pairs; GroupNorm / SiLU / "
+                                         "pose bias / residual in its epilogue)",
             "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": conv_tf / peak_tf if peak_tf else None, "peak_source": f"{peak_src} (sustained bf16 cuBLAS)",
+            "peak_burst": peak_burst, "frac_of_burst": conv_tf / peak_burst if peak_burst else None,
+            "executed_tflops": conv_exec_tf,
             "traffic": ncu_traffic(), "traffic_source": "profiles/roofline_traffic.json (ncu --set full, "
             "dram__bytes_read.sum + dram__bytes_write.sum per launch, sweep convolutions)",
             "launches_per_step": prof["conv_launches"],
             "conv_ms_per_step": prof["conv_ms"], "conv_share_of_step": prof["conv_ms"] / ms if ms else None,
-            "algorithmic_tflop_per_step": prof["conv_flops"] / 1e12,
+            "algorithmic_tflop_per_step": prof["conv_alg_flops"] / 1e12,
             "best_single_launch_tflops": prof["max_launch_tflops"],
             "whole_step_tflops": value * GFLOP_PER_HYP / 1e3,
+            "whole_step_frac": value * GFLOP_PER_HYP / 1e3 / peak_tf if peak_tf else None,
         },
+        "modes": modes,
         "cpu_baseline": cpu,
         "eager_gpu_baseline": eager,
+        "variants": variants,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ldm_summary(args, dev):
+    """One short resident timing of the LDM variant for the default line's `variants`:
+    the full line (e2e, clocks, cpu baseline) is `bench.py --variant ldm`."""
+    import torch
+    from nope_b200.ldm import UNetModelPose
+    from nope_b200.poses import synthetic_pose_batch
+    from nope_b200.synth_weights import ldm_flops_per_hyp, make_ldm_state_dict
+    m = UNetModelPose(device=str(dev), chunk=min(args.chunk, 642))
+    m.load_state_dict(make_ldm_state_dict(seed=0))
+    poses, _ = synthetic_pose_batch(N_POSES, 1)
+    g = torch.Generator().manual_seed(0)
+    ref = torch.randn(1, 4, 32, 32, generator=g).to(dev)
+    qry = torch.randn(1, 4, 32, 32, generator=g).to(dev)
+    poses = poses.to(dev)
+    run = lambda: m.sweep(ref, poses, qry, want_emb=False, k=5)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    m.profile(True)
+    run()
+    prof = m.profile_read()
+    m.profile(False)
+    peak_tf, _, peak_src, peak_burst = measured_peaks()
+    gm, at = prof["gemm"], prof["attention"]
+    gemm_tf = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+    fl = ldm_flops_per_hyp()
+    out = {"workload": f"UNetModelPose (vae_cin_ldm.yaml) on 4x32x32 latents, {N_POSES}-pose grid, batch=1",
+           "value": N_POSES / (ms * 1e-3), "unit": "hyp/s", "ms_per_step": ms, "gflop_per_hyp": fl["total"] / 1e9,
+           "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel", "achieved": gemm_tf, "peak": peak_tf,
+                        "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None,
+                        "frac_of_burst": gemm_tf / peak_burst if peak_burst else None,
+                        "gemm_share_of_step": gm["ms"] / ms,
+                        "attention_tflops": at["flops"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] > 0 else 0.0,
+                        "attention_share_of_step": at["ms"] / ms},
+           "full_line": "python bench.py --variant ldm"}
+    del m
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

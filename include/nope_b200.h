@@ -32,6 +32,11 @@ typedef struct nope_unet nope_unet_t;
 
 #define NOPE_METRIC_L2 0      /* reference "l2": -(sum_hw sqrt(sum_c (q-t)^4)), model.py:260-262 */
 #define NOPE_METRIC_COSINE 1  /* extension: cosine of flattened descriptors (not in the reference) */
+/* extension: occlusion-aware cosine -- the per-pixel cosine over channels (the encoder's
+ * `sim_distance = nn.CosineSimilarity(dim=1)`, src/model/encoder/template.py:45) with similarities <=
+ * threshold set to zero (`OcclusionAwareSimilarity`, src/model/encoder/base_template.py:67-75; threshold
+ * 0.2 in configs/model/template_base.yaml), averaged over the 32x32 pixels */
+#define NOPE_METRIC_COSINE_OCC 2
 
 /* Thread-local message of the last failing call on this thread. */
 const char* nope_last_error(void);
@@ -106,6 +111,10 @@ int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, i
                     const float* query_feat, float* out_emb, float* out_sim, int k,
                     float* out_topv, int64_t* out_topi, int64_t idx_base, void* stream);
 
+/* Similarity metric of the scoring fused onto the sweep's last layer (NOPE_METRIC_*; default l2, the only
+ * one the reference implements, model.py:254-266).  occlusion_threshold is used by NOPE_METRIC_COSINE_OCC. */
+int nope_unet_set_metric(nope_unet_t* u, int metric, float occlusion_threshold);
+
 /* Number of kernels the last nope_unet_sweep call enqueued (for bench.py's gpu_launches). */
 int64_t nope_unet_last_launch_count(const nope_unet_t* u);
 
@@ -141,12 +150,24 @@ int64_t nope_encoder_last_launch_count(const nope_encoder_t* e);
  * PoseConditional.retrieval (model.py:254-266) after encode_image.
  *   query_feat [B, C, HW] fp32, emb [B, N, C, HW] fp32 -> sim [B, N], topv/topi [B, k]. */
 int nope_score_topk(const float* query_feat, const float* emb, int B, int N, int C, int HW,
-                    int metric, int k, float* out_sim, float* out_topv, int64_t* out_topi,
-                    int64_t idx_base, void* stream);
+                    int metric, float occlusion_threshold, int k, float* out_sim, float* out_topv,
+                    int64_t* out_topi, int64_t idx_base, void* stream);
 
 /* Rank an existing similarity matrix sim [B, N] (used to merge per-GPU shards). */
 int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_topi,
               int64_t idx_base, void* stream);
+
+/* Multi-GPU merge: each rank sweeps a contiguous slice of the pose grid and contributes
+ * ONE packed record to a single all-gather:
+ *   [ topv: B*k f32 | 1 pad float if B*k is odd | topi: B*k int64 (GLOBAL indices, -1 = padding) |
+ *     similarity slice: B * n_local f32 (optional) ]
+ * nope_topk_pack_floats gives the record length in floats (n_local_max = ceil(N / world)).
+ * nope_topk_merge turns the `world` gathered records (each pack_floats long) into the global top-k
+ * per batch row (descending, ties -> lowest index; identical on every rank) and, when has_sim, the
+ * full similarity rows [B, N].  Rank r owns poses [r*per, min(N, (r+1)*per)). */
+int64_t nope_topk_pack_floats(int B, int k, int n_local_max, int want_sim);
+int nope_topk_merge(const float* gathered, int world, int64_t pack_floats, int B, int k, int N, int per,
+                    int has_sim, float* out_sim, float* out_topv, int64_t* out_topi, void* stream);
 
 /* ---- per-op entry points (parity tests drive single layers through these) -----------
  * All tensors fp32 NCHW device pointers; conversion to the internal NHWC fp16 layout

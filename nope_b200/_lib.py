@@ -40,9 +40,13 @@ SIGNATURES = {
     "nope_encoder_finalize": (C.c_int, [C.c_void_p]),
     "nope_encoder_encode": (C.c_int, [C.c_void_p, c_f32p, C.c_int, c_f32p, C.c_void_p]),
     "nope_encoder_last_launch_count": (C.c_int64, [C.c_void_p]),
-    "nope_score_topk": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "nope_score_topk": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                   C.c_int, c_f32p, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
+    "nope_unet_set_metric": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "nope_topk": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_i64p, C.c_int64, C.c_void_p]),
+    "nope_topk_pack_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nope_topk_merge": (C.c_int, [c_f32p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  c_f32p, c_f32p, c_i64p, C.c_void_p]),
     "nope_op_conv": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, c_f32p, c_f32p,
                                c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nope_op_conv_gn": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, c_f32p, c_f32p,

@@ -50,7 +50,9 @@ struct ConvSeg {
 // (Block.forward / ResnetBlock.forward, model_utils.py:237-253, 271-279; PreNorm / to_out[1] of
 // LinearAttention, model_utils.py:230, 401).  The statistics of an image are spread over the CTA
 // tiles that hold its pixels (and, for groups wider than one tile, its channels): every such tile
-// publishes its partial sums, then waits for the `expected` tiles of its sync group (all resident:
+// publishes its partial sums as {value, epoch} words (8-byte stores: value and tag arrive together,
+// the low-latency flag protocol of NCCL's LL mode -- no fences, no atomics), then polls the
+// `expected` slots of its sync group until all carry this launch's epoch (all tiles are resident:
 // the kernel is persistent with one CTA per SM).  Partials are combined in slot order, so results
 // do not depend on launch size or timing.
 struct GnFuse {
@@ -72,14 +74,16 @@ struct GnFuse {
   int has_res;           // residual tile arrives through ConvParams::rmap (TMA) into the output staging
   int res_div, res_base; // res_div > 0: residual image index = (res_base + img) / res_div (hoisted prefix)
   int n_img;             // valid images
-  float2* xpart;         // [sync group][slot][ipt * gpt] partial (sum, sum of squares)
-  unsigned* xcnt;        // [sync group] arrival counters, monotone (+expected per launch), private per layer
+  uint2* xpart;          // [sync group][slot][ipt * gpt][2]: {sum, epoch}, {sum of squares, epoch}
+  unsigned epoch;        // tag of this launch (unique per launch on the buffer, never 0)
   float2* emit;          // optional: GroupNorm(1, C) partial sums of the stored output,
   int emit_parts;        //   emit[img * emit_parts + (m_in_img * n_tiles + n_tile)], emit_parts = mt * n_tiles
   // split precision (activations carried as fp16 hi + lo): remainder of the output, [pixel][n_total],
   // and of the residual (same layout; the residual image mapping of res_div applies)
   __half* out_lo;
   const __half* res_lo;
+  int dbg;               // development knobs (NOPE_GN_DBG): 1 skip the poll, 2 skip SiLU, 4 skip pass 2 math
+  unsigned long long* ts;  // development: per (CTA, tile iteration) phase timestamps [grid][64][8] (globaltimer, ns)
 };
 
 struct ConvParams {

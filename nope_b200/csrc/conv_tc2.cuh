@@ -122,25 +122,26 @@ struct Conv2Smem {
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBufs * kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
   // EPI == 3 (GroupNorm fused): gamma | beta (fp32 [BN] each) | pose bias (fp16 [8][BN]) |
-  // segment partial sums (fp32 [8][BN/8][2]) | (mean, rstd) [64] | octet -> group table [BN/8] | emit scratch
+  // segment partial sums (fp32 [8][BN/8][2]) | (mean, rstd) [64] | octet -> group table [BN/8] | emit scratch |
+  // gathered cross-CTA partials (fp32 [256])
   static constexpr int kGnOffset = kBiasOffset + BN * 4;
-  static constexpr int kGnBytes = EPI == 3 ? (2 * BN * 4 + 8 * BN * 2 + 8 * (BN / 8) * 8 + 64 * 8 + (BN / 8) * 4 + 16 * 8) : 0;
+  static constexpr int kGnBytes = EPI == 3 ? (2 * BN * 4 + 8 * BN * 2 + 8 * (BN / 8) * 8 + 64 * 8 + (BN / 8) * 4 + 32 * 8 + 256 * 4) : 0;
   static constexpr int kTotal = kGnOffset + kGnBytes + 1024;
 };
 
-// ld / st that bypass L1 (cross-CTA partial sums live in L2)
-__device__ __forceinline__ float2 ld_cg_f2(const float2* p) {
-  float2 r;
-  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// 8-byte {value, tag} words of the cross-CTA partial-sum exchange: single-copy atomic, L2-coherent
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
   return r;
 }
-__device__ __forceinline__ void st_cg_f2(float2* p, float2 v) {
-  asm volatile("st.global.cg.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
-  unsigned r;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
-  return r;
+__device__ __forceinline__ void st_volatile_u2(uint2* p, uint2 v) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -155,12 +156,42 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 //      (skipped when the tile holds whole images and whole groups);
 //   4. normalise, activate, add pose bias / residual in place in the swizzled staging buffer, TMA-store.
 // ---------------------------------------------------------------------------------------------
+// read-only shared-memory tables of pass 2: plain (non-volatile, no memory clobber) asm loads, so the
+// compiler may hoist them above the in-place stores to the staging tile (same shared array: it must
+// otherwise assume they alias and serialises every 8-channel octet).  `tok` is produced by a volatile asm
+// after the barrier that publishes the tables, which keeps the loads below that barrier.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 r;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 r;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint32_t order_token(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v) : "memory");
+  return r;
+}
+
+__host__ __device__ constexpr int gn_epi_warps(int BN) { return 4 * (BN / 64); }           // one (lane quarter, 64-column sub-tile) each
+__host__ __device__ constexpr int gn_threads(int BN) { return 128 + 32 * gn_epi_warps(BN); }
+
 template <int BN, int STAGES>
 __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8_t* smem, uint32_t tmem_base,
                                                       uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar,
                                                       int tile0, int tile_step, int num_tiles, uint32_t rank) {
   using S = Conv2Smem<BN, STAGES, 3>;
   constexpr int kOct = BN / 8;
+  constexpr int kNS = BN / 64;                       // 64-column sub-tiles
+  constexpr int kEpiThreads = 32 * gn_epi_warps(BN);
   uint8_t* out_stage = smem + STAGES * S::kStageBytes;
   float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
   float* s_gamma = reinterpret_cast<float*>(smem + S::kGnOffset);
@@ -169,12 +200,13 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
   float* s_part = reinterpret_cast<float*>(s_pb + 8 * BN);               // [8 segs][kOct][2]
   float2* s_mr = reinterpret_cast<float2*>(s_part + 8 * kOct * 2);       // [ipt * gpt] (mean, rstd)
   int* s_og = reinterpret_cast<int*>(s_mr + 64);                         // [kOct] octet -> group in tile
-  float2* s_em = reinterpret_cast<float2*>(s_og + kOct);                 // [2][8] emit scratch
+  float2* s_em = reinterpret_cast<float2*>(s_og + kOct);                 // [4][8] emit scratch
+  float* s_x = reinterpret_cast<float*>(s_em + 32);                      // [expected][npairs][2] gathered partials
 
   const GnFuse& g = p.gn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = warp - 4, etid = threadIdx.x - 128;
-  const int q = e & 3, hh = e >> 2;
+  const int q = e & 3, cc = e >> 2;                  // TMEM lane quarter, 64-column sub-tile of this warp
   const int row = q * 32 + lane;
   const bool leader = rank == 0;
   const int hw = p.stats_hw;
@@ -182,10 +214,14 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
   const int it = hw < kBM ? (row >> g.hw_shift) : 0;    // image of this thread's row inside the tile
   const int npairs = g.ipt * g.gpt;
   if (etid < kOct) s_og[etid] = (g.G > 0 && g.cpg < BN) ? (etid * 8) / g.cpg : 0;
+#define NOPE_EPI_BAR() asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory")
 
   int acc = 0, obuf = 0;
   uint32_t acc_phase = 0, res_phase = 0;
-  for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+  int iter = 0;
+#define NOPE_TS(k) do { if (g.ts && etid == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 8 + (k)] = global_ns(); } while (0)
+  for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
+    NOPE_TS(0);
     const int m_pair = tile / p.n_tiles;
     const int n_tile = tile - m_pair * p.n_tiles;
     const int m_tile = 2 * m_pair + (int)rank;
@@ -202,11 +238,11 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         const int rb = g.res_div > 0 ? (g.res_base + b0) / g.res_div : b0;
         mbar_expect_tx(res_bar, S::kOutBytes);
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 64; ++cc)
-          tma_load_4d(ost + cc * (kBM * 128), &p.rmap, res_bar, n_chan0 + cc * 64, 0, y0, rb);
+        for (int c2 = 0; c2 < kNS; ++c2)
+          tma_load_4d(ost + c2 * (kBM * 128), &p.rmap, res_bar, n_chan0 + c2 * 64, 0, y0, rb);
       }
     }
-    if (etid < BN) {
+    if (etid < BN && (tile == tile0 || p.n_tiles > 1)) {     // channel parameters of this N-tile
       s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
       if (g.G > 0) {
         s_gamma[etid] = __ldg(g.gamma + n_chan0 + etid);
@@ -214,7 +250,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
       }
     }
     if (g.pb) {
-      for (int i = etid; i < g.ipt * kOct; i += 256) {
+      for (int i = etid; i < g.ipt * kOct; i += kEpiThreads) {
         const int ii = i / kOct, o8 = i - ii * kOct;
         const int img = img0 + ii;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -223,16 +259,18 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         *reinterpret_cast<uint4*>(s_pb + ii * BN + o8 * 8) = v;
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    NOPE_EPI_BAR();
+    NOPE_TS(1);
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
+    NOPE_TS(2);
 
     // ---- pass 1: TMEM -> registers, free the accumulator, per-octet partial sums
-    uint32_t a[BN / 64][32];
+    uint32_t a[64];
     {
-      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + hh * 32;
-#pragma unroll
-      for (int cc = 0; cc < BN / 64; ++cc) tmem_ld_32x32(t_row + cc * 64, a[cc]);
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + cc * 64;
+      tmem_ld_32x32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
+      tmem_ld_32x32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -243,7 +281,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
     }
     if (live) {
 #pragma unroll
-      for (int cc = 0; cc < BN / 64; ++cc) {
+      for (int hh = 0; hh < 2; ++hh) {
         const float* bs = s_bias + cc * 64 + hh * 32;
         float st[8];
 #pragma unroll
@@ -254,8 +292,8 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            f[i] = __uint_as_float(a[cc][j * 8 + i]) + bb[i];
-            a[cc][j * 8 + i] = __float_as_uint(f[i]);
+            f[i] = __uint_as_float(a[hh * 32 + j * 8 + i]) + bb[i];
+            a[hh * 32 + j * 8 + i] = __float_as_uint(f[i]);
           }
           float sm = (f[0] + f[1]) + (f[2] + f[3]) + ((f[4] + f[5]) + (f[6] + f[7]));
           float q2 = f[0] * f[0];
@@ -272,7 +310,8 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         }
       }
       if (g.G > 0) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        NOPE_EPI_BAR();
+        NOPE_TS(3);
         float Sx = 0.f, Qx = 0.f;
         if (etid < npairs) {
           const int ii = etid / g.gpt, gl = etid - ii * g.gpt;
@@ -287,34 +326,36 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
             }
         }
         if (g.expected > 1) {
-          // publish, then wait for the other tiles of this (image, group-set)
+          // publish {value, epoch}; then one thread per word of the sync group's [slot][pair][2] block polls
+          // until its word carries this launch's epoch (every poll of the CTA in flight at once)
           const int sg = (m_tile / g.mt) * (p.n_tiles / g.tpg) + n_tile / g.tpg;
           const int slot = (m_tile % g.mt) * g.tpg + (n_tile % g.tpg);
-          float2* xp = g.xpart + (size_t)sg * g.expected * npairs;
-          if (etid < npairs) st_cg_f2(xp + slot * npairs + etid, make_float2(Sx, Qx));
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (etid == 0) {
-            __threadfence();
-            const unsigned old = atomicAdd(g.xcnt + sg, 1u);
-            const unsigned target = (old / (unsigned)g.expected + 1u) * (unsigned)g.expected;
-            if ((int)(ld_volatile_u32(g.xcnt + sg) - target) < 0) {
+          uint2* xp = g.xpart + (size_t)sg * g.expected * npairs * 2;
+          if (etid < npairs) {
+            st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2, make_uint2(__float_as_uint(Sx), g.epoch));
+            st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2 + 1, make_uint2(__float_as_uint(Qx), g.epoch));
+          }
+          if (etid < g.expected * npairs * 2) {
+            uint2 u = ld_volatile_u2(xp + etid);
+            if (u.y != g.epoch && !(g.dbg & 1)) {
               const long long t0 = clock64();
-              while ((int)(ld_volatile_u32(g.xcnt + sg) - target) < 0) {
+              do {
+                u = ld_volatile_u2(xp + etid);
                 if (clock64() - t0 > 4000000000LL) {
                   printf("nope_b200: GroupNorm tile sync timed out (block %d tile %d)\n", (int)blockIdx.x, tile);
                   __trap();
                 }
-              }
+              } while (u.y != g.epoch);
             }
-            __threadfence();
+            s_x[etid] = __uint_as_float(u.x);
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (etid < npairs) {
+          NOPE_EPI_BAR();
+          NOPE_TS(4);
+          if (etid < npairs) {           // fixed slot order
             Sx = 0.f; Qx = 0.f;
             for (int sl = 0; sl < g.expected; ++sl) {
-              const float2 t = ld_cg_f2(xp + sl * npairs + etid);
-              Sx += t.x;
-              Qx += t.y;
+              Sx += s_x[(sl * npairs + etid) * 2];
+              Qx += s_x[(sl * npairs + etid) * 2 + 1];
             }
           }
         }
@@ -323,101 +364,102 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
           const float var = fmaxf(Qx * g.inv_cnt - mean * mean, 0.f);
           s_mr[etid] = make_float2(mean, rsqrtf(var + g.eps));
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        NOPE_EPI_BAR();
       }
 
       // ---- pass 2: normalise / activate / add, in place in the swizzled staging tile
+      NOPE_TS(5);
       if (g.has_res) mbar_wait(res_bar, res_phase);
       float e1 = 0.f, e2 = 0.f;
-      const float2* mrp = s_mr + it * g.gpt;
-      const __half* pbp = s_pb + it * BN;
+      const uint32_t tok = order_token(smem_u32(smem));          // tables below are read after the barrier above
+      const uint32_t a_gamma = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_gamma) - smem) + cc * 256;
+      const uint32_t a_beta = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_beta) - smem) + cc * 256;
+      const uint32_t a_pb = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_pb) - smem) + (it * BN + cc * 64) * 2;
+      const uint32_t a_mr = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_mr) - smem) + it * g.gpt * 8;
       const int grow = m_tile * kBM + row;            // linear output pixel
       const bool row_ok = grow < p.m_valid;
       // residual pixel under the hoisted-prefix image mapping (32x32 images: one image per tile)
       const long long rpix = g.res_div > 0
           ? (long long)((g.res_base + b0) / g.res_div) * hw + (m_tile % g.mt) * kBM + row
           : (long long)grow;
+      uint8_t* srow = ost + cc * (kBM * 128) + row * 128;
+      const bool do_norm = g.G > 0 && !(g.dbg & 4);
+      const bool do_silu = g.silu && !(g.dbg & 2);
 #pragma unroll
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        uint8_t* srow = ost + cc * (kBM * 128) + row * 128;
+      for (int j = 0; j < 8; ++j) {
+        const int lc = cc * 64 + j * 8;
+        uint4* sp = reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4));
+        float f[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int lc = cc * 64 + hh * 32 + j * 8;
-          uint4* sp = reinterpret_cast<uint4*>(srow + (((hh * 4 + j) ^ (row & 7)) << 4));
-          float f[8];
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(a[j * 8 + i]);
+        if (do_norm) {
+          const float2 mr = lds_f2(a_mr + s_og[lc >> 3] * 8);
+          const float4 g0 = lds_f4(a_gamma + j * 32), g1 = lds_f4(a_gamma + j * 32 + 16);
+          const float4 h0 = lds_f4(a_beta + j * 32), h1 = lds_f4(a_beta + j * 32 + 16);
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bt[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(a[cc][j * 8 + i]);
-          if (g.G > 0) {
-            const float2 mr = mrp[s_og[lc >> 3]];
-            const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + lc);
-            const float4 g1 = *reinterpret_cast<const float4*>(s_gamma + lc + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(s_beta + lc);
-            const float4 h1 = *reinterpret_cast<const float4*>(s_beta + lc + 4);
-            const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float bt[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] - mr.x, mr.y * gm[i], bt[i]);
+        }
+        if (do_silu) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] - mr.x, mr.y * gm[i], bt[i]);
+          for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
+        }
+        if (g.pb) {
+          const uint4 pv = lds_u4(a_pb + j * 16);
+          const __half2* hp = reinterpret_cast<const __half2*>(&pv);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const float2 t = __half22float2(hp[k2]);
+            f[2 * k2] += t.x;
+            f[2 * k2 + 1] += t.y;
           }
-          if (g.silu) {
+        }
+        if (g.has_res) {
+          const uint4 rv = *sp;
+          const __half2* hr = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const float2 t = __half22float2(hr[k2]);
+            f[2 * k2] += t.x;
+            f[2 * k2 + 1] += t.y;
           }
-          if (g.pb) {
-            const uint4 pv = *reinterpret_cast<const uint4*>(pbp + lc);
-            const __half2* hp = reinterpret_cast<const __half2*>(&pv);
+          if (g.res_lo && row_ok) {
+            const uint4 rl = *reinterpret_cast<const uint4*>(g.res_lo + rpix * p.n_total + n_chan0 + lc);
+            const __half2* hl = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
             for (int k2 = 0; k2 < 4; ++k2) {
-              const float2 t = __half22float2(hp[k2]);
+              const float2 t = __half22float2(hl[k2]);
               f[2 * k2] += t.x;
               f[2 * k2 + 1] += t.y;
             }
           }
-          if (g.has_res) {
-            const uint4 rv = *sp;
-            const __half2* hr = reinterpret_cast<const __half2*>(&rv);
+        }
+        uint4 w;
+        w.x = pack_half2(f[0], f[1]);
+        w.y = pack_half2(f[2], f[3]);
+        w.z = pack_half2(f[4], f[5]);
+        w.w = pack_half2(f[6], f[7]);
+        *sp = w;
+        if (g.out_lo && row_ok) {
+          const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+          uint4 wl;
+          uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
 #pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const float2 t = __half22float2(hr[k2]);
-              f[2 * k2] += t.x;
-              f[2 * k2 + 1] += t.y;
-            }
-            if (g.res_lo && row_ok) {
-              const uint4 rl = *reinterpret_cast<const uint4*>(g.res_lo + rpix * p.n_total + n_chan0 + lc);
-              const __half2* hl = reinterpret_cast<const __half2*>(&rl);
-#pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const float2 t = __half22float2(hl[k2]);
-                f[2 * k2] += t.x;
-                f[2 * k2 + 1] += t.y;
-              }
-            }
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const float2 t = __half22float2(hw2[k2]);
+            pl[k2] = pack_half2(f[2 * k2] - t.x, f[2 * k2 + 1] - t.y);
           }
-          uint4 w;
-          w.x = pack_half2(f[0], f[1]);
-          w.y = pack_half2(f[2], f[3]);
-          w.z = pack_half2(f[4], f[5]);
-          w.w = pack_half2(f[6], f[7]);
-          *sp = w;
-          if (g.out_lo && row_ok) {
-            const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
-            uint4 wl;
-            uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
+          *reinterpret_cast<uint4*>(g.out_lo + (size_t)grow * p.n_total + n_chan0 + lc) = wl;
+        }
+        if (g.emit) {       // statistics of the values as stored (what the consumer reads)
+          const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
 #pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const float2 t = __half22float2(hw2[k2]);
-              pl[k2] = pack_half2(f[2 * k2] - t.x, f[2 * k2 + 1] - t.y);
-            }
-            *reinterpret_cast<uint4*>(g.out_lo + (size_t)grow * p.n_total + n_chan0 + lc) = wl;
-          }
-          if (g.emit) {       // statistics of the values as stored (what the consumer reads)
-            const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const float2 t = __half22float2(hw2[k2]);
-              e1 += t.x + t.y;
-              e2 = fmaf(t.x, t.x, e2);
-              e2 = fmaf(t.y, t.y, e2);
-            }
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const float2 t = __half22float2(hw2[k2]);
+            e1 += t.x + t.y;
+            e2 = fmaf(t.x, t.x, e2);
+            e2 = fmaf(t.y, t.y, e2);
           }
         }
       }
@@ -429,12 +471,12 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
           e1 += __shfl_xor_sync(0xffffffffu, e1, off);
           e2 += __shfl_xor_sync(0xffffffffu, e2, off);
         }
-        if ((lane & 15) == 0) s_em[hh * 8 + (row >> 4)] = make_float2(e1, e2);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if ((lane & 15) == 0) s_em[cc * 8 + (row >> 4)] = make_float2(e1, e2);
+        NOPE_EPI_BAR();
         if (etid < g.ipt && img0 + etid < g.n_img) {
           const int r16 = hw >= kBM ? 8 : (hw >> 4);
           float s1 = 0.f, s2 = 0.f;
-          for (int h2 = 0; h2 < 2; ++h2)
+          for (int h2 = 0; h2 < kNS; ++h2)
             for (int r = etid * r16; r < (etid + 1) * r16; ++r) {
               s1 += s_em[h2 * 8 + r].x;
               s2 += s_em[h2 * 8 + r].y;
@@ -443,11 +485,12 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         }
       }
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      NOPE_EPI_BAR();
+      NOPE_TS(6);
       if (etid == 0) {
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 64; ++cc)
-          tma_store_4d(&p.omap[0], ost + cc * (kBM * 128), n_chan0 + cc * 64, 0, y0, b0);
+        for (int c2 = 0; c2 < kNS; ++c2)
+          tma_store_4d(&p.omap[0], ost + c2 * (kBM * 128), n_chan0 + c2 * 64, 0, y0, b0);
         tma_store_commit();
       }
     }
@@ -456,11 +499,13 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
     if (acc == 0) acc_phase ^= 1;
   }
   if (etid == 0) tma_store_wait_all();
+#undef NOPE_TS
+#undef NOPE_EPI_BAR
 }
 
 // EPI: 0 = plain epilogue (the sweep), 1 = extras (ReLU / residual / hi-lo / fp32), 2 = GEGLU
 template <int BN, int STAGES, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI == 3 ? gn_threads(BN) : kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   using S = Conv2Smem<BN, STAGES, EPI>;
   constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -498,7 +543,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 2 * kEpiWarps);
+      mbar_init(&tempty_bar[a], 2 * (EPI == 3 ? gn_epi_warps(BN) : kEpiWarps));
     }
     mbar_init(res_bar, 1);
     fence_mbar_init();
@@ -670,7 +715,7 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof cfg);
       cfg.gridDim = dim3(num_sms, 1, 1);
-      cfg.blockDim = dim3(kConvThreads, 1, 1);
+      cfg.blockDim = dim3(EPI == 3 ? gn_threads(BN) : kConvThreads, 1, 1);
       cfg.dynamicSmemBytes = S::kTotal;
       cudaLaunchAttribute at;
       at.id = cudaLaunchAttributeClusterDimension;
@@ -687,7 +732,7 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = max_clusters_of[dev];
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
-  conv_tc2_kernel<BN, STAGES, EPI><<<2 * clusters, kConvThreads, S::kTotal, stream>>>(p);
+  conv_tc2_kernel<BN, STAGES, EPI><<<2 * clusters, EPI == 3 ? gn_threads(BN) : kConvThreads, S::kTotal, stream>>>(p);
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -740,15 +740,26 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 // ----------------------------------------------------------------------------
 constexpr int kFinalThreads = 128;
 constexpr int kMaxLatent = 8;
+constexpr int kScoreParts = 3;     // partial sums per (hypothesis, pixel slab): metric-dependent
+// Similarity metrics (include/nope_b200.h): 0 the reference's "l2" (model.py:260-262); 1 cosine of the
+// flattened C*H*W descriptors (extension, F.cosine_similarity semantics, eps 1e-8); 2 occlusion-aware
+// cosine: the per-pixel cosine over channels (the encoder's `sim_distance = nn.CosineSimilarity(dim=1)`,
+// template.py:45) with similarities <= threshold zeroed (`OcclusionAwareSimilarity`,
+// base_template.py:67-75), averaged over the pixels.
+__device__ __forceinline__ float finish_score(int metric, float a, float b, float c, int hw) {
+  if (metric == 0) return -a;
+  if (metric == 1) return a / (fmaxf(sqrtf(b), 1e-8f) * fmaxf(sqrtf(c), 1e-8f));
+  return a / (float)hw;
+}
 
 __global__ void __launch_bounds__(kFinalThreads)
 final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ w,
                         const float* __restrict__ bias, float* __restrict__ emb,
                         const float* __restrict__ query, const int* __restrict__ ref_of,
                         float* __restrict__ partial, int hw, int C, int Cl,
-                        const __half* __restrict__ x_lo = nullptr) {
+                        const __half* __restrict__ x_lo = nullptr, int metric = 0, float occ_thr = 0.f) {
   extern __shared__ float s_w[];  // [Cl][C]
-  __shared__ float s_part[kFinalThreads / 32];
+  __shared__ float s_part[kScoreParts][kFinalThreads / 32];
   const int slab = blockIdx.x, h = blockIdx.y, nslab = gridDim.x;
   for (int i = threadIdx.x; i < Cl * C; i += kFinalThreads) s_w[i] = w[i];
   __syncthreads();
@@ -756,7 +767,7 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
   float acc[kMaxLatent];
 #pragma unroll
   for (int c = 0; c < kMaxLatent; ++c) acc[c] = (c < Cl) ? bias[c] : 0.f;
-  float dist = 0.f;
+  float dist = 0.f, d1 = 0.f, d2 = 0.f;      // metric-dependent partial sums of this pixel
   if (p < hw) {
     const __half* xp = x + ((long long)h * hw + p) * C;
     const __half* xl = x_lo ? x_lo + ((long long)h * hw + p) * C : nullptr;
@@ -794,26 +805,45 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
     }
     if (query) {
       const float* qp = query + (long long)ref_of[h] * Cl * hw + p;
-      float s4 = 0.f;
+      float s4 = 0.f, qe = 0.f, qq = 0.f, ee = 0.f;
 #pragma unroll
       for (int c = 0; c < kMaxLatent; ++c)
         if (c < Cl) {
-          const float d = qp[(long long)c * hw] - acc[c];
-          const float d2 = d * d;
-          s4 = fmaf(d2, d2, s4);
+          const float qv = qp[(long long)c * hw];
+          const float d = qv - acc[c];
+          const float dd = d * d;
+          s4 = fmaf(dd, dd, s4);
+          qe = fmaf(qv, acc[c], qe);
+          qq = fmaf(qv, qv, qq);
+          ee = fmaf(acc[c], acc[c], ee);
         }
-      dist = sqrtf(s4);
+      if (metric == 0) {                 // reference "l2" (model.py:260-262)
+        dist = sqrtf(s4);
+      } else if (metric == 1) {          // cosine of the flattened descriptors: three global sums
+        dist = qe; d1 = qq; d2 = ee;
+      } else {                           // per-pixel cosine over channels, occlusion threshold
+        const float sc = qe / (fmaxf(sqrtf(qq), 1e-8f) * fmaxf(sqrtf(ee), 1e-8f));
+        dist = sc > occ_thr ? sc : 0.f;
+      }
     }
   }
   if (partial) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dist;
+    for (int o = 16; o > 0; o >>= 1) {
+      dist += __shfl_xor_sync(0xffffffffu, dist, o);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_part[0][threadIdx.x >> 5] = dist;
+      s_part[1][threadIdx.x >> 5] = d1;
+      s_part[2][threadIdx.x >> 5] = d2;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < kScoreParts) {
       float t = 0.f;
-      for (int i = 0; i < kFinalThreads / 32; ++i) t += s_part[i];
-      partial[(long long)h * nslab + slab] = t;
+      for (int i = 0; i < kFinalThreads / 32; ++i) t += s_part[threadIdx.x][i];
+      partial[((long long)h * nslab + slab) * kScoreParts + threadIdx.x] = t;
     }
   }
 }
@@ -824,7 +854,7 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
 // One CTA per (b, n).
 __global__ void __launch_bounds__(256)
 score_kernel(const float* __restrict__ query, const float* __restrict__ emb,
-             float* __restrict__ sim, int N, int Cl, int hw, int metric) {
+             float* __restrict__ sim, int N, int Cl, int hw, int metric, float occ_thr) {
   __shared__ float s_a[8], s_b[8], s_c[8];
   const int n = blockIdx.x, b = blockIdx.y;
   const float* e = emb + ((long long)b * N + n) * Cl * hw;
@@ -839,13 +869,23 @@ score_kernel(const float* __restrict__ query, const float* __restrict__ emb,
         s4 = fmaf(d2, d2, s4);
       }
       a0 += sqrtf(s4);
-    } else {
+    } else if (metric == 1) {
       for (int c = 0; c < Cl; ++c) {
         const float x = q[c * hw + p], y = e[c * hw + p];
         a0 = fmaf(x, y, a0);
         a1 = fmaf(x, x, a1);
         a2 = fmaf(y, y, a2);
       }
+    } else {
+      float qe = 0.f, qq = 0.f, ee = 0.f;
+      for (int c = 0; c < Cl; ++c) {
+        const float x = q[c * hw + p], y = e[c * hw + p];
+        qe = fmaf(x, y, qe);
+        qq = fmaf(x, x, qq);
+        ee = fmaf(y, y, ee);
+      }
+      const float sc = qe / (fmaxf(sqrtf(qq), 1e-8f) * fmaxf(sqrtf(ee), 1e-8f));
+      a0 += sc > occ_thr ? sc : 0.f;
     }
   }
 #pragma unroll
@@ -863,10 +903,7 @@ score_kernel(const float* __restrict__ query, const float* __restrict__ emb,
   if (threadIdx.x == 0) {
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t0 += s_a[i]; t1 += s_b[i]; t2 += s_c[i]; }
-    if (metric == 0)
-      sim[(long long)b * N + n] = -t0;
-    else
-      sim[(long long)b * N + n] = t0 / (fmaxf(sqrtf(t1), 1e-8f) * fmaxf(sqrtf(t2), 1e-8f));
+    sim[(long long)b * N + n] = finish_score(metric, t0, t1, t2, hw);
   }
 }
 
@@ -878,7 +915,7 @@ score_kernel(const float* __restrict__ query, const float* __restrict__ emb,
 __global__ void __launch_bounds__(256)
 sim_topk_kernel(const float* __restrict__ partial, int nslab, float* __restrict__ sim, int N,
                 int k, float* __restrict__ top_val, long long* __restrict__ top_idx,
-                long long idx_base) {
+                long long idx_base, int nparts = 1, int metric = 0, int hw = 1) {
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   __shared__ int s_chosen[64];
@@ -886,9 +923,10 @@ sim_topk_kernel(const float* __restrict__ partial, int nslab, float* __restrict_
   float* srow = sim + (long long)b * N;
   if (partial) {
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-      float t = 0.f;
-      for (int s = 0; s < nslab; ++s) t += partial[((long long)b * N + n) * nslab + s];
-      srow[n] = -t;
+      float t[3] = {0.f, 0.f, 0.f};
+      for (int s = 0; s < nslab; ++s)
+        for (int q = 0; q < nparts; ++q) t[q] += partial[(((long long)b * N + n) * nslab + s) * nparts + q];
+      srow[n] = finish_score(metric, t[0], t[1], t[2], hw);
     }
     __syncthreads();
   }
@@ -928,6 +966,58 @@ sim_topk_kernel(const float* __restrict__ partial, int nslab, float* __restrict_
       top_idx[(long long)b * k + r] = (bi == 0x7fffffff) ? -1 : (long long)bi + idx_base;
     }
     __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Multi-GPU merge: every rank contributes ONE packed record to a single all-gather,
+//   [ topv: B*k f32 | pad to even | topi: B*k i64 | sim slice: B*n_local f32 (optional) ]      (`pack` floats)
+// with GLOBAL pose indices (idx -1 = padding).  This kernel turns the W gathered records into the
+// global top-k per batch row (descending score, ties -> lowest index: deterministic, identical on
+// every rank) and the full similarity rows.  One CTA per batch row; candidates W*k <= 1024.
+// rank r owns poses [r*per, min(N, (r+1)*per)).
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ gathered, int world, long long pack, int B, int k, int N, int per,
+                  int has_sim, float* __restrict__ out_sim, float* __restrict__ top_val,
+                  long long* __restrict__ top_idx) {
+  __shared__ float s_v[1024];
+  __shared__ long long s_i[1024];
+  const int b = blockIdx.x;
+  const int kk = (B * k + 1) & ~1;                    // floats before the index block (8-byte aligned)
+  const int ncand = world * k;
+  for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+    const int r = c / k, j = c - r * k;
+    const float* rec = gathered + (long long)r * pack;
+    const long long idx = reinterpret_cast<const long long*>(rec + kk)[b * k + j];
+    s_i[c] = idx;
+    s_v[c] = idx < 0 ? -INFINITY : rec[b * k + j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+    const float v = s_v[c];
+    const long long i = s_i[c];
+    if (i < 0) continue;
+    int rank = 0;                                     // candidates that beat this one
+    for (int o = 0; o < ncand; ++o) {
+      const long long io = s_i[o];
+      if (io < 0 || o == c) continue;
+      const float vo = s_v[o];
+      rank += (vo > v || (vo == v && io < i)) ? 1 : 0;
+    }
+    if (rank < k) {
+      top_val[(long long)b * k + rank] = v;
+      top_idx[(long long)b * k + rank] = i;
+    }
+  }
+  // fewer than k valid candidates (N < k cannot happen: the callers clamp k): nothing to pad
+  if (has_sim && out_sim) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const int r = n / per, j = n - r * per;
+      const int lo = r * per, hi = min(N, lo + per);
+      const float* rec = gathered + (long long)r * pack + kk + 2 * B * k;
+      out_sim[(long long)b * N + n] = rec[(long long)b * (hi - lo) + j];
+    }
   }
 }
 

@@ -7,6 +7,8 @@
 #include "../../include/nope_b200.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -42,7 +44,6 @@ struct ConvLayer {
   CUtensorMap wmap;
   CUtensorMap wmap_half;  // BN/2-row box for the 2-CTA kernel
   bool has_map = false;
-  int id = -1;            // index of the layer's private tile-sync counters (fused GroupNorm)
 };
 
 struct NormLayer {
@@ -93,6 +94,8 @@ struct nope_unet {
   // 0: fp16 operands; 1: exact weights (W_hi + W_lo K-segments, 2x the MMA work); 2: split precision
   // (exact weights + activations carried as hi + lo: A_hi W_hi + A_hi W_lo + A_lo W_hi, 3x)
   int precision = 0;
+  int metric = 0;            // NOPE_METRIC_* of the fused scoring
+  float occ_threshold = 0.2f;
   int chunk = 642;
   int64_t launches = 0;
 
@@ -103,7 +106,6 @@ struct nope_unet {
   std::map<std::string, NormLayer> norms;
   std::map<std::string, int> pb_off;
   int P = 0;  // total pose-projection width
-  int n_layers = 0;
   ConvLayer poseproj;
   float *pose_w = nullptr, *pose_b = nullptr, *init_w = nullptr, *init_b = nullptr,
         *final_w = nullptr, *final_b = nullptr;
@@ -122,9 +124,9 @@ struct nope_unet {
   __half* pt = nullptr;
   float2* gn_partial = nullptr;   // gn_stats_kernel output (per-op test path only)
   float2 *SA = nullptr, *SB = nullptr;   // unfused statistics: conv epilogue / gn_apply emit; SB also fused emit
-  float2* xpart = nullptr;        // fused GroupNorm: cross-tile partial sums
-  unsigned* xcnt = nullptr;       // fused GroupNorm: per-layer arrival counters [n_layers][xcnt_per_layer]
-  size_t xcnt_per_layer = 0, xcnt_total = 0;
+  uint2* xpart = nullptr;         // fused GroupNorm: cross-tile partial sums, {value, epoch} words
+  size_t xpart_words = 0;
+  unsigned gn_epoch = 0;          // tag of the last fused launch that exchanged partial sums
   int* ref_of = nullptr;
   float* score_partial = nullptr;
   float* sim_buf = nullptr;
@@ -283,7 +285,6 @@ struct nope_unet {
     if (make_weight_map(&L.wmap, L.w, rows, L.Kp, L.bn)) return -1;
     if (make_weight_map(&L.wmap_half, L.w, rows, L.Kp, L.bn / 2)) return -1;
     L.has_map = true;
-    L.id = n_layers++;
     convs[name] = L;
     return 0;
   }
@@ -427,15 +428,11 @@ struct nope_unet {
     b.take(&ref_of, m);
     b.take(&SA, m * ((size_t)S0 * S0 * dim / 256));   // (hw/32) x (C/8) at the top level
     b.take(&SB, m * 8);
-    b.take(&xpart, (m + 8) * 64);
-    const size_t per_layer = m * 8, cnt_total = per_layer * (size_t)std::max(n_layers, 1);
-    if (b.base) {
-      xcnt_per_layer = per_layer;
-      xcnt_total = cnt_total;
-    }
-    b.take(&xcnt, cnt_total);
+    // <= 64 (slot, image, group) entries of two {value, epoch} words per image
+    if (b.base) xpart_words = (m + 8) * 64 * 2;
+    b.take(&xpart, (m + 8) * 64 * 2);
     const int nslab = (S0 * S0 + kFinalThreads - 1) / kFinalThreads;
-    b.take(&score_partial, (size_t)n_total_scores * nslab);
+    b.take(&score_partial, (size_t)n_total_scores * nslab * kScoreParts);
     b.take(&sim_buf, (size_t)n_total_scores);
     return b.off;
   }
@@ -478,10 +475,10 @@ struct nope_unet {
     ws_external = true;
     return adopt(c, r, sc);
   }
-  // the tile-sync counters start at zero (and stay multiples of `expected` between launches)
+  // the tile-sync words of a fresh slab carry epoch 0, which no launch uses
   int prepare_stream(cudaStream_t st) {
     if (ws_fresh) {
-      NOPE_CUDA(cudaMemsetAsync(xcnt, 0, xcnt_total * sizeof(unsigned), st));
+      NOPE_CUDA(cudaMemsetAsync(xpart, 0, xpart_words * sizeof(uint2), st));
       ws_fresh = false;
     }
     return 0;
@@ -673,25 +670,56 @@ struct nope_unet {
       f.res_div = gs->res_div;
       f.res_base = gs->res_base;
       f.out_lo = out.lo;
+      static const int dbg = std::getenv("NOPE_GN_DBG") ? std::atoi(std::getenv("NOPE_GN_DBG")) : 0;
+      f.dbg = dbg;
       f.emit = gs->emit;
       f.emit_parts = f.mt * p.n_tiles;
       NOPE_CHECK(f.ipt * f.gpt <= 64 && f.ipt <= 8, "fused GroupNorm: tile holds too many (image, group) pairs");
       if (f.expected > 1) {
         const size_t n_sg = (size_t)(p.m_tiles / f.mt + 1) * (p.n_tiles / f.tpg);
-        NOPE_CHECK(L.id >= 0 && L.id < std::max(n_layers, 1) && n_sg <= xcnt_per_layer && xpart && xcnt,
-                   "fused GroupNorm: workspace for the tile sync is missing");
-        NOPE_CHECK(n_sg * f.expected * f.ipt * f.gpt <= (size_t)std::max(cap, cap_ref) * 64 + 64 * 8,
-                   "fused GroupNorm: partial-sum buffer too small");
+        NOPE_CHECK(xpart && f.expected * f.ipt * f.gpt * 2 <= 256, "fused GroupNorm: sync group too large");
+        NOPE_CHECK(n_sg * f.expected * f.ipt * f.gpt * 2 <= xpart_words, "fused GroupNorm: partial-sum buffer too small");
         f.xpart = xpart;
-        f.xcnt = xcnt + (size_t)L.id * xcnt_per_layer;
+        if (++gn_epoch == 0) ++gn_epoch;     // 0 is the tag of a fresh buffer
+        f.epoch = gn_epoch;
       }
     } else if (out.lo) {
       p.out_lo = out.lo;                // extras epilogue writes the remainder
+    }
+    // development: NOPE_GN_TS=<k> records phase timestamps of the k-th fused launch into NOPE_GN_TS_FILE
+    unsigned long long* ts_dev = nullptr;
+    if (gs) {
+      static const int ts_k = std::getenv("NOPE_GN_TS") ? std::atoi(std::getenv("NOPE_GN_TS")) : -1;
+      static int ts_count = 0;
+      if (ts_k >= 0 && ts_count++ == ts_k) {
+        cudaMalloc(reinterpret_cast<void**>(&ts_dev), (size_t)num_sms * 64 * 8 * sizeof(unsigned long long));
+        cudaMemset(ts_dev, 0, (size_t)num_sms * 64 * 8 * sizeof(unsigned long long));
+        p.gn.ts = ts_dev;
+      }
     }
     auto launch = [&]() {
       if (gs) return launch_conv_gn(p, L.bn, num_sms, st);
       return conv_impl == 2 ? launch_conv_tc2(p, L.bn, num_sms, st) : launch_conv_tc(p, L.bn, num_sms, st);
     };
+    if (ts_dev) {
+      const int rc = launch();
+      cudaDeviceSynchronize();
+      std::vector<unsigned long long> h((size_t)num_sms * 64 * 8);
+      cudaMemcpy(h.data(), ts_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      cudaFree(ts_dev);
+      if (FILE* f = std::fopen(std::getenv("NOPE_GN_TS_FILE") ? std::getenv("NOPE_GN_TS_FILE") : "gn_ts.csv", "w")) {
+        std::fprintf(f, "# So=%d n_img=%d cout=%d K=%d expected=%d m_tiles=%d n_tiles=%d\n", So, n_img, L.cout, L.K,
+                     p.gn.expected, p.m_tiles, p.n_tiles);
+        for (int c = 0; c < num_sms; ++c)
+          for (int it = 0; it < 64; ++it) {
+            const unsigned long long* r = &h[((size_t)c * 64 + it) * 8];
+            if (r[0] == 0) continue;
+            std::fprintf(f, "%d,%d,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c, it, r[0], r[1], r[2], r[3], r[4], r[5], r[6]);
+          }
+        std::fclose(f);
+      }
+      return rc;
+    }
     if (!profile) return launch();
     cudaEvent_t e0, e1;
     NOPE_CUDA(cudaEventCreate(&e0));
@@ -986,7 +1014,8 @@ struct nope_unet {
     const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
     final_conv_score_kernel<<<dim3(nslab, n), kFinalThreads, (size_t)Cl * dim * sizeof(float), st>>>(
         curb.hi, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat, ref_of,
-        score_part ? score_part + (size_t)hyp0 * nslab : nullptr, hw, dim, Cl, sp ? curb.lo : nullptr);
+        score_part ? score_part + (size_t)hyp0 * nslab * kScoreParts : nullptr, hw, dim, Cl, sp ? curb.lo : nullptr,
+        metric, occ_threshold);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     return 0;
@@ -1172,6 +1201,17 @@ int nope_unet_profile_read(nope_unet_t* u, double* conv_ms, double* conv_flops, 
     alg += u->prof_alg[i];
     if (t > 0.f) best = std::max(best, u->prof_flops[i] / (t * 1e-3) / 1e12);
   }
+  if (const char* path = std::getenv("NOPE_PROF_DUMP")) {     // development aid: per-launch table
+    if (FILE* f = std::fopen(path, "a")) {
+      std::fprintf(f, "# launch,ms,executed_gflop,algorithmic_gflop\n");
+      for (size_t i = 0; i < u->prof_flops.size(); ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, u->prof_ev[2 * i], u->prof_ev[2 * i + 1]);
+        std::fprintf(f, "%zu,%.4f,%.3f,%.3f\n", i, t, u->prof_flops[i] / 1e9, u->prof_alg[i] / 1e9);
+      }
+      std::fclose(f);
+    }
+  }
   *conv_ms = ms;
   *conv_flops = fl;
   if (conv_alg_flops) *conv_alg_flops = alg;
@@ -1208,23 +1248,33 @@ int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, i
   if (query_feat && (out_sim || k > 0)) {
     float* sim = out_sim ? out_sim : u->sim_buf;
     sim_topk_kernel<<<B, 256, 0, st>>>(part, nslab, sim, N, k, out_topv,
-                                       reinterpret_cast<long long*>(out_topi), (long long)idx_base);
+                                       reinterpret_cast<long long*>(out_topi), (long long)idx_base,
+                                       kScoreParts, u->metric, hw);
     NOPE_CUDA(cudaGetLastError());
     ++u->launches;
   }
   return 0;
 }
 
+int nope_unet_set_metric(nope_unet_t* u, int metric, float occlusion_threshold) {
+  NOPE_CHECK(u, "null engine");
+  NOPE_CHECK(metric == NOPE_METRIC_L2 || metric == NOPE_METRIC_COSINE || metric == NOPE_METRIC_COSINE_OCC,
+             "unknown similarity metric (l2, cosine and cosine_occlusion exist)");
+  u->metric = metric;
+  u->occ_threshold = occlusion_threshold;
+  return 0;
+}
+
 int nope_score_topk(const float* query_feat, const float* emb, int B, int N, int C, int HW, int metric,
-                    int k, float* out_sim, float* out_topv, int64_t* out_topi, int64_t idx_base,
-                    void* stream) {
+                    float occlusion_threshold, int k, float* out_sim, float* out_topv, int64_t* out_topi,
+                    int64_t idx_base, void* stream) {
   NOPE_CHECK(query_feat && emb && out_sim, "null argument");
-  NOPE_CHECK(metric == NOPE_METRIC_L2 || metric == NOPE_METRIC_COSINE,
-             "unknown similarity metric (only l2 and cosine exist)");
+  NOPE_CHECK(metric == NOPE_METRIC_L2 || metric == NOPE_METRIC_COSINE || metric == NOPE_METRIC_COSINE_OCC,
+             "unknown similarity metric (l2, cosine and cosine_occlusion exist)");
   NOPE_CHECK(k >= 0 && k <= N && k <= 64, "k must be in [0, min(N, 64)]");
   NOPE_CHECK(k == 0 || (out_topv && out_topi), "top-k outputs missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  score_kernel<<<dim3(N, B), 256, 0, st>>>(query_feat, emb, out_sim, N, C, HW, metric);
+  score_kernel<<<dim3(N, B), 256, 0, st>>>(query_feat, emb, out_sim, N, C, HW, metric, occlusion_threshold);
   NOPE_CUDA(cudaGetLastError());
   if (k > 0) {
     sim_topk_kernel<<<B, 256, 0, st>>>(nullptr, 0, out_sim, N, k, out_topv,
@@ -1240,6 +1290,26 @@ int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_top
   NOPE_CHECK(k >= 1 && k <= N && k <= 64, "k must be in [1, min(N, 64)]");
   sim_topk_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       nullptr, 0, sim, N, k, out_topv, reinterpret_cast<long long*>(out_topi), (long long)idx_base);
+  NOPE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t nope_topk_pack_floats(int B, int k, int n_local_max, int want_sim) {
+  if (B < 1 || k < 1 || n_local_max < 0) return -1;
+  const int64_t kk = ((int64_t)B * k + 1) & ~(int64_t)1;
+  return kk + 2 * (int64_t)B * k + (want_sim ? (int64_t)B * n_local_max : 0);
+}
+
+int nope_topk_merge(const float* gathered, int world, int64_t pack_floats, int B, int k, int N, int per,
+                    int has_sim, float* out_sim, float* out_topv, int64_t* out_topi, void* stream) {
+  NOPE_CHECK(gathered && out_topv && out_topi, "null argument");
+  NOPE_CHECK(world >= 1 && B >= 1 && k >= 1 && k <= N && world * k <= 1024, "bad merge geometry (world * k <= 1024)");
+  NOPE_CHECK(per >= 1 && (int64_t)per * world >= N, "per-rank pose count does not cover the grid");
+  NOPE_CHECK(pack_floats >= nope_topk_pack_floats(B, k, has_sim ? per : 0, has_sim), "packed record too short");
+  NOPE_CHECK(!has_sim || out_sim, "similarity output missing");
+  topk_merge_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gathered, world, (long long)pack_floats, B, k, N, per, has_sim, out_sim, out_topv,
+      reinterpret_cast<long long*>(out_topi));
   NOPE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1438,7 +1508,6 @@ int nope_op_conv_gn_fused(int mode, int precision, const float* x0, int C0, cons
   nope_unet eng;
   eng.conv_impl = 2;
   eng.precision = precision;
-  eng.n_layers = 1;
   cudaDeviceProp prop;
   int dev = 0;
   NOPE_CUDA(cudaGetDevice(&dev));
@@ -1450,7 +1519,7 @@ int nope_op_conv_gn_fused(int mode, int precision, const float* x0, int C0, cons
   eng.pb = pbh;
   eng.P = Cout;
   ConvLayer L;
-  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = K; L.Kp = Kp; L.bn = pick_bn(Cout); L.w = wp; L.id = 0;
+  L.mode = mode; L.cin = cin; L.cout = Cout; L.K = K; L.Kp = Kp; L.bn = pick_bn(Cout); L.w = wp;
   L.bias = const_cast<float*>(bias);
   if (make_weight_map(&L.wmap, wp, Cout, Kp, L.bn) || make_weight_map(&L.wmap_half, wp, Cout, Kp, L.bn / 2))
     return -1;

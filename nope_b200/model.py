@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import _lib
 
-_METRICS = {"l2": 0, "cosine": 1}
+_METRICS = {"l2": 0, "cosine": 1, "cosine_occlusion": 2}     # NOPE_METRIC_* of include/nope_b200.h
 
 
 def _ns(d):
@@ -37,6 +37,10 @@ class PoseConditional:
         loss_type = getattr(self.optim_config, "loss_type", "l1")
         self.loss = F.l1_loss if loss_type == "l1" else F.mse_loss
         self.dist = None     # optional nope_b200.dist.ShardedSweep for multi-GPU
+        from .metrics import GeodesicError
+        self.metric = GeodesicError()              # model.py:56
+        self.logged = {}                           # what Lightning's self.log would have received
+        self.global_step, self.global_rank = 0, 0
 
     @property
     def device(self):
@@ -91,9 +95,14 @@ class PoseConditional:
     def retrieval(self, query, template_feat, k=5):
         metric = getattr(self.testing_config, "similarity_metric", "l2")
         if metric not in _METRICS:
-            raise ValueError(f"unknown similarity_metric {metric!r} (supported: l2, cosine)")
+            raise ValueError(f"unknown similarity_metric {metric!r} (supported: {sorted(_METRICS)})")
         query_feat = self.u_net.encoder.encode_image(query, mode="mode")
-        return score_topk(query_feat, template_feat, k=k, metric=metric)
+        return score_topk(query_feat, template_feat, k=k, metric=metric, threshold=self._occlusion_threshold())
+
+    def _occlusion_threshold(self):
+        """`threshold` of the template encoder (OcclusionAwareSimilarity, base_template.py:67-75;
+        configs/model/template_base.yaml: 0.2)."""
+        return float(getattr(self.u_net.encoder, "threshold", 0.2))
 
     # ------------------------------------------------------------------ model.py:313-357
     @torch.no_grad()
@@ -104,8 +113,9 @@ class PoseConditional:
         only materialised when asked for."""
         metric = getattr(self.testing_config, "similarity_metric", "l2")
         if metric not in _METRICS:
-            raise ValueError(f"unknown similarity_metric {metric!r} (supported: l2, cosine)")
+            raise ValueError(f"unknown similarity_metric {metric!r} (supported: {sorted(_METRICS)})")
         enc = self.u_net.encoder
+        self.u_net.set_metric(metric, self._occlusion_threshold())     # scored in the sweep's last layer
         B = query.shape[0]
         feats = enc.encode_image(torch.cat([query.to(self.device), reference.to(self.device)]))
         query_feat, reference_feat = feats[:B], feats[B:]
@@ -113,28 +123,73 @@ class PoseConditional:
         k = min(k, N)
         if self.dist is not None:
             sim, topi, emb = self.dist.sweep(self.u_net, reference_feat, all_relativeR, query_feat,
-                                             k=k, metric=metric, want_emb=return_templates)
-        elif metric == "l2":
+                                             k=k, metric=metric, want_emb=return_templates,
+                                             threshold=self._occlusion_threshold())
+        else:
             out = self.u_net.sweep(reference_feat, all_relativeR, query_feat=query_feat,
                                    want_emb=return_templates, k=k)
             sim, topi, emb = out["sim"], out["topi"], out["emb"]
-        else:
-            emb = self.u_net.sweep(reference_feat, all_relativeR, want_emb=True)["emb"]
-            sim, topi = score_topk(query_feat, emb, k=k, metric=metric)
         R = None
         if template_poses is not None:
             tp = template_poses[0] if template_poses.dim() == 4 else template_poses
             R = tp.to(topi.device)[topi]          # model.py:352-354
         if return_templates:
+            # under sharding `emb` is (local templates, lo, hi): each rank keeps only its slice
             return R, topi, sim, emb
         return R, topi, sim
 
 
-def score_topk(query_feat, template_feat, k=5, metric="l2", idx_base=0):
+    # ------------------------------------------------------------------ model.py:185-191, 268-376, 550-565
+    def log(self, name, value, **kwargs):
+        self.logged.setdefault(name, []).append(float(value))
+
+    def log_score(self, dict_scores, split_name):
+        for key, value in dict_scores.items():
+            self.log(f"{key}/{split_name}", value, sync_dist=True)
+
+    @torch.no_grad()
+    def eval_geodesic(self, batch, data_name, visualize=False, save_prediction=False):
+        """`eval_geodesic` of the reference without the wandb / image logging (the template encoder has
+        no decoder, so the reference itself sets visualize=False on this path, model.py:269-274):
+        validation loss under the ground-truth pose, template sweep + retrieval, geodesic accuracy."""
+        query, reference = batch["query"], batch["reference"]
+        loss = self.forward(query=query, relativeR=batch["gt_relativeR"], reference=reference)
+        self.log(f"loss/val_{data_name}", loss)
+        template_poses = batch["template_poses"][0]
+        predR, nearest_idx, similarity = self.predict_pose(query, reference, batch["all_relativeR"],
+                                                           template_poses, k=5)
+        error, acc = self.metric(predR=predR, gtR=batch["query_pose"].to(predR.device),
+                                 symmetry=batch["symmetry"].reshape(-1).to(predR.device))
+        self.log_score(acc, split_name=f"val_{data_name}")
+        if save_prediction and self.save_dir is not None:
+            import os
+            import numpy as np
+            os.makedirs(os.path.join(self.save_dir, "predictions"), exist_ok=True)
+            np.savez(os.path.join(self.save_dir, "predictions",
+                                  f"pred_{data_name}_step{self.global_step}_rank{self.global_rank}"),
+                     query_pose=batch["query_pose"].cpu().numpy(), similarity=similarity.cpu().numpy(),
+                     nearest_idx=nearest_idx.cpu().numpy())
+        return error, nearest_idx, similarity
+
+    def test_step(self, batch, idx_batch):
+        """model.py:550-565: one entry per dataloader, keyed "<dataset>_<category>"."""
+        out = {}
+        for dataloader_name in batch.keys():
+            data_name, category = dataloader_name.split("_")
+            if data_name in ["tless"]:
+                raise ValueError("the T-LESS / VSD evaluation (eval_vsd, pyrender) is outside this package's "
+                                 "scope (SURVEY.md section 2): only shapeNet_<category> dataloaders are handled")
+            out[dataloader_name] = self.eval_geodesic(batch[dataloader_name], category, visualize=True,
+                                                      save_prediction=True)
+        self.global_step += 1
+        return out
+
+
+def score_topk(query_feat, template_feat, k=5, metric="l2", idx_base=0, threshold=0.2):
     """similarity [B,N] and nearest_idx [B,k] of materialised templates
     (the arithmetic of model.py:260-265) on the GPU."""
     if metric not in _METRICS:
-        raise ValueError(f"unknown similarity_metric {metric!r} (supported: l2, cosine)")
+        raise ValueError(f"unknown similarity_metric {metric!r} (supported: {sorted(_METRICS)})")
     lib = _lib.load()
     dev = template_feat.device
     if dev.type != "cuda":
@@ -149,7 +204,7 @@ def score_topk(query_feat, template_feat, k=5, metric="l2", idx_base=0):
     topv = torch.empty((B, k), device=dev, dtype=torch.float32)
     topi = torch.empty((B, k), device=dev, dtype=torch.int64)
     with torch.cuda.device(dev):
-        _lib.check(lib.nope_score_topk(_lib.ptr(q), _lib.ptr(t), B, N, Cc, hw, _METRICS[metric], k,
+        _lib.check(lib.nope_score_topk(_lib.ptr(q), _lib.ptr(t), B, N, Cc, hw, _METRICS[metric], float(threshold), k,
                                        _lib.ptr(sim), _lib.ptr(topv), _lib.ptr(topi), idx_base,
                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return sim, topi

@@ -63,13 +63,28 @@ def icosphere_object_rotations(level, upper_only=False):
     return np.stack(Rs)
 
 
+def inplane_expand(R, n_inplane):
+    """Every grid rotation combined with `n_inplane` in-plane rotations (about the camera's optical
+    axis, z): [N,3,3] -> [N * n_inplane, 3,3], in-plane index fastest.  BASELINE configs[3]'s "10k
+    hypotheses" = the level-3 grid (2562 viewpoints) x 4 in-plane rotations = 10248 (SURVEY.md 8d)."""
+    out = []
+    for a in range(n_inplane):
+        t = 2.0 * np.pi * a / n_inplane
+        Rz = np.array([[np.cos(t), -np.sin(t), 0.0], [np.sin(t), np.cos(t), 0.0], [0.0, 0.0, 1.0]])
+        out.append(Rz[None] @ R)
+    return np.stack(out, axis=1).reshape(-1, 3, 3)
+
+
 def synthetic_pose_batch(n_poses, batch, seed=0):
     """[B,N,6] relative rotations for benchmarking: icosphere grids for the sizes the
-    reference ships (42/162/642/2562/10242), seeded random rotations otherwise."""
+    reference ships (42/162/642/2562/10242), the level-3 grid x 4 in-plane rotations for 10248,
+    seeded random rotations otherwise."""
     sizes = {42: 0, 162: 1, 642: 2, 2562: 3, 10242: 4}
     g = torch.Generator().manual_seed(seed)
     if n_poses in sizes:
         R = icosphere_object_rotations(sizes[n_poses])
+    elif n_poses == 10248:
+        R = inplane_expand(icosphere_object_rotations(3), 4)
     else:
         q = torch.randn((n_poses, 4), generator=g, dtype=torch.float64)
         q = q / q.norm(dim=1, keepdim=True)

@@ -172,6 +172,12 @@ class UNet:
         if self._h is not None:
             _lib.check(_lib.load().nope_unet_set_option(self._h, name.encode(), int(value)))
 
+    def set_metric(self, metric, threshold=0.2):
+        """Similarity metric of the scoring fused onto the sweep: 'l2' (the reference's, model.py:254-266),
+        'cosine' or 'cosine_occlusion' (extensions; include/nope_b200.h NOPE_METRIC_*)."""
+        from .model import _METRICS
+        _lib.check(_lib.load().nope_unet_set_metric(self._handle(), _METRICS[metric], float(threshold)))
+
     def set_conv_impl(self, impl):
         """'tcgen05_2cta' (CTA pairs, default), 'tcgen05' (1-CTA tiles) or 'simt' (debug twin)."""
         _lib.check(_lib.load().nope_unet_set_conv_impl(
@@ -212,9 +218,11 @@ class UNet:
 
     # ------------------------------------------------------------------ hot path
     def sweep(self, ref_feat, poses, query_feat=None, want_emb=True, want_sim=None, k=0,
-              idx_base=0):
+              idx_base=0, out=None):
         """ref_feat [B,C,32,32], poses [B,N,6] (+ query_feat [B,C,32,32]) ->
-        dict(emb [B,N,C,32,32] | None, sim [B,N] | None, topv/topi [B,k] | None)."""
+        dict(emb [B,N,C,32,32] | None, sim [B,N] | None, topv/topi [B,k] | None).
+        `out` may carry preallocated contiguous `sim` / `topv` / `topi` tensors to write into (the
+        multi-GPU path points them into its all-gather record)."""
         if not self._finalized:
             raise _lib.NopeError("load_state_dict() must be called before the sweep")
         lib = _lib.load()
@@ -231,9 +239,17 @@ class UNet:
             assert query_feat.shape == ref_feat.shape
         emb = torch.empty((B, N, self.channels, 32, 32), device=dev, dtype=torch.float32) \
             if want_emb else None
-        sim = torch.empty((B, N), device=dev, dtype=torch.float32) if want_sim else None
-        topv = torch.empty((B, k), device=dev, dtype=torch.float32) if k > 0 else None
-        topi = torch.empty((B, k), device=dev, dtype=torch.int64) if k > 0 else None
+        out = out or {}
+        sim = out.get("sim") if want_sim else None
+        if want_sim and sim is None:
+            sim = torch.empty((B, N), device=dev, dtype=torch.float32)
+        topv, topi = (out.get("topv"), out.get("topi")) if k > 0 else (None, None)
+        if k > 0 and topv is None:
+            topv = torch.empty((B, k), device=dev, dtype=torch.float32)
+            topi = torch.empty((B, k), device=dev, dtype=torch.int64)
+        for t, shape, dt in ((sim, (B, N), torch.float32), (topv, (B, k), torch.float32), (topi, (B, k), torch.int64)):
+            if t is not None:
+                assert t.is_contiguous() and tuple(t.shape) == shape and t.dtype == dt and t.device == dev
         self.reserve(min(self._chunk, B * N), B, B * N if query_feat is not None else 0)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):

@@ -201,6 +201,18 @@ def cosine_similarity(query_feat, template_feat, eps=1e-8):
     return F.cosine_similarity(q, template_feat.reshape(b, n, -1), dim=-1, eps=eps)
 
 
+def cosine_occlusion_similarity(query_feat, template_feat, threshold=0.2, eps=1e-8):
+    """Extension: the two modules the reference's encoder declares but
+    never calls -- `sim_distance = nn.CosineSimilarity(dim=1)` (per-pixel cosine over channels,
+    src/model/encoder/template.py:45) followed by `OcclusionAwareSimilarity(threshold)` (similarities
+    <= threshold set to zero, src/model/encoder/base_template.py:67-75) -- averaged over the pixels."""
+    b, n = template_feat.shape[:2]
+    q = query_feat[:, None].expand_as(template_feat)
+    s = F.cosine_similarity(q, template_feat, dim=2, eps=eps)          # [B, N, H, W]
+    s = torch.where(s <= threshold, torch.zeros_like(s), s)
+    return s.flatten(2).mean(dim=2)
+
+
 def topk_lowest_index(similarity, k):
     """torch.topk's tie order is unspecified; the contract here is descending
     score, ties broken by the LOWEST index (SURVEY.md section 7 'Tie-breaking')."""

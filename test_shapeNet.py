@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """Evaluation entry point the reference's README names (README.md:82) but does not ship
-(SURVEY.md F1): for every test batch, predict the query pose from one reference view by
-sweeping the pose grid, and report the geodesic metrics the reference logs
-(src/model/model.py:268-358, src/model/loss.py:74-115).
+(SURVEY.md F1): what `trainer.test(model, dataloaders={"shapeNet_<category>": ...})` would run --
+for every test batch `PoseConditional.test_step` (src/model/model.py:550-565) -> `eval_geodesic`
+(model.py:268-376): validation loss under the ground-truth pose, pose-grid sweep + retrieval from one
+reference view, geodesic accuracy (src/model/loss.py:74-115), predictions saved per step.
 
-The ShapeNet renders (~2 TB) and the trained checkpoint are not available here, so without
---data-root the script runs on SYNTHETIC batches with the reference's batch schema
-(src/dataloader/shapeNet.py:348-357) and seeded random weights -- it then measures plumbing and
-throughput, not accuracy, and says so.  With torchrun (one process per GPU) the pose grid is
-sharded across ranks.
+The ShapeNet renders (~2 TB) and the trained checkpoint are not available here, so without a dataset
+the script runs on `SyntheticShapeNet` items -- same item schema (src/dataloader/shapeNet.py:348-357),
+same "shapeNet_<category>" dataloader keys over the reference's test categories
+(src/utils/shapeNet_utils.py:21-32), seeded random images / weights -- and says so: it then measures
+plumbing and throughput, not accuracy.  Batches of the reference schema from any other source go through
+`nope_b200.shapenet.ShapeNetBatchAdapter` the same way.  With torchrun (one process per GPU) the pose
+grid is sharded across ranks (one all-gather of packed top-k records per batch).
 
-  python test_shapeNet.py --batches 4 --batch-size 2 --grid 642
-  python test_shapeNet.py --checkpoint last.ckpt --data-root /data/shapenet ...   (needs a loader)
+  python test_shapeNet.py --batches 1 --batch-size 2 --grid 642 --categories bottle,mug
+  python test_shapeNet.py --checkpoint last.ckpt ...        (reference Lightning checkpoint)
 """
 import argparse
 import json
@@ -20,88 +23,83 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import torch
 
 
-def synthetic_batches(n_batches, batch_size, grid, seed=0):
-    """Yields dicts with the keys of src/dataloader/shapeNet.py:348-357 (gt_templates omitted:
-    it is only used for visualisation in the reference)."""
-    from nope_b200.poses import relative_rotation_6d, synthetic_pose_batch
-    g = torch.Generator().manual_seed(seed)
-    _, R = synthetic_pose_batch(grid, 1)
-    R = R.numpy()
-    for _ in range(n_batches):
-        qi = torch.randint(0, len(R), (batch_size,), generator=g)
-        ri = torch.randint(0, len(R), (batch_size,), generator=g)
-        yield {
-            "query": torch.rand(batch_size, 3, 256, 256, generator=g) * 2 - 1,
-            "reference": torch.rand(batch_size, 3, 256, 256, generator=g) * 2 - 1,
-            "all_relativeR": torch.stack([relative_rotation_6d(R, R[int(i)]) for i in ri]),
-            "gt_relativeR": torch.stack([relative_rotation_6d(R[int(q)][None], R[int(i)])[0]
-                                         for q, i in zip(qi, ri)]),
-            "query_pose": torch.from_numpy(R[qi.numpy()]),
-            "template_poses": torch.from_numpy(R)[None].expand(batch_size, -1, -1, -1),
-            "symmetry": torch.zeros(batch_size, 1),
-        }
+def build_loaders(categories, batches, batch_size, grid, seed=0):
+    from nope_b200.shapenet import SyntheticShapeNet
+    return {c: torch.utils.data.DataLoader(SyntheticShapeNet(c, n_items=batches * batch_size, grid=grid, seed=seed),
+                                           batch_size=batch_size, shuffle=False, num_workers=0)
+            for c in categories}
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--checkpoint", default=None, help="Lightning .ckpt or state_dict of the reference model")
-    ap.add_argument("--data-root", default=None)
-    ap.add_argument("--batches", type=int, default=2)
+    ap.add_argument("--batches", type=int, default=1, help="batches per category")
     ap.add_argument("--batch-size", type=int, default=2)
-    ap.add_argument("--grid", type=int, default=642, help="pose-grid size (642 = level 2, 'all')")
-    ap.add_argument("--metric", default="l2", choices=["l2", "cosine"])
-    args = ap.parse_args()
-    if args.data_root is not None:
-        raise SystemExit("a ShapeNet render loader is out of scope (SURVEY.md section 2); pass batches "
-                         "with the reference schema to PoseConditional.predict_pose instead")
+    ap.add_argument("--grid", type=int, default=642, help="pose-grid size (642 = level 2 'all'; 26/341 'upper')")
+    ap.add_argument("--categories", default="bottle,mug", help="comma list out of the reference's test_cats, or 'all'")
+    ap.add_argument("--metric", default="l2", choices=["l2", "cosine", "cosine_occlusion"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16_w2", "parity"])
+    ap.add_argument("--save-dir", default=None, help="predictions/pred_<cat>_step<k>_rank<r>.npz are written here")
+    ap.add_argument("--json-out", default=None)
+    args = ap.parse_args(argv)
     import torch.distributed as dist
-    from nope_b200.metrics import GeodesicError
     from nope_b200.model import build_model
+    from nope_b200.shapenet import TEST_CATS, ShapeNetBatchAdapter, keyed_batches
+    from nope_b200.weight import load_checkpoint
+    cats = TEST_CATS if args.categories == "all" else [c for c in args.categories.split(",") if c]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     rank = int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    model = build_model(device=f"cuda:{local}", similarity_metric=args.metric)
+    model = build_model(device=f"cuda:{local}", similarity_metric=args.metric, precision=args.precision)
+    model.save_dir = args.save_dir
+    model.global_rank = rank
+    from nope_b200 import synth_weights as weights
+    model.load_state_dict(weights.make_full_state_dict(seed=0))
+    weights_desc = "seeded random init (no trained checkpoint available)"
     if args.checkpoint:
-        sd = torch.load(args.checkpoint, map_location="cpu")
-        model.load_state_dict(sd.get("state_dict", sd))
-        weights_desc = args.checkpoint
-    else:
-        from nope_b200 import synth_weights as weights
-        model.load_state_dict(weights.make_full_state_dict(seed=0))
-        weights_desc = "seeded random init (no trained checkpoint available)"
+        # the reference's own loading rule (src/utils/weight.py:6-37): prefix stripped, shape-filtered
+        loaded, cannot, not_updated = load_checkpoint(model, args.checkpoint, checkpoint_key="state_dict")
+        weights_desc = f"{args.checkpoint} ({len(loaded)} tensors loaded, {len(cannot)} skipped)"
     if world > 1:
         from nope_b200.dist import ShardedSweep
         model.dist = ShardedSweep()
-    metric = GeodesicError()
-    errs, n_hyp, t0 = [], 0, time.time()
-    agg = {}
-    for batch in synthetic_batches(args.batches, args.batch_size, args.grid):
-        R, idx, sim = model.predict_pose(batch["query"], batch["reference"], batch["all_relativeR"],
-                                         batch["template_poses"], k=5)
-        err, res = metric(R.cpu(), batch["query_pose"], batch["symmetry"].reshape(-1))
-        errs.append(err)
-        for k, v in res.items():
-            agg.setdefault(k, []).append(float(v))
-        n_hyp += batch["all_relativeR"].shape[0] * batch["all_relativeR"].shape[1]
+    adapter = ShapeNetBatchAdapter(device=f"cuda:{local}")
+    loaders = build_loaders(cats, args.batches, args.batch_size, args.grid)
+    n_hyp, t0, top1 = 0, time.time(), {}
+    for idx_batch, step in enumerate(keyed_batches(loaders)):
+        step = {name: adapter(b) for name, b in step.items()}
+        out = model.test_step(step, idx_batch)                      # model.py:550-565
+        for name, (err, nearest_idx, sim) in out.items():
+            top1.setdefault(name, []).extend(nearest_idx[:, 0].tolist())
+            n_hyp += sim.numel()
     torch.cuda.synchronize()
     dt = time.time() - t0
+    # Lightning reports the epoch mean of everything logged
+    scores = {k: sum(v) / len(v) for k, v in model.logged.items()}
+    result = {
+        "data": "synthetic items with the ShapeNet test schema (accuracy numbers are meaningless without "
+                "the dataset + checkpoint)",
+        "weights": weights_desc, "grid": args.grid, "categories": cats, "batches_per_category": args.batches,
+        "batch_size": args.batch_size, "gpus": world, "metric": args.metric, "precision": args.precision,
+        "hypotheses": n_hyp, "hyp_per_s_incl_first_call": n_hyp / dt, "top1_idx": top1, "scores": scores}
     if rank == 0:
-        print(json.dumps({
-            "data": "synthetic (accuracy numbers are meaningless without the dataset + checkpoint)",
-            "weights": weights_desc, "grid": args.grid, "batches": args.batches,
-            "batch_size": args.batch_size, "gpus": world, "hypotheses": n_hyp,
-            "hyp_per_s_incl_first_call": n_hyp / dt,
-            **{k: sum(v) / len(v) for k, v in agg.items()}}))
-    if world > 1:
+        print(json.dumps(result))
+        if args.json_out:
+            with open(args.json_out, "w") as f:
+                json.dump(result, f)
+    if world > 1 and argv is None:
         dist.destroy_process_group()
+    return result
 
 
 if __name__ == "__main__":

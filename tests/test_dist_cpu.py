@@ -36,8 +36,13 @@ def _worker(rank, world, port, n_poses, k, ret):
             tv = torch.empty(3, 0)
             ti = torch.empty(3, 0, dtype=torch.int64)
         ss = ShardedSweep()
-        full, topi = ss.gather_merge(local, tv, ti, n_poses, k)
+        send, recv, topv_v, topi_v, off_s, pack, per = ss.record(3, k, n_poses, True, torch.device("cpu"))
+        ss.fill_record(send, topv_v, topi_v, off_s, local, tv, ti)
+        full, topi = ss.gather_merge(send, recv, 3, k, n_poses, per, pack, True)     # ONE all-gather
         ok = torch.equal(full, sim) and torch.equal(topi, topk_lowest_index(sim, k))
+        # the record layout is the one the CUDA merge kernel reads (include/nope_b200.h)
+        from nope_b200 import _lib
+        ok = ok and pack == _lib.load().nope_topk_pack_floats(3, k, per, 1)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

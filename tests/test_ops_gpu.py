@@ -141,7 +141,7 @@ def test_conv_simt(dev, n, C0, C1, Cout, S, mode):
     assert e < FP16_TOL
 
 
-@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("metric", ["l2", "cosine", "cosine_occlusion"])
 def test_score_topk(dev, metric):
     from nope_b200.model import score_topk
     from oracle import unet_oracle as orc
@@ -149,7 +149,8 @@ def test_score_topk(dev, metric):
     q = torch.randn(3, 8, 32, 32, generator=g)
     t = torch.randn(3, 41, 8, 32, 32, generator=g)
     t[1, 7] = t[1, 3]                                  # exact tie -> lowest index wins
-    ref = orc.l2_similarity(q, t) if metric == "l2" else orc.cosine_similarity(q, t)
+    ref = {"l2": orc.l2_similarity, "cosine": orc.cosine_similarity,
+           "cosine_occlusion": orc.cosine_occlusion_similarity}[metric](q, t)
     sim, idx = score_topk(q.to(dev), t.to(dev), k=5, metric=metric)
     e = rel_l2(sim, ref)
     log("score_topk", metric=metric, rel_l2=e)

@@ -130,6 +130,43 @@ def test_forward_call_and_loss(gpu_model, golden_dir):
     assert abs(float(loss) - float(ref_loss)) < 2e-3 * float(ref_loss)
 
 
+@pytest.mark.parametrize("metric", ["cosine", "cosine_occlusion"])
+def test_fused_extension_metrics(gpu_model, golden_dir, metric):
+    """the cosine / occlusion-aware similarities are evaluated in the sweep's last
+    layer (no [B,N,C,32,32] tensor) and must equal (a) the standalone scoring of the materialised
+    templates and (b) the torch oracle of the metric on those templates."""
+    from nope_b200.model import score_topk
+    from oracle import unet_oracle as orc
+    g = np.load(f"{golden_dir}/grid26_b2.npz")
+    rf, qf = torch.from_numpy(g["ref_feat"]), torch.from_numpy(g["query_feat"])
+    poses = torch.from_numpy(g["all_relativeR"])
+    u = gpu_model.u_net
+    try:
+        u.set_metric(metric, 0.2)
+        out = u.sweep(rf, poses, query_feat=qf, want_emb=True, k=5)
+    finally:
+        u.set_metric("l2")
+    sim2, idx2 = score_topk(qf.cuda(), out["emb"], k=5, metric=metric, threshold=0.2)
+    fn = orc.cosine_similarity if metric == "cosine" else orc.cosine_occlusion_similarity
+    ref = fn(qf, out["emb"].cpu())
+    e_std, e_orc = max_rel(out["sim"], sim2), max_rel(out["sim"], ref)
+    log("fused_metric", metric=metric, vs_standalone=e_std, vs_oracle=e_orc, topi=out["topi"].tolist())
+    assert e_std < 1e-5 and e_orc < 1e-5
+    assert torch.equal(out["topi"].cpu(), orc.topk_lowest_index(out["sim"].cpu(), 5))
+    # through the task module: similarity_metric in testing_config (configs/model/template_base.yaml:24)
+    from oracle import inputs
+    q, r = inputs.make_images(seed=0, batch=2)
+    old = gpu_model.testing_config.similarity_metric
+    try:
+        gpu_model.testing_config.similarity_metric = metric
+        _, idx3, sim3 = gpu_model.predict_pose(q, r, poses, None, k=5)
+    finally:
+        gpu_model.testing_config.similarity_metric = old
+        u.set_metric("l2")
+    assert sim3.shape == (2, 26) and idx3.shape == (2, 5)
+    assert torch.equal(idx3.cpu(), orc.topk_lowest_index(sim3.cpu(), 5))
+
+
 def test_bad_arguments_raise(gpu_model):
     from nope_b200 import NopeError
     rf = torch.zeros(1, 8, 32, 32)
