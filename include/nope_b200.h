@@ -81,7 +81,9 @@ int nope_unet_set_conv_impl(nope_unet_t* u, int impl);
  *   "fuse_gn" (default 1): GroupNorm + SiLU + pose bias + residual run in the epilogue of the producing
  *       convolution (Block.forward / ResnetBlock.forward, model_utils.py:237-279); 0 = separate
  *       gn_apply pass (round-1 schedule; also what conv_impl 0 / 1 use);
- *   "conv_impl": as nope_unet_set_conv_impl. */
+ *   "conv_impl": as nope_unet_set_conv_impl;
+ *   "attn_impl": LinearAttention core, 0 = tcgen05 kernel at 32x32 / 16x16 (CUDA cores below 128 tokens),
+ *       1 = CUDA-core kernel everywhere. */
 int nope_unet_set_option(nope_unet_t* u, const char* name, int value);
 int nope_unet_get_option(const nope_unet_t* u, const char* name, int* value);
 
@@ -200,8 +202,9 @@ int nope_op_conv_gn_fused(int mode, int precision, const float* x0, int C0, cons
 int nope_op_groupnorm(const float* x, const float* gamma, const float* beta, int G, int silu,
                       const float* chan_bias, const float* residual, float* out, int n_img,
                       int C, int H, int W, void* stream);
-/* LinearAttention core on qkv [n, 384, H, W] -> [n, 128, H, W] (model_utils.py:403-417) */
-int nope_op_linear_attention(const float* qkv, float* out, int n_img, int H, int W, void* stream);
+/* LinearAttention core on qkv [n, 384, H, W] -> [n, 128, H, W] (model_utils.py:403-417).
+ * impl 0: tcgen05 kernel (both contractions on tensor cores, H*W a multiple of 128), 1: CUDA cores. */
+int nope_op_linear_attention(int impl, const float* qkv, float* out, int n_img, int H, int W, void* stream);
 /* Attention core on qkv [n, 384, H, W] -> [n, 128, H, W], H*W <= 32 (model_utils.py:376-388) */
 int nope_op_attention(const float* qkv, float* out, int n_img, int H, int W, void* stream);
 /* nearest x2 upsample (model_utils.py:161-163) */

@@ -181,6 +181,15 @@ __device__ __forceinline__ uint32_t order_token(uint32_t v) {
   return r;
 }
 
+// x * sigmoid(x) on two MUFU ops and three FMA-pipe ops (flush-to-zero variants: the IEEE-denormal
+// handling of __expf / __fdividef costs four more instructions per element in this issue-bound pass)
+__device__ __forceinline__ float silu_ftz(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+
 __host__ __device__ constexpr int gn_epi_warps(int BN) { return 4 * (BN / 64); }           // one (lane quarter, 64-column sub-tile) each
 __host__ __device__ constexpr int gn_threads(int BN) { return 128 + 32 * gn_epi_warps(BN); }
 
@@ -213,6 +222,12 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
   const bool small = hw < 32;                       // 4x4 images: 16-row segments, two per warp
   const int it = hw < kBM ? (row >> g.hw_shift) : 0;    // image of this thread's row inside the tile
   const int npairs = g.ipt * g.gpt;
+  // one image per tile (>= 128-pixel images, always synchronised across tiles): normalisation through
+  // per-channel scale / shift tables, which live behind the single pose-bias row in the s_pb region
+  const bool use_tab = g.G > 0 && g.ipt == 1 && g.expected > 1;
+  float* s_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_pb) + 512);
+  float* s_sh = s_sc + BN;
+  static_assert(512 + 2 * BN * 4 <= 8 * BN * 2, "scale / shift tables must fit behind the first pose-bias row");
   if (etid < kOct) s_og[etid] = (g.G > 0 && g.cpg < BN) ? (etid * 8) / g.cpg : 0;
 #define NOPE_EPI_BAR() asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory")
 
@@ -231,17 +246,22 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
     conv_tile_coords(p, m_tile, b0, y0);
     const int img0 = p.tiles_per_img > 0 ? m_tile / g.mt : m_tile * g.ipt;   // first image of the tile
     uint8_t* ost = out_stage + obuf * S::kOutBytes;
-    if (etid == 0) {
-      if constexpr (S::kOutBufs == 2) tma_store_wait_read1();
-      else tma_store_wait_read0();
-      if (g.has_res && live) {     // residual tile -> staging buffer (same box / swizzle as the store)
-        const int rb = g.res_div > 0 ? (g.res_base + b0) / g.res_div : b0;
-        mbar_expect_tx(res_bar, S::kOutBytes);
+    // staging buffer: free once the TMA store that last used it has read it; then the residual tile is
+    // loaded into it (same box / swizzle as the store).  Issued after pass 1, so that the store drain and
+    // the load latency overlap the accumulator read-out and the tile sync.
+    auto stage_residual = [&]() {
+      if (etid == 0) {
+        if constexpr (S::kOutBufs == 2) tma_store_wait_read1();
+        else tma_store_wait_read0();
+        if (g.has_res && live) {
+          const int rb = g.res_div > 0 ? (g.res_base + b0) / g.res_div : b0;
+          mbar_expect_tx(res_bar, S::kOutBytes);
 #pragma unroll 1
-        for (int c2 = 0; c2 < kNS; ++c2)
-          tma_load_4d(ost + c2 * (kBM * 128), &p.rmap, res_bar, n_chan0 + c2 * 64, 0, y0, rb);
+          for (int c2 = 0; c2 < kNS; ++c2)
+            tma_load_4d(ost + c2 * (kBM * 128), &p.rmap, res_bar, n_chan0 + c2 * 64, 0, y0, rb);
+        }
       }
-    }
+    };
     if (etid < BN && (tile == tile0 || p.n_tiles > 1)) {     // channel parameters of this N-tile
       s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
       if (g.G > 0) {
@@ -279,6 +299,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         else mbar_arrive_remote(&tempty_bar[acc], 0);
       }
     }
+    if (!live || g.G == 0 || g.expected == 1) stage_residual();
     if (live) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -335,6 +356,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
             st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2, make_uint2(__float_as_uint(Sx), g.epoch));
             st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2 + 1, make_uint2(__float_as_uint(Qx), g.epoch));
           }
+          stage_residual();
           if (etid < g.expected * npairs * 2) {
             uint2 u = ld_volatile_u2(xp + etid);
             if (u.y != g.epoch && !(g.dbg & 1)) {
@@ -351,7 +373,23 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
           }
           NOPE_EPI_BAR();
           NOPE_TS(4);
-          if (etid < npairs) {           // fixed slot order
+          if (use_tab) {
+            // one image per tile: per-channel scale / shift tables, y = x * sc[c] + sh[c]; every channel's
+            // thread sums its group's partials itself (fixed slot order), no (mean, rstd) hand-over
+            if (etid < BN) {
+              const int gl = s_og[etid >> 3];
+              float s1 = 0.f, s2 = 0.f;
+              for (int sl = 0; sl < g.expected; ++sl) {
+                s1 += s_x[(sl * npairs + gl) * 2];
+                s2 += s_x[(sl * npairs + gl) * 2 + 1];
+              }
+              const float mean = s1 * g.inv_cnt;
+              const float var = fmaxf(s2 * g.inv_cnt - mean * mean, 0.f);
+              const float sc = rsqrtf(var + g.eps) * s_gamma[etid];
+              s_sc[etid] = sc;
+              s_sh[etid] = s_beta[etid] - mean * sc;
+            }
+          } else if (etid < npairs) {           // fixed slot order
             Sx = 0.f; Qx = 0.f;
             for (int sl = 0; sl < g.expected; ++sl) {
               Sx += s_x[(sl * npairs + etid) * 2];
@@ -359,7 +397,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
             }
           }
         }
-        if (etid < npairs) {
+        if (!use_tab && etid < npairs) {
           const float mean = Sx * g.inv_cnt;
           const float var = fmaxf(Qx * g.inv_cnt - mean * mean, 0.f);
           s_mr[etid] = make_float2(mean, rsqrtf(var + g.eps));
@@ -376,6 +414,8 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
       const uint32_t a_beta = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_beta) - smem) + cc * 256;
       const uint32_t a_pb = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_pb) - smem) + (it * BN + cc * 64) * 2;
       const uint32_t a_mr = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_mr) - smem) + it * g.gpt * 8;
+      const uint32_t a_sc = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_sc) - smem) + cc * 256;
+      const uint32_t a_sh = tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_sh) - smem) + cc * 256;
       const int grow = m_tile * kBM + row;            // linear output pixel
       const bool row_ok = grow < p.m_valid;
       // residual pixel under the hoisted-prefix image mapping (32x32 images: one image per tile)
@@ -392,7 +432,14 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(a[j * 8 + i]);
-        if (do_norm) {
+        if (do_norm && use_tab) {
+          const float4 g0 = lds_f4(a_sc + j * 32), g1 = lds_f4(a_sc + j * 32 + 16);
+          const float4 h0 = lds_f4(a_sh + j * 32), h1 = lds_f4(a_sh + j * 32 + 16);
+          const float sc[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+        } else if (do_norm) {
           const float2 mr = lds_f2(a_mr + s_og[lc >> 3] * 8);
           const float4 g0 = lds_f4(a_gamma + j * 32), g1 = lds_f4(a_gamma + j * 32 + 16);
           const float4 h0 = lds_f4(a_beta + j * 32), h1 = lds_f4(a_beta + j * 32 + 16);

@@ -20,6 +20,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "kernels.cuh"
+#include "linattn_tc.cuh"
 #include "encoder.cuh"
 #include "ldm.cuh"
 
@@ -94,6 +95,7 @@ struct nope_unet {
   // 0: fp16 operands; 1: exact weights (W_hi + W_lo K-segments, 2x the MMA work); 2: split precision
   // (exact weights + activations carried as hi + lo: A_hi W_hi + A_hi W_lo + A_lo W_hi, 3x)
   int precision = 0;
+  int attn_impl = 1;         // LinearAttention core: 0 tcgen05 (token counts >= 128), 1 CUDA cores
   int metric = 0;            // NOPE_METRIC_* of the fused scoring
   float occ_threshold = 0.2f;
   int chunk = 642;
@@ -865,8 +867,12 @@ struct nope_unet {
     if (gn(&norms.at(p + ".prenorm"), x.hi, TB.hi, S, C, n, false, -1, nullptr, nullptr, st, SB, eparts, 1))
       return -1;
     if (conv(convs.at(p + ".qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
-    linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD.hi, TC.hi, S * S);
-    NOPE_CUDA(cudaGetLastError());
+    if (attn_impl == 0 && S * S >= kBM) {
+      if (launch_linattn_tc(TD.hi, TC.hi, n, S * S, num_sms, st)) return -1;
+    } else {
+      linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD.hi, TC.hi, S * S);
+      NOPE_CUDA(cudaGetLastError());
+    }
     ++launches;
     if (fused()) {
       GnSpec s;
@@ -1154,6 +1160,11 @@ int nope_unet_set_option(nope_unet_t* u, const char* name, int value) {
     return 0;
   }
   if (std::strcmp(name, "conv_impl") == 0) return nope_unet_set_conv_impl(u, value);
+  if (std::strcmp(name, "attn_impl") == 0) {
+    NOPE_CHECK(value == 0 || value == 1, "attn_impl must be 0 (tcgen05) or 1 (CUDA cores)");
+    u->attn_impl = value;
+    return 0;
+  }
   return fail(std::string("unknown option: ") + name);
 }
 int nope_unet_get_option(const nope_unet_t* u, const char* name, int* value) {
@@ -1161,6 +1172,7 @@ int nope_unet_get_option(const nope_unet_t* u, const char* name, int* value) {
   if (std::strcmp(name, "fuse_gn") == 0) { *value = u->fuse_gn ? 1 : 0; return 0; }
   if (std::strcmp(name, "precision") == 0) { *value = u->precision; return 0; }
   if (std::strcmp(name, "conv_impl") == 0) { *value = u->conv_impl; return 0; }
+  if (std::strcmp(name, "attn_impl") == 0) { *value = u->attn_impl; return 0; }
   return fail(std::string("unknown option: ") + name);
 }
 int64_t nope_unet_last_launch_count(const nope_unet_t* u) { return u ? u->launches : 0; }
@@ -1586,13 +1598,22 @@ int nope_op_groupnorm(const float* x, const float* gamma, const float* beta, int
   return 0;
 }
 
-int nope_op_linear_attention(const float* qkv, float* out, int n_img, int H, int W, void* stream) {
+int nope_op_linear_attention(int impl, const float* qkv, float* out, int n_img, int H, int W, void* stream) {
   NOPE_CHECK(qkv && out, "null argument");
+  NOPE_CHECK(impl == 1 || (impl == 0 && (H * W) % kBM == 0), "impl 0 (tcgen05) needs H*W % 128 == 0; impl 1 = CUDA cores");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Scratch s;
   __half *a = nullptr, *o = nullptr;
   if (to_nhwc(qkv, &a, s, n_img, 384, H * W, st) || s.get(&o, (size_t)n_img * 128 * H * W)) return -1;
-  linattn_kernel<<<dim3(4, n_img), kLinAttnThreads, 0, st>>>(a, o, H * W);
+  if (impl == 0) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    NOPE_CUDA(cudaGetDevice(&dev));
+    NOPE_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (launch_linattn_tc(a, o, n_img, H * W, prop.multiProcessorCount, st)) return -1;
+  } else {
+    linattn_kernel<<<dim3(4, n_img), kLinAttnThreads, 0, st>>>(a, o, H * W);
+  }
   NOPE_CUDA(cudaGetLastError());
   if (to_nchw(o, out, n_img, 128, H * W, st)) return -1;
   NOPE_CUDA(cudaStreamSynchronize(st));

@@ -90,15 +90,16 @@ def groupnorm(x, gamma, beta, groups, silu=False, chan_bias=None, residual=None)
     return out
 
 
-def linear_attention(qkv):
+def linear_attention(qkv, impl="simt"):
+    """impl 'tcgen05' (both contractions on tensor cores; H*W a multiple of 128) or 'simt'."""
     lib = _lib.load()
     qkv = _f32(qkv)
     n, c, h, w = qkv.shape
     assert c == 384
     out = torch.empty((n, 128, h, w), device=qkv.device, dtype=torch.float32)
     with torch.cuda.device(qkv.device):
-        _lib.check(lib.nope_op_linear_attention(_lib.ptr(qkv), _lib.ptr(out), n, h, w,
-                                                _stream(qkv.device)))
+        _lib.check(lib.nope_op_linear_attention({"tcgen05": 0, "simt": 1}[impl], _lib.ptr(qkv), _lib.ptr(out),
+                                                n, h, w, _stream(qkv.device)))
     return out
 
 

@@ -14,6 +14,8 @@ Writes:
   tests/golden/unet_taps.npz    per-layer activation statistics of one UNet forward
   tests/golden/ldm_b1_n3.npz    (--only-ldm) LDM-variant UNet (UNetModelPose): 3 hypotheses, embeddings,
                                 scores, per-block activation statistics
+  tests/golden/cfg2_b8_n2562.npz (--only-cfg2) BASELINE configs[2] at full size: 8 queries x the 2562-pose
+                                level-3 grid: scores, top-5, embedding norms, three full templates
   tests/golden/meta.json        weight checksum, torch version, oracle-vs-reference errors
 It asserts (hard failure) that
   * the seeded state_dict loads into the reference modules with strict=True
@@ -103,6 +105,51 @@ def write_full_grid_fixture():
     return {"reference_cpu_seconds": secs, "top5": idx.tolist(), "min_rel_gap_top6": gap}
 
 
+def write_cfg2_fixture(batch=8):
+    """tests/golden/cfg2_b8_n2562.npz: BASELINE configs[2] at FULL size -- 8 queries x the shipped
+    2562-pose level-3 grid (src/poses/predefined_poses/obj_poses_level3.npy) through the reference's own
+    encoder / UNet modules (16 hypotheses per forward), "l2" similarity (model.py:260-262) and topk(5).
+    20 496 reference forwards: ~40 minutes on 8 cores.  Stored: latents, the grid, similarity rows, top-5,
+    per-hypothesis embedding norms and three full templates."""
+    pp = os.path.join(REFERENCE_ROOT, "src/poses/predefined_poses")
+    R3 = np.load(os.path.join(pp, "obj_poses_level3.npy"))[:, :3, :3].astype(np.float64)
+    n = R3.shape[0]
+    ref_idx = [(7 + 311 * b) % n for b in range(batch)]
+    relR = torch.stack([inputs.relative_rot6d(R3, R3[i]) for i in ref_idx])          # [B, n, 6]
+    model = build_reference_model()
+    sd = weights.make_full_state_dict(seed=0)
+    model.u_net.load_state_dict(sd, strict=True)
+    q, r = inputs.make_images(seed=7, batch=batch)
+    keep = [(0, 0), (3, 1000), (batch - 1, n - 1)]
+    kept = {}
+    with torch.no_grad():
+        qf = torch.cat([model.u_net.encoder.encode_image(q[b:b + 1]) for b in range(batch)])
+        rf = torch.cat([model.u_net.encoder.encode_image(r[b:b + 1]) for b in range(batch)])
+        sim = torch.zeros(batch, n)
+        l2n = torch.zeros(batch, n)
+        t0 = time.time()
+        for b in range(batch):
+            for s0 in range(0, n, 16):
+                p = relR[b, s0:s0 + 16]
+                emb = model.u_net(rf[b:b + 1].expand(p.shape[0], -1, -1, -1), p)        # [16, 8, 32, 32]
+                d = (qf[b:b + 1] - emb) ** 2
+                sim[b, s0:s0 + p.shape[0]] = -torch.norm(d, dim=1).sum(dim=(1, 2))
+                l2n[b, s0:s0 + p.shape[0]] = emb.flatten(1).norm(dim=1)
+                for (kb, kn) in keep:
+                    if kb == b and s0 <= kn < s0 + p.shape[0]:
+                        kept[f"emb_b{kb}_n{kn}"] = emb[kn - s0].numpy().copy()
+            print(f"cfg2: query {b} done, {time.time() - t0:.0f} s", flush=True)
+        _, idx = sim.topk(k=5, dim=1)
+        secs = time.time() - t0
+    srt = torch.sort(sim, dim=1, descending=True).values
+    gap = ((srt[:, :-1] - srt[:, 1:]) / srt[:, :-1].abs())[:, :5]
+    np.savez_compressed(os.path.join(OUT, "cfg2_b8_n2562.npz"), query_feat=qf.numpy(), ref_feat=rf.numpy(),
+                        level3_all=R3, ref_idx=np.array(ref_idx), similarity=sim.numpy(), nearest_idx=idx.numpy(),
+                        emb_l2=l2n.numpy(), **kept)
+    return {"reference_cpu_seconds": secs, "top5": idx.tolist(), "min_rel_gap_top6": float(gap.min()),
+            "hypotheses": batch * n}
+
+
 def make_ldm_inputs(seed, batch, n):
     """Seeded LDM-variant inputs: VAE-like latents N(0,1) [B,4,32,32] (the diffusers VAE itself
     is absent, see ref_import.build_reference_ldm_unet) and [B,n,6] level-0 relative poses."""
@@ -154,6 +201,10 @@ def main():
     if "--only-full-grid" in sys.argv:
         torch.set_num_threads(os.cpu_count())
         print(json.dumps(write_full_grid_fixture(), indent=1))
+        return
+    if "--only-cfg2" in sys.argv:
+        torch.set_num_threads(int(os.environ.get("NOPE_GOLDEN_THREADS", os.cpu_count())))
+        print(json.dumps(write_cfg2_fixture(), indent=1))
         return
     if "--only-geodesic" in sys.argv:
         print(json.dumps(write_geodesic_fixture(), indent=1))

@@ -25,6 +25,19 @@ def seeded_state_dict():
 
 
 @pytest.fixture(scope="session")
+def gpu_model_parity(seeded_state_dict):
+    """The same model in the split-precision mode (exact weights + hi/lo activations): the mode that
+    carries the north-star 1e-3 embedding tolerance."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from nope_b200.model import build_model
+    m = build_model(device="cuda:0", precision="parity")
+    m.load_state_dict(seeded_state_dict)
+    return m.eval()
+
+
+@pytest.fixture(scope="session")
 def gpu_model(seeded_state_dict):
     """nope_b200 PoseConditional on cuda:0 with the seeded weights (session-wide)."""
     import torch

@@ -69,6 +69,28 @@ def test_linear_attention(dev, n, S):
     assert e < FP16_TOL
 
 
+@pytest.mark.parametrize("n,S", [(3, 32), (5, 16), (150, 16), (1, 32)])
+def test_linear_attention_tcgen05(dev, n, S):
+    """The tensor-core LinearAttention core (csrc/linattn_tc.cuh): ek^T v and qs ctx as tcgen05 GEMMs over
+    token-major operands (MN-major descriptors), exp / softmax transforms in place.  fp16 operands (ek, qs,
+    ctx) add ~3e-4 to the one output rounding of the CUDA-core kernel."""
+    from nope_b200 import ops
+    g = _g(S + n)
+    qkv = h(torch.randn(n, 384, S, S, generator=g) * 1.5)
+    b, hw = n, S * S
+    q, k, v = [t.reshape(b, 4, 32, hw).double() for t in qkv.chunk(3, dim=1)]
+    q = q.softmax(dim=-2) * 32 ** -0.5
+    k = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    ref = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(b, 128, S, S)
+    out = ops.linear_attention(qkv.to(dev), impl="tcgen05")
+    e = rel_l2(out, ref)
+    simt = ops.linear_attention(qkv.to(dev), impl="simt")
+    log("linear_attention_tc", n=n, S=S, rel_l2=e, rel_l2_simt=rel_l2(simt, ref), vs_simt=rel_l2(out, simt))
+    assert e < FP16_TOL
+    assert torch.equal(ops.linear_attention(qkv.to(dev), impl="tcgen05"), out)     # deterministic
+
+
 @pytest.mark.parametrize("n,S", [(6, 4), (2, 2)])
 def test_attention(dev, n, S):
     from nope_b200 import ops

@@ -14,8 +14,22 @@ from _util import log, max_rel, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-EMB_TOL = 2.5e-3   # measured 1.4-1.8e-3; fp16 weight rounding alone is 0.9e-3 (tools/precision_budget.py)
+# Stated tolerances (BASELINE.json north_star: embeddings and scores within 1e-3 of the fp32 reference,
+# argmax identical):
+#   precision "parity" (split precision)  embeddings <= 1e-3 (measured ~1e-4), scores <= 1e-3, top-5 identical
+#   precision "fp16"  (default, fast)     scores <= 1e-3 (measured 7e-4) and argmax identical, but embeddings
+#                                         1.2-1.5e-3: fp16 WEIGHT rounding alone is 0.9e-3 and every stored
+#                                         activation adds 2.8e-4 rms (tools/precision_sim.py) -- the fast mode
+#                                         is gated at 2e-3 and does NOT claim the embedding bar
+EMB_TOL = 2.0e-3
+EMB_TOL_PARITY = 1e-3
 SIM_TOL = 1e-3
+
+
+def _swaps(idx_ref, idx):
+    """positions 2..5 of the top-5 that differ from the reference (position 1 is asserted equal)"""
+    idx_ref = torch.as_tensor(idx_ref)
+    return int((idx.cpu()[:, 1:] != idx_ref[:, 1:]).sum())
 
 
 def _cmp_ranking(sim_ref, idx_ref, idx, tol):
@@ -165,6 +179,62 @@ def test_fused_extension_metrics(gpu_model, golden_dir, metric):
         u.set_metric("l2")
     assert sim3.shape == (2, 26) and idx3.shape == (2, 5)
     assert torch.equal(idx3.cpu(), orc.topk_lowest_index(sim3.cpu(), 5))
+
+
+def test_parity_mode_meets_the_north_star_tolerance(gpu_model_parity, gpu_model, golden_dir):
+    """precision="parity": every convolution runs A_hi W_hi + A_hi W_lo + A_lo W_hi on fp16 (hi, lo) pairs
+    (22 significant bits), activations travel as pairs.  Against the UNMODIFIED reference's goldens:
+    embeddings <= 1e-3 (the stated bar, with an order of magnitude to spare), scores <= 1e-3, the whole
+    top-5 identical; the fast fp16 mode's rank swaps on the same grids are reported next to it."""
+    m = gpu_model_parity
+    g = np.load(f"{golden_dir}/cfg1_b1_n6.npz")
+    out = m.u_net.sweep(torch.from_numpy(g["ref_feat"]), torch.from_numpy(g["all_relativeR"]),
+                        query_feat=torch.from_numpy(g["query_feat"]), want_emb=True, k=5)
+    e1 = rel_l2(out["emb"], torch.from_numpy(g["emb"]))
+    s1 = max_rel(out["sim"], torch.from_numpy(g["similarity"]))
+    assert e1 < EMB_TOL_PARITY and s1 < SIM_TOL
+    assert torch.equal(out["topi"].cpu(), torch.from_numpy(g["nearest_idx"]))
+    g2 = np.load(f"{golden_dir}/grid26_b2.npz")
+    out2 = m.u_net.sweep(torch.from_numpy(g2["ref_feat"]), torch.from_numpy(g2["all_relativeR"]),
+                         query_feat=torch.from_numpy(g2["query_feat"]), want_emb=True, k=5)
+    e2 = max(rel_l2(out2["emb"][0, 0], torch.from_numpy(g2["emb_b0_n0"])),
+             rel_l2(out2["emb"][1, 25], torch.from_numpy(g2["emb_b1_n25"])))
+    s2 = max_rel(out2["sim"], torch.from_numpy(g2["similarity"]))
+    assert e2 < EMB_TOL_PARITY and s2 < SIM_TOL
+    assert torch.equal(out2["topi"].cpu(), torch.from_numpy(g2["nearest_idx"]))
+    g3 = np.load(f"{golden_dir}/level2_642_b1.npz")
+    args3 = (torch.from_numpy(g3["ref_feat"]), torch.from_numpy(g3["all_relativeR"]))
+    out3 = m.u_net.sweep(*args3, query_feat=torch.from_numpy(g3["query_feat"]), want_emb=True, k=5)
+    e3 = max(rel_l2(out3["emb"][0, 0], torch.from_numpy(g3["emb_n0"])),
+             rel_l2(out3["emb"][0, 641], torch.from_numpy(g3["emb_n641"])))
+    s3 = max_rel(out3["sim"], torch.from_numpy(g3["similarity"]))
+    fast = gpu_model.u_net.sweep(*args3, query_feat=torch.from_numpy(g3["query_feat"]), want_emb=False, k=5)
+    log("parity_mode", cfg1_emb=e1, cfg1_sim=s1, grid26_emb=e2, grid26_sim=s2, level2_642_emb=e3, level2_642_sim=s3,
+        top5_642=out3["topi"].tolist(), swaps_642_parity=_swaps(g3["nearest_idx"], out3["topi"]),
+        swaps_642_fp16=_swaps(g3["nearest_idx"], fast["topi"]))
+    assert e3 < EMB_TOL_PARITY and s3 < SIM_TOL
+    assert torch.equal(out3["topi"].cpu(), torch.from_numpy(g3["nearest_idx"]))
+    # chunking / determinism hold in this mode too
+    m.u_net.set_chunk(100)
+    out4 = m.u_net.sweep(*args3, query_feat=torch.from_numpy(g3["query_feat"]), want_emb=False, k=5)
+    m.u_net.set_chunk(642)
+    assert torch.equal(out4["sim"], out3["sim"]) and torch.equal(out4["topi"], out3["topi"])
+
+
+def test_exact_weights_mode(seeded_state_dict, golden_dir):
+    """precision="fp16_w2" (W_hi + W_lo K-segments, fp16 activations): measured between the two other
+    modes; gated at the fast mode's tolerance."""
+    from nope_b200.model import build_model
+    m = build_model(device="cuda:0", precision="fp16_w2")
+    m.load_state_dict(seeded_state_dict)
+    g3 = np.load(f"{golden_dir}/level2_642_b1.npz")
+    out = m.u_net.sweep(torch.from_numpy(g3["ref_feat"]), torch.from_numpy(g3["all_relativeR"]),
+                        query_feat=torch.from_numpy(g3["query_feat"]), want_emb=True, k=5)
+    e = max(rel_l2(out["emb"][0, 0], torch.from_numpy(g3["emb_n0"])), rel_l2(out["emb"][0, 641], torch.from_numpy(g3["emb_n641"])))
+    s = max_rel(out["sim"], torch.from_numpy(g3["similarity"]))
+    log("w2_mode", level2_642_emb=e, level2_642_sim=s, swaps=_swaps(g3["nearest_idx"], out["topi"]))
+    assert e < EMB_TOL and s < SIM_TOL
+    assert int(out["topi"][0, 0]) == int(g3["nearest_idx"][0, 0])
 
 
 def test_bad_arguments_raise(gpu_model):

@@ -9,6 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,nohe
 run() { echo "== $1"; shift; timeout "$@"; echo "rc=$?"; }
 for step in "$@"; do
 case "$step" in
+  linattn)  run "linattn tc tests" 600 python -m pytest tests/test_ops_gpu.py -m gpu -q -x --tb=short -k "linear_attention" > gpurun_out/t_linattn.log 2>&1; tail -15 gpurun_out/t_linattn.log ;;
   fused)    run "fused op tests" 900 python -m pytest tests/test_fused_gpu.py -m gpu -q -x --tb=short > gpurun_out/t_fused.log 2>&1; tail -15 gpurun_out/t_fused.log ;;
   unet)     run "unet tests" 1500 python -m pytest tests/test_unet_gpu.py -m gpu -q --tb=short > gpurun_out/t_unet.log 2>&1; tail -25 gpurun_out/t_unet.log ;;
   tests)    rm -f gpurun_out/parity_log.jsonl; run "pytest -m gpu" 2400 python -m pytest tests -m gpu -q -rA --tb=short > gpurun_out/pytest_gpu.log 2>&1; tail -8 gpurun_out/pytest_gpu.log ;;
