@@ -82,6 +82,15 @@ struct GnFuse {
   // and of the residual (same layout; the residual image mapping of res_div applies)
   __half* out_lo;
   const __half* res_lo;
+  // Pre-norm fold (PreNorm(GroupNorm(1, C)) in front of a bias-free 1x1, model_utils.py:226-234, 399):
+  //   W (gamma * (x - mean) * rstd + beta) = rstd * (W' x) - rstd * mean * w1 + wb,   W' = W diag(gamma),
+  // W' is what the layer's packed weights hold, w1[c] = sum_k W'[c,k], wb[c] = sum_k W[c,k] beta[k].
+  // (mean, rstd) of an input image come from the partial sums its producer emitted (GnFuse::emit layout).
+  const float2* pre_stats;   // [img][pre_parts] or nullptr
+  int pre_parts;
+  float pre_inv_cnt;         // 1 / (H*W * Cin)
+  const float* pre_w1;       // [n_total]
+  const float* pre_wb;       // [n_total]
   int dbg;               // development knobs (NOPE_GN_DBG): 1 skip the poll, 2 skip SiLU, 4 skip pass 2 math
   unsigned long long* ts;  // development: per (CTA, tile iteration) phase timestamps [grid][64][8] (globaltimer, ns)
 };

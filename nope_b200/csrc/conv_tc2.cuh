@@ -267,6 +267,9 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
       if (g.G > 0) {
         s_gamma[etid] = __ldg(g.gamma + n_chan0 + etid);
         s_beta[etid] = __ldg(g.beta + n_chan0 + etid);
+      } else if (g.pre_stats) {
+        s_gamma[etid] = __ldg(g.pre_w1 + n_chan0 + etid);
+        s_beta[etid] = __ldg(g.pre_wb + n_chan0 + etid);
       }
     }
     if (g.pb) {
@@ -405,6 +408,35 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         NOPE_EPI_BAR();
       }
 
+      if (g.pre_stats) {
+        // folded pre-norm: (mean, rstd) of each input image of the tile from its producer's partial sums
+        if (g.ipt == 1) {
+          if (etid < BN) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int k = 0; k < g.pre_parts; ++k) {
+              const float2 t = g.pre_stats[(size_t)img0 * g.pre_parts + k];
+              s1 += t.x;
+              s2 += t.y;
+            }
+            const float mean = s1 * g.pre_inv_cnt;
+            const float rstd = rsqrtf(fmaxf(s2 * g.pre_inv_cnt - mean * mean, 0.f) + g.eps);
+            s_sc[etid] = rstd;
+            s_sh[etid] = s_beta[etid] - rstd * mean * s_gamma[etid];
+          }
+        } else if (etid < g.ipt) {
+          float s1 = 0.f, s2 = 0.f;
+          if (img0 + etid < g.n_img)
+            for (int k = 0; k < g.pre_parts; ++k) {
+              const float2 t = g.pre_stats[(size_t)(img0 + etid) * g.pre_parts + k];
+              s1 += t.x;
+              s2 += t.y;
+            }
+          const float mean = s1 * g.pre_inv_cnt;
+          s_mr[etid] = make_float2(mean, rsqrtf(fmaxf(s2 * g.pre_inv_cnt - mean * mean, 0.f) + g.eps));
+        }
+        NOPE_EPI_BAR();
+      }
+
       // ---- pass 2: normalise / activate / add, in place in the swizzled staging tile
       NOPE_TS(5);
       if (g.has_res) mbar_wait(res_bar, res_phase);
@@ -424,6 +456,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
           : (long long)grow;
       uint8_t* srow = ost + cc * (kBM * 128) + row * 128;
       const bool do_norm = g.G > 0 && !(g.dbg & 4);
+      const bool pre = g.pre_stats != nullptr;
       const bool do_silu = g.silu && !(g.dbg & 2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -432,7 +465,16 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(a[j * 8 + i]);
-        if (do_norm && use_tab) {
+        if (pre && g.ipt > 1) {
+          const float2 mr = lds_f2(tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_mr) - smem) + it * 8);
+          const float4 g0 = lds_f4(a_gamma + j * 32), g1 = lds_f4(a_gamma + j * 32 + 16);
+          const float4 h0 = lds_f4(a_beta + j * 32), h1 = lds_f4(a_beta + j * 32 + 16);
+          const float w1[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float wb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const float nm = -mr.x * mr.y;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], mr.y, fmaf(nm, w1[i], wb[i]));
+        } else if ((do_norm && use_tab) || pre) {
           const float4 g0 = lds_f4(a_sc + j * 32), g1 = lds_f4(a_sc + j * 32 + 16);
           const float4 h0 = lds_f4(a_sh + j * 32), h1 = lds_f4(a_sh + j * 32 + 16);
           const float sc[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};

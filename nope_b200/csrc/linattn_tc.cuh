@@ -128,10 +128,19 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
     const uint32_t smem_base = smem_u32(smem);
     uint32_t item = 0, n_img_done = 0, dcount = 0;
     for (int img = blockIdx.x; img < p.n_img; img += gridDim.x, ++n_img_done) {
-      item += T;                                                           // pass 1 items: SIMT only
+      // parity waits only work for a thread that observes EVERY phase of a barrier: this warp walks the
+      // pass-1 items too, and it (not the SIMT warps) hands their slots back, so the producer can never
+      // run a phase ahead of it
+      for (int t = 0; t < T; ++t, ++item) {
+        mbar_wait(&full[item % kLaSlots], (item / kLaSlots) & 1);
+        mbar_wait(&ready[item % kLaSlots], (item / kLaSlots) & 1);       // SIMT warps are done with the tile
+        if (elect_one()) mbar_arrive(&empty[item % kLaSlots]);
+        __syncwarp();
+      }
       // ---- pass 2: ctx += ek^T v
       for (int t = 0; t < T; ++t) {
         const int sk = item % kLaSlots, sv = (item + 1) % kLaSlots;
+        mbar_wait(&full[sk], (item / kLaSlots) & 1);
         mbar_wait(&ready[sk], (item / kLaSlots) & 1);                      // ek written in place
         mbar_wait(&full[sv], ((item + 1) / kLaSlots) & 1);                 // v landed
         mbar_wait(&ready[sv], ((item + 1) / kLaSlots) & 1);
@@ -153,6 +162,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
       mbar_wait(ctxm_ready, n_img_done & 1);
       for (int t = 0; t < T; ++t, ++dcount) {
         const int sq = item % kLaSlots, db = dcount & 1;
+        mbar_wait(&full[sq], (item / kLaSlots) & 1);
         mbar_wait(&ready[sq], (item / kLaSlots) & 1);                      // qs written in place
         mbar_wait(&d_empty[db], ((dcount >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -202,10 +212,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 0) {
-          mbar_arrive(&ready[s]);        // nobody waits: keeps the slot's three barriers in step
-          mbar_arrive(&empty[s]);
-        }
+        if (tid == 0) mbar_arrive(&ready[s]);        // the MMA warp returns the slot
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 16));

@@ -45,6 +45,9 @@ struct ConvLayer {
   CUtensorMap wmap;
   CUtensorMap wmap_half;  // BN/2-row box for the 2-CTA kernel
   bool has_map = false;
+  // pre-norm folded into this (bias-free 1x1) layer: weights hold W diag(gamma); see GnFuse::pre_*
+  float* pre_w1 = nullptr;
+  float* pre_wb = nullptr;
 };
 
 struct NormLayer {
@@ -71,6 +74,8 @@ struct GnSpec {
   Act res;                           // residual (hi == nullptr: none)
   int res_div = 0, res_base = 0;     // residual image = (res_base + img) / res_div (hoisted prefix)
   float2* emit = nullptr;            // GroupNorm(1) partial sums of the output for a following pre-norm
+  const float2* pre_stats = nullptr; // folded pre-norm: partial sums of the INPUT images ([img][pre_parts])
+  int pre_parts = 0;
 };
 
 // bump allocator over one device slab (base == nullptr: size computation only)
@@ -311,9 +316,48 @@ struct nope_unet {
       if (make_conv(p + ".res", p + ".res_conv.weight", p + ".res_conv.bias", 1)) return -1;
     return 0;
   }
+  // to_qkv with the PreNorm GroupNorm(1) folded in (model_utils.py:226-234, 399): packed weights
+  // W' = W diag(gamma); w1[c] = sum_k W'[c,k] over the values the tensor core actually multiplies
+  // (fp16 hi, + lo in the exact-weight modes); wb[c] = sum_k W[c,k] beta[k].
+  int make_qkv_folded(const std::string& name, const std::string& wkey, const std::string& nprefix) {
+    const HostTensor& W = host.at(wkey);
+    const std::vector<float>& gm = host.at(nprefix + ".weight").data;
+    const std::vector<float>& bt = host.at(nprefix + ".bias").data;
+    const int rows = (int)W.shape[0], cin = (int)W.shape[1];
+    HostTensor Wf;
+    Wf.shape = W.shape;
+    Wf.data.resize(W.data.size());
+    std::vector<float> w1(rows), wb(rows);
+    for (int o = 0; o < rows; ++o) {
+      double s1 = 0.0, sb = 0.0;
+      for (int k = 0; k < cin; ++k) {
+        const float w = W.data[(size_t)o * cin + k];
+        const float wf = w * gm[k];
+        Wf.data[(size_t)o * cin + k] = wf;
+        const __half hi = __float2half_rn(wf);
+        s1 += (double)__half2float(hi);
+        if (precision >= 1) s1 += (double)__half2float(__float2half_rn(wf - __half2float(hi)));
+        sb += (double)w * (double)bt[k];
+      }
+      w1[o] = (float)s1;
+      wb[o] = (float)sb;
+    }
+    const std::string tmpkey = "__folded." + name;
+    host[tmpkey] = std::move(Wf);
+    if (make_conv(name, tmpkey, "", 1)) return -1;
+    host.erase(tmpkey);
+    ConvLayer& L = convs[name];
+    for (auto pr : {std::make_pair(&L.pre_w1, &w1), std::make_pair(&L.pre_wb, &wb)}) {
+      NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(pr.first), rows * sizeof(float)));
+      owned.push_back(*pr.first);
+      NOPE_CUDA(cudaMemcpy(*pr.first, pr.second->data(), rows * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+  }
   int make_linattn(const std::string& p) {
     if (make_norm(p + ".prenorm", p + ".fn.norm", 1)) return -1;
     if (make_conv(p + ".qkv", p + ".fn.fn.to_qkv.weight", "", 1)) return -1;
+    if (make_qkv_folded(p + ".qkvf", p + ".fn.fn.to_qkv.weight", p + ".fn.norm")) return -1;
     if (make_conv(p + ".out", p + ".fn.fn.to_out.0.weight", p + ".fn.fn.to_out.0.bias", 1)) return -1;
     if (make_norm(p + ".outnorm", p + ".fn.fn.to_out.1", 1)) return -1;
     return 0;
@@ -373,6 +417,7 @@ struct nope_unet {
     if (make_resblock("mid_block1") || make_resblock("mid_block2")) return -1;
     if (make_norm("mid_attn.prenorm", "mid_attn.fn.norm", 1)) return -1;
     if (make_conv("mid_attn.qkv", "mid_attn.fn.fn.to_qkv.weight", "", 1)) return -1;
+    if (make_qkv_folded("mid_attn.qkvf", "mid_attn.fn.fn.to_qkv.weight", "mid_attn.fn.norm")) return -1;
     if (make_conv("mid_attn.out", "mid_attn.fn.fn.to_out.weight", "mid_attn.fn.fn.to_out.bias", 1))
       return -1;
     for (int j = 0; j < 4; ++j) {
@@ -671,6 +716,14 @@ struct nope_unet {
       }
       f.res_div = gs->res_div;
       f.res_base = gs->res_base;
+      if (gs->pre_stats) {
+        NOPE_CHECK(!gs->norm && L.pre_w1 && L.pre_wb && L.mode == 1 && !L.bias, "pre-norm fold: bias-free 1x1 layer with folded weights");
+        f.pre_stats = gs->pre_stats;
+        f.pre_parts = gs->pre_parts;
+        f.pre_inv_cnt = 1.0f / ((float)hw * (float)L.cin);
+        f.pre_w1 = L.pre_w1;
+        f.pre_wb = L.pre_wb;
+      }
       f.out_lo = out.lo;
       static const int dbg = std::getenv("NOPE_GN_DBG") ? std::atoi(std::getenv("NOPE_GN_DBG")) : 0;
       f.dbg = dbg;
@@ -864,9 +917,17 @@ struct nope_unet {
   // to_out convolution's epilogue (fused) or come from its epilogue statistics (unfused).
   int linattn(const std::string& p, const Act& x, const Act& out, int C, int S, int n, cudaStream_t st) {
     const int eparts = fused() ? fused_emit_parts(S, C) : emit_parts_of(S * S);
-    if (gn(&norms.at(p + ".prenorm"), x.hi, TB.hi, S, C, n, false, -1, nullptr, nullptr, st, SB, eparts, 1))
-      return -1;
-    if (conv(convs.at(p + ".qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
+    if (fused()) {
+      // pre-norm folded into to_qkv: x is read once, un-normalised, by the 1x1 itself
+      GnSpec s;
+      s.pre_stats = SB;
+      s.pre_parts = eparts;
+      if (conv(convs.at(p + ".qkvf"), x, Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st, nullptr, &s)) return -1;
+    } else {
+      if (gn(&norms.at(p + ".prenorm"), x.hi, TB.hi, S, C, n, false, -1, nullptr, nullptr, st, SB, eparts, 1))
+        return -1;
+      if (conv(convs.at(p + ".qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
+    }
     if (attn_impl == 0 && S * S >= kBM) {
       if (launch_linattn_tc(TD.hi, TC.hi, n, S * S, num_sms, st)) return -1;
     } else {
@@ -889,9 +950,16 @@ struct nope_unet {
   int midattn(const Act& x, const Act& out, int C, int S, int n, cudaStream_t st) {
     NOPE_CHECK(S * S <= 32, "bottleneck attention supports at most 32 tokens");
     const int eparts = fused() ? fused_emit_parts(S, C) : emit_parts_of(S * S);
-    if (gn(&norms.at("mid_attn.prenorm"), x.hi, TB.hi, S, C, n, false, -1, nullptr, nullptr, st, SB, eparts, 1))
-      return -1;
-    if (conv(convs.at("mid_attn.qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
+    if (fused()) {
+      GnSpec s;
+      s.pre_stats = SB;
+      s.pre_parts = eparts;
+      if (conv(convs.at("mid_attn.qkvf"), x, Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st, nullptr, &s)) return -1;
+    } else {
+      if (gn(&norms.at("mid_attn.prenorm"), x.hi, TB.hi, S, C, n, false, -1, nullptr, nullptr, st, SB, eparts, 1))
+        return -1;
+      if (conv(convs.at("mid_attn.qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
+    }
     midattn_kernel<<<n, 128, 0, st>>>(TD.hi, TC.hi, S * S);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
