@@ -456,100 +456,115 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
           : (long long)grow;
       uint8_t* srow = ost + cc * (kBM * 128) + row * 128;
       const bool do_norm = g.G > 0 && !(g.dbg & 4);
-      const bool pre = g.pre_stats != nullptr;
       const bool do_silu = g.silu && !(g.dbg & 2);
+      const bool pre = g.pre_stats != nullptr;
+      // Every step below runs over all 64 values of the thread with its (launch-uniform) condition tested
+      // OUTSIDE the unrolled loop: one long basic block per step, so the scheduler can keep tens of
+      // independent shared-memory loads / MUFU chains in flight (with the tests inside a per-octet loop
+      // every octet fell apart into five short blocks and the pass ran at a quarter of the issue rate).
+      float* f = reinterpret_cast<float*>(a);
+      if (pre && g.ipt > 1) {
+        const float2 mr = lds_f2(tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_mr) - smem) + it * 8);
+        const float nm = -mr.x * mr.y;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int lc = cc * 64 + j * 8;
-        uint4* sp = reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4));
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(a[j * 8 + i]);
-        if (pre && g.ipt > 1) {
-          const float2 mr = lds_f2(tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_mr) - smem) + it * 8);
-          const float4 g0 = lds_f4(a_gamma + j * 32), g1 = lds_f4(a_gamma + j * 32 + 16);
-          const float4 h0 = lds_f4(a_beta + j * 32), h1 = lds_f4(a_beta + j * 32 + 16);
-          const float w1[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float wb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-          const float nm = -mr.x * mr.y;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], mr.y, fmaf(nm, w1[i], wb[i]));
-        } else if ((do_norm && use_tab) || pre) {
-          const float4 g0 = lds_f4(a_sc + j * 32), g1 = lds_f4(a_sc + j * 32 + 16);
-          const float4 h0 = lds_f4(a_sh + j * 32), h1 = lds_f4(a_sh + j * 32 + 16);
-          const float sc[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
-        } else if (do_norm) {
-          const float2 mr = lds_f2(a_mr + s_og[lc >> 3] * 8);
-          const float4 g0 = lds_f4(a_gamma + j * 32), g1 = lds_f4(a_gamma + j * 32 + 16);
-          const float4 h0 = lds_f4(a_beta + j * 32), h1 = lds_f4(a_beta + j * 32 + 16);
-          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float bt[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] - mr.x, mr.y * gm[i], bt[i]);
+        for (int j = 0; j < 16; ++j) {
+          const float4 w1 = lds_f4(a_gamma + j * 16), wb = lds_f4(a_beta + j * 16);
+          f[4 * j + 0] = fmaf(f[4 * j + 0], mr.y, fmaf(nm, w1.x, wb.x));
+          f[4 * j + 1] = fmaf(f[4 * j + 1], mr.y, fmaf(nm, w1.y, wb.y));
+          f[4 * j + 2] = fmaf(f[4 * j + 2], mr.y, fmaf(nm, w1.z, wb.z));
+          f[4 * j + 3] = fmaf(f[4 * j + 3], mr.y, fmaf(nm, w1.w, wb.w));
         }
-        if (do_silu) {
+      } else if ((do_norm && use_tab) || pre) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
+        for (int j = 0; j < 16; ++j) {
+          const float4 sc = lds_f4(a_sc + j * 16), sh = lds_f4(a_sh + j * 16);
+          f[4 * j + 0] = fmaf(f[4 * j + 0], sc.x, sh.x);
+          f[4 * j + 1] = fmaf(f[4 * j + 1], sc.y, sh.y);
+          f[4 * j + 2] = fmaf(f[4 * j + 2], sc.z, sh.z);
+          f[4 * j + 3] = fmaf(f[4 * j + 3], sc.w, sh.w);
         }
-        if (g.pb) {
+      } else if (do_norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 mr = lds_f2(a_mr + s_og[(cc * 64 + j * 8) >> 3] * 8);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 gm = lds_f4(a_gamma + j * 32 + h2 * 16), bt = lds_f4(a_beta + j * 32 + h2 * 16);
+            float* ff = f + j * 8 + h2 * 4;
+            ff[0] = fmaf(ff[0] - mr.x, mr.y * gm.x, bt.x);
+            ff[1] = fmaf(ff[1] - mr.x, mr.y * gm.y, bt.y);
+            ff[2] = fmaf(ff[2] - mr.x, mr.y * gm.z, bt.z);
+            ff[3] = fmaf(ff[3] - mr.x, mr.y * gm.w, bt.w);
+          }
+        }
+      }
+      if (do_silu) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) f[i] = silu_ftz(f[i]);
+      }
+      if (g.pb) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
           const uint4 pv = lds_u4(a_pb + j * 16);
           const __half2* hp = reinterpret_cast<const __half2*>(&pv);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
             const float2 t = __half22float2(hp[k2]);
-            f[2 * k2] += t.x;
-            f[2 * k2 + 1] += t.y;
+            f[j * 8 + 2 * k2] += t.x;
+            f[j * 8 + 2 * k2 + 1] += t.y;
           }
         }
-        if (g.has_res) {
-          const uint4 rv = *sp;
+      }
+      if (g.has_res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(srow + ((j ^ (row & 7)) << 4));
           const __half2* hr = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
             const float2 t = __half22float2(hr[k2]);
-            f[2 * k2] += t.x;
-            f[2 * k2 + 1] += t.y;
+            f[j * 8 + 2 * k2] += t.x;
+            f[j * 8 + 2 * k2 + 1] += t.y;
           }
-          if (g.res_lo && row_ok) {
-            const uint4 rl = *reinterpret_cast<const uint4*>(g.res_lo + rpix * p.n_total + n_chan0 + lc);
+        }
+        if (g.res_lo && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 rl = *reinterpret_cast<const uint4*>(g.res_lo + rpix * p.n_total + n_chan0 + cc * 64 + j * 8);
             const __half2* hl = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
             for (int k2 = 0; k2 < 4; ++k2) {
               const float2 t = __half22float2(hl[k2]);
-              f[2 * k2] += t.x;
-              f[2 * k2 + 1] += t.y;
+              f[j * 8 + 2 * k2] += t.x;
+              f[j * 8 + 2 * k2 + 1] += t.y;
             }
           }
         }
+      }
+      const bool want_lo = g.out_lo && row_ok;
+      const bool want_emit = g.emit != nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
         uint4 w;
-        w.x = pack_half2(f[0], f[1]);
-        w.y = pack_half2(f[2], f[3]);
-        w.z = pack_half2(f[4], f[5]);
-        w.w = pack_half2(f[6], f[7]);
-        *sp = w;
-        if (g.out_lo && row_ok) {
+        w.x = pack_half2(f[j * 8 + 0], f[j * 8 + 1]);
+        w.y = pack_half2(f[j * 8 + 2], f[j * 8 + 3]);
+        w.z = pack_half2(f[j * 8 + 4], f[j * 8 + 5]);
+        w.w = pack_half2(f[j * 8 + 6], f[j * 8 + 7]);
+        *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) = w;
+        if (want_lo || want_emit) {
           const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
           uint4 wl;
           uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
             const float2 t = __half22float2(hw2[k2]);
-            pl[k2] = pack_half2(f[2 * k2] - t.x, f[2 * k2 + 1] - t.y);
-          }
-          *reinterpret_cast<uint4*>(g.out_lo + (size_t)grow * p.n_total + n_chan0 + lc) = wl;
-        }
-        if (g.emit) {       // statistics of the values as stored (what the consumer reads)
-          const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
-#pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2) {
-            const float2 t = __half22float2(hw2[k2]);
-            e1 += t.x + t.y;
+            pl[k2] = pack_half2(f[j * 8 + 2 * k2] - t.x, f[j * 8 + 2 * k2 + 1] - t.y);
+            e1 += t.x + t.y;                 // statistics of the values as stored (what the consumer reads)
             e2 = fmaf(t.x, t.x, e2);
             e2 = fmaf(t.y, t.y, e2);
           }
+          if (want_lo)
+            *reinterpret_cast<uint4*>(g.out_lo + (size_t)grow * p.n_total + n_chan0 + cc * 64 + j * 8) = wl;
         }
       }
       if (g.has_res) res_phase ^= 1;
