@@ -234,6 +234,44 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
   int acc = 0, obuf = 0;
   uint32_t acc_phase = 0, res_phase = 0;
   int iter = 0;
+  // The residual tile of tile t is TMA-loaded into the staging buffer tile t will be written to (same box /
+  // swizzle as the store).  It is issued by the thread that issues the stores, as soon as the store that
+  // last used the buffer has read it: right after tile t-1's store (or before the loop for the first
+  // tile), so the load latency hides behind tile t's accumulator read-out and tile sync.
+  auto stage_residual = [&](int t, int buf) {
+    if (t >= num_tiles) return;
+    const int mp = t / p.n_tiles;
+    const int nt = t - mp * p.n_tiles;
+    const int mt2 = 2 * mp + (int)rank;
+    if constexpr (S::kOutBufs == 2) tma_store_wait_read1();
+    else tma_store_wait_read0();
+    if (g.has_res && mt2 < p.m_tiles) {
+      int bb, yy;
+      conv_tile_coords(p, mt2, bb, yy);
+      const int rb = g.res_div > 0 ? (g.res_base + bb) / g.res_div : bb;
+      uint8_t* dst = out_stage + buf * S::kOutBytes;
+      mbar_expect_tx(res_bar, S::kOutBytes);
+#pragma unroll 1
+      for (int c2 = 0; c2 < kNS; ++c2)
+        tma_load_4d(dst + c2 * (kBM * 128), &p.rmap, res_bar, nt * BN + c2 * 64, 0, yy, rb);
+    }
+  };
+  if (etid == 0) stage_residual(tile0, 0);
+  // pose-bias rows of the NEXT tile are fetched into a register while the current tile is normalised
+  uint4 pb_next = make_uint4(0, 0, 0, 0);
+  auto fetch_pb = [&](int t) {
+    if (!g.pb || t >= num_tiles || etid >= g.ipt * kOct) return;
+    const int mp = t / p.n_tiles;
+    const int nt = t - mp * p.n_tiles;
+    const int mt2 = 2 * mp + (int)rank;
+    const int i0 = p.tiles_per_img > 0 ? mt2 / g.mt : mt2 * g.ipt;
+    const int ii = etid / kOct, o8 = etid - ii * kOct;
+    pb_next = make_uint4(0, 0, 0, 0);
+    if (i0 + ii < g.n_img)
+      pb_next = *reinterpret_cast<const uint4*>(g.pb + (size_t)(i0 + ii) * g.pb_stride + g.pb_off + nt * BN + o8 * 8);
+  };
+  static_assert(8 * kOct <= kEpiThreads, "one thread per (image, octet) of the pose-bias rows");
+  fetch_pb(tile0);
 #define NOPE_TS(k) do { if (g.ts && etid == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 8 + (k)] = global_ns(); } while (0)
   for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
     NOPE_TS(0);
@@ -246,22 +284,6 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
     conv_tile_coords(p, m_tile, b0, y0);
     const int img0 = p.tiles_per_img > 0 ? m_tile / g.mt : m_tile * g.ipt;   // first image of the tile
     uint8_t* ost = out_stage + obuf * S::kOutBytes;
-    // staging buffer: free once the TMA store that last used it has read it; then the residual tile is
-    // loaded into it (same box / swizzle as the store).  Issued after pass 1, so that the store drain and
-    // the load latency overlap the accumulator read-out and the tile sync.
-    auto stage_residual = [&]() {
-      if (etid == 0) {
-        if constexpr (S::kOutBufs == 2) tma_store_wait_read1();
-        else tma_store_wait_read0();
-        if (g.has_res && live) {
-          const int rb = g.res_div > 0 ? (g.res_base + b0) / g.res_div : b0;
-          mbar_expect_tx(res_bar, S::kOutBytes);
-#pragma unroll 1
-          for (int c2 = 0; c2 < kNS; ++c2)
-            tma_load_4d(ost + c2 * (kBM * 128), &p.rmap, res_bar, n_chan0 + c2 * 64, 0, y0, rb);
-        }
-      }
-    };
     if (etid < BN && (tile == tile0 || p.n_tiles > 1)) {     // channel parameters of this N-tile
       s_bias[etid] = p.bias ? __ldg(p.bias + n_chan0 + etid) : 0.f;
       if (g.G > 0) {
@@ -272,18 +294,11 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         s_beta[etid] = __ldg(g.pre_wb + n_chan0 + etid);
       }
     }
-    if (g.pb) {
-      for (int i = etid; i < g.ipt * kOct; i += kEpiThreads) {
-        const int ii = i / kOct, o8 = i - ii * kOct;
-        const int img = img0 + ii;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (img < g.n_img)
-          v = *reinterpret_cast<const uint4*>(g.pb + (size_t)img * g.pb_stride + g.pb_off + n_chan0 + o8 * 8);
-        *reinterpret_cast<uint4*>(s_pb + ii * BN + o8 * 8) = v;
-      }
-    }
+    if (g.pb && etid < g.ipt * kOct)
+      *reinterpret_cast<uint4*>(s_pb + (etid / kOct) * BN + (etid % kOct) * 8) = pb_next;
     NOPE_EPI_BAR();
     NOPE_TS(1);
+    fetch_pb(tile + tile_step);
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     NOPE_TS(2);
@@ -302,7 +317,6 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         else mbar_arrive_remote(&tempty_bar[acc], 0);
       }
     }
-    if (!live || g.G == 0 || g.expected == 1) stage_residual();
     if (live) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -359,7 +373,6 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
             st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2, make_uint2(__float_as_uint(Sx), g.epoch));
             st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2 + 1, make_uint2(__float_as_uint(Qx), g.epoch));
           }
-          stage_residual();
           if (etid < g.expected * npairs * 2) {
             uint2 u = ld_volatile_u2(xp + etid);
             if (u.y != g.epoch && !(g.dbg & 1)) {
@@ -598,6 +611,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         tma_store_commit();
       }
     }
+    if (etid == 0) stage_residual(tile + tile_step, obuf ^ (S::kOutBufs - 1));
     obuf ^= S::kOutBufs - 1;
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;

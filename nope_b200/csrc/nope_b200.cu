@@ -100,7 +100,7 @@ struct nope_unet {
   // 0: fp16 operands; 1: exact weights (W_hi + W_lo K-segments, 2x the MMA work); 2: split precision
   // (exact weights + activations carried as hi + lo: A_hi W_hi + A_hi W_lo + A_lo W_hi, 3x)
   int precision = 0;
-  int attn_impl = 1;         // LinearAttention core: 0 tcgen05 (token counts >= 128), 1 CUDA cores
+  int attn_impl = 0;         // LinearAttention core: 0 tcgen05 (token counts >= 128), 1 CUDA cores
   int metric = 0;            // NOPE_METRIC_* of the fused scoring
   float occ_threshold = 0.2f;
   int chunk = 642;
@@ -935,7 +935,11 @@ struct nope_unet {
       NOPE_CUDA(cudaGetLastError());
     }
     ++launches;
-    if (fused()) {
+    // to_out (K = 128: two K-steps per tile) is bound by its epilogue, not by its GEMM: the fused
+    // GroupNorm(1) epilogue with its cross-tile exchange measured slower than the plain convolution plus one
+    // normalisation pass (319 vs 244 us at 32x32), so this layer keeps the two-kernel form unless the
+    // split-precision mode needs the (hi, lo) output pair
+    if (fused() && split()) {
       GnSpec s;
       s.norm = &norms.at(p + ".outnorm");
       s.res = x;

@@ -1,0 +1,64 @@
+"""GPU: BASELINE configs[2] at FULL size -- 8 queries x the shipped 2562-pose level-3 grid (20 496
+hypotheses) -- against tests/golden/cfg2_b8_n2562.npz, which oracle/make_golden.py --only-cfg2 generated
+with the UNMODIFIED reference modules (encoder, UNet, "l2" retrieval, topk(5); ~40 CPU-minutes).
+Checked per precision mode: similarity rows, the whole top-5 of every query (swaps of ranks 2-5 are
+counted and reported, rank 1 must be identical), per-hypothesis embedding norms and three full templates."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import log, max_rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg2_b8_n2562.npz")
+
+# (embedding rel-L2, similarity max-rel): the north-star 1e-3 for the split-precision mode; the fast fp16 mode
+# is gated on scores + argmax (embeddings measured 1.2-1.5e-3, see tests/test_unet_gpu.py)
+TOL = {"parity": (1e-3, 1e-3), "fp16": (2e-3, 1e-3)}
+
+
+def _inputs():
+    from oracle import inputs
+    g = np.load(FIX)
+    R3 = g["level3_all"]
+    relR = torch.stack([inputs.relative_rot6d(R3, R3[int(i)]) for i in g["ref_idx"]])
+    return g, relR
+
+
+@pytest.mark.skipif(not os.path.exists(FIX), reason="cfg2 fixture not generated")
+@pytest.mark.parametrize("precision", ["fp16", "parity"])
+def test_cfg2_full_size_against_reference(precision, gpu_model, gpu_model_parity):
+    m = gpu_model if precision == "fp16" else gpu_model_parity
+    g, relR = _inputs()
+    B, N = relR.shape[:2]
+    assert (B, N) == (8, 2562)
+    rf, qf = torch.from_numpy(g["ref_feat"]), torch.from_numpy(g["query_feat"])
+    out = m.u_net.sweep(rf, relR, query_feat=qf, want_emb=True, k=5)
+    sim, topi, emb = out["sim"], out["topi"].cpu(), out["emb"]
+    e_sim = max_rel(sim, torch.from_numpy(g["similarity"]))
+    e_l2 = max_rel(emb.flatten(2).norm(dim=2), torch.from_numpy(g["emb_l2"]))
+    e_emb = max(rel_l2(emb[b, n], torch.from_numpy(g[f"emb_b{b}_n{n}"])) for b, n in ((0, 0), (3, 1000), (7, 2561)))
+    ref_idx = torch.from_numpy(g["nearest_idx"])
+    swaps = int((topi[:, 1:] != ref_idx[:, 1:]).sum())
+    set_diff = sum(len(set(topi[b].tolist()) ^ set(ref_idx[b].tolist())) // 2 for b in range(B))
+    log("cfg2_full", precision=precision, sim_max_rel=e_sim, emb_rel_l2=e_emb, emb_norm_max_rel=e_l2,
+        rank1_equal=bool(torch.equal(topi[:, 0], ref_idx[:, 0])), rank2to5_swaps=swaps, top5_set_differences=set_diff,
+        launches=m.u_net.last_launch_count)
+    emb_tol, sim_tol = TOL[precision]
+    assert e_sim < sim_tol and e_emb < emb_tol
+    assert torch.equal(topi[:, 0], ref_idx[:, 0])                       # bit-exact argmax pose index
+    if precision == "parity":
+        assert torch.equal(topi, ref_idx)                               # and the whole top-5
+    else:
+        # a swap is only tolerated between candidates the reference itself separates by < 2e-3 relative
+        s_ref = torch.from_numpy(g["similarity"])
+        for b in range(B):
+            for r in range(5):
+                i, j = int(topi[b, r]), int(ref_idx[b, r])
+                if i != j:
+                    assert abs(float(s_ref[b, i] - s_ref[b, j])) / abs(float(s_ref[b, j])) < 2e-3, (b, r, i, j)
+    # the sweep never lets hypotheses of different queries interact: one query alone reproduces its row
+    one = m.u_net.sweep(rf[5:6], relR[5:6], query_feat=qf[5:6], want_emb=False, k=5)
+    assert torch.equal(one["sim"][0], sim[5]) and torch.equal(one["topi"][0].cpu(), topi[5])

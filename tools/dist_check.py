@@ -22,11 +22,12 @@ g = torch.Generator().manual_seed(3)
 rf = torch.randn(2, 8, 32, 32, generator=g) * 1.5
 qf = torch.randn(2, 8, 32, 32, generator=g) * 1.5
 ok = True
-for n in (162, 643):     # 643: uneven shards
+ss = ShardedSweep()
+for n in (7, 162, 643):     # 7: shards of one pose / empty shards (k > shard size); 643: uneven shards
     poses, _ = synthetic_pose_batch(642, 2)
     poses = poses[:, :n] if n <= 642 else torch.cat([poses, poses[:, :1]], dim=1)
     single = model.u_net.sweep(rf, poses, query_feat=qf, want_emb=False, k=5)
-    sim, topi, _ = ShardedSweep().sweep(model.u_net, rf.to(dev), poses.to(dev), qf.to(dev), k=5)
+    sim, topi, _ = ss.sweep(model.u_net, rf.to(dev), poses.to(dev), qf.to(dev), k=5)
     same = torch.equal(sim, single["sim"]) and torch.equal(topi, single["topi"])
     ok = ok and same
     print(f"rank {rank} n={n}: sharded == single: {same}; top5 {topi[0].tolist()}", flush=True)

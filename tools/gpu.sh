@@ -28,6 +28,9 @@ case "$step" in
             ncu -i /tmp/prof_conv.ncu-rep --page raw --csv > gpurun_out/prof_conv_raw.csv 2>/dev/null ;;
   ncu_mem)  run "ncu full: memory-bound" 900 ncu --profile-from-start off --set full --clock-control none -k regex:'gn_|linattn|final_conv|bcast|midattn|pose_embed|topk' -c 40 -o /tmp/prof_mem -f python tools/profile_step.py > gpurun_out/ncu_mem.log 2>&1
             ncu -i /tmp/prof_mem.ncu-rep --page raw --csv > gpurun_out/prof_mem_raw.csv 2>/dev/null ;;
+  dist)     N=${NGPU:-2}; run "dist_check N=$N" 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; tail -12 gpurun_out/dist_check_$N.log ;;
+  benchN)   N=${NGPU:-2}; run "bench N=$N weak" 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.log 2>&1; tail -1 gpurun_out/bench_n$N.log | cut -c 1-600
+            run "bench N=$N strong 10248" 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --global-poses 10248 > gpurun_out/bench_strong_n$N.log 2>&1; tail -1 gpurun_out/bench_strong_n$N.log | cut -c 1-600 ;;
   sanitize) run "memcheck smoke" 1200 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck.log 2>&1; tail -5 gpurun_out/sanitizer_memcheck.log ;;
   *) echo "unknown step $step" ;;
 esac
