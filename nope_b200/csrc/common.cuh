@@ -233,6 +233,31 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool bf16) {
 // ~10-instruction Newton sequence, which made the GroupNorm+SiLU pass issue-bound.
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// 16-bit storage of activations / weights: fp16 (default) or bf16 (engine precision "bf16",
+// BASELINE configs[2]).  Pointers stay `__half*` (opaque 16-bit lanes); `bf` selects the conversion.
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool bf) {
+  uint32_t r;
+  if (bf) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));       // {hi, lo} = {b, a}
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    r = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, bool bf) {
+  if (bf) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ float ld16(const __half* p, bool bf) {
+  const unsigned short u = *reinterpret_cast<const unsigned short*>(p);
+  return bf ? __uint_as_float(static_cast<uint32_t>(u) << 16) : __half2float(*p);
+}
+__device__ __forceinline__ void st16(__half* p, float v, bool bf) {
+  if (bf) *reinterpret_cast<unsigned short*>(p) = static_cast<unsigned short>(pack2(v, 0.f, true) & 0xffffu);
+  else *p = __float2half_rn(v);
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -108,6 +108,7 @@ struct ConvParams {
   // model_utils.py:161-165): n_par == 4 makes n_tile enumerate (parity, channel tile); parity
   // (py, px) shifts every tap by (+py, +px), reads weight rows parity * n_per_par + ..., and
   // stores through omap[parity] (the stride-2 sub-lattice of the 2H x 2W output).
+  int bf16;           // operands and the stored output are bf16 instead of fp16 (plain / GroupNorm-fused epilogues)
   int n_par;          // 1 or 4
   int n_tiles_par;    // channel tiles per parity (== n_tiles when n_par == 1)
   int src_w, src_hw;  // n_par == 4: width / pixels of one SOURCE image (out_lo addressing)
@@ -316,9 +317,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint8_t*
       st[2 * j] = s;
       st[2 * j + 1] = q2;
       const int phys = (hh * 4 + j) ^ (row & 7);   // SWIZZLE_128B: chunk index XOR (row mod 8)
+      const bool bf = p.bf16 != 0;
       *reinterpret_cast<uint4*>(srow + phys * 16) =
-          make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]),
-                     pack_half2(f[6], f[7]));
+          make_uint4(pack2(f[0], f[1], bf), pack2(f[2], f[3], bf), pack2(f[4], f[5], bf), pack2(f[6], f[7], bf));
     }
     if (p.stats) {
       const bool small = p.stats_hw < 32;            // 4x4 images: two per warp
@@ -465,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_f16(kBM, BN, false);
+    const uint32_t idesc = make_idesc_f16(kBM, BN, false) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;

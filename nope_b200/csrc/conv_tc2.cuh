@@ -256,7 +256,8 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         tma_load_4d(dst + c2 * (kBM * 128), &p.rmap, res_bar, nt * BN + c2 * 64, 0, yy, rb);
     }
   };
-  if (etid == 0) stage_residual(tile0, 0);
+  const bool res_late = (g.dbg & 8) != 0;      // development: issue the residual load inside the tile (after the publish)
+  if (etid == 0 && !res_late) stage_residual(tile0, 0);
   // pose-bias rows of the NEXT tile are fetched into a register while the current tile is normalised
   uint4 pb_next = make_uint4(0, 0, 0, 0);
   auto fetch_pb = [&](int t) {
@@ -294,11 +295,12 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         s_beta[etid] = __ldg(g.pre_wb + n_chan0 + etid);
       }
     }
+    if (g.dbg & 16) fetch_pb(tile);
     if (g.pb && etid < g.ipt * kOct)
       *reinterpret_cast<uint4*>(s_pb + (etid / kOct) * BN + (etid % kOct) * 8) = pb_next;
     NOPE_EPI_BAR();
     NOPE_TS(1);
-    fetch_pb(tile + tile_step);
+    if (!(g.dbg & 16)) fetch_pb(tile + tile_step);
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     NOPE_TS(2);
@@ -317,6 +319,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         else mbar_arrive_remote(&tempty_bar[acc], 0);
       }
     }
+    if (res_late && etid == 0 && (!live || g.G == 0 || g.expected == 1)) stage_residual(tile, obuf);
     if (live) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -373,6 +376,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
             st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2, make_uint2(__float_as_uint(Sx), g.epoch));
             st_volatile_u2(xp + ((size_t)slot * npairs + etid) * 2 + 1, make_uint2(__float_as_uint(Qx), g.epoch));
           }
+          if (res_late && etid == 0) stage_residual(tile, obuf);
           if (etid < g.expected * npairs * 2) {
             uint2 u = ld_volatile_u2(xp + etid);
             if (u.y != g.epoch && !(g.dbg & 1)) {
@@ -476,6 +480,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
       // independent shared-memory loads / MUFU chains in flight (with the tests inside a per-octet loop
       // every octet fell apart into five short blocks and the pass ran at a quarter of the issue rate).
       float* f = reinterpret_cast<float*>(a);
+      const bool bf = p.bf16 != 0;
       if (pre && g.ipt > 1) {
         const float2 mr = lds_f2(tok + (uint32_t)(reinterpret_cast<uint8_t*>(s_mr) - smem) + it * 8);
         const float nm = -mr.x * mr.y;
@@ -519,10 +524,10 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 pv = lds_u4(a_pb + j * 16);
-          const __half2* hp = reinterpret_cast<const __half2*>(&pv);
+          const uint32_t* hp = reinterpret_cast<const uint32_t*>(&pv);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
-            const float2 t = __half22float2(hp[k2]);
+            const float2 t = unpack2(hp[k2], bf);
             f[j * 8 + 2 * k2] += t.x;
             f[j * 8 + 2 * k2 + 1] += t.y;
           }
@@ -532,10 +537,10 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 rv = *reinterpret_cast<const uint4*>(srow + ((j ^ (row & 7)) << 4));
-          const __half2* hr = reinterpret_cast<const __half2*>(&rv);
+          const uint32_t* hr = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
-            const float2 t = __half22float2(hr[k2]);
+            const float2 t = unpack2(hr[k2], bf);
             f[j * 8 + 2 * k2] += t.x;
             f[j * 8 + 2 * k2 + 1] += t.y;
           }
@@ -559,18 +564,18 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint4 w;
-        w.x = pack_half2(f[j * 8 + 0], f[j * 8 + 1]);
-        w.y = pack_half2(f[j * 8 + 2], f[j * 8 + 3]);
-        w.z = pack_half2(f[j * 8 + 4], f[j * 8 + 5]);
-        w.w = pack_half2(f[j * 8 + 6], f[j * 8 + 7]);
+        w.x = pack2(f[j * 8 + 0], f[j * 8 + 1], bf);
+        w.y = pack2(f[j * 8 + 2], f[j * 8 + 3], bf);
+        w.z = pack2(f[j * 8 + 4], f[j * 8 + 5], bf);
+        w.w = pack2(f[j * 8 + 6], f[j * 8 + 7], bf);
         *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) = w;
         if (want_lo || want_emit) {
-          const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+          const uint32_t* hw2 = reinterpret_cast<const uint32_t*>(&w);
           uint4 wl;
           uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
-            const float2 t = __half22float2(hw2[k2]);
+            const float2 t = unpack2(hw2[k2], bf);
             pl[k2] = pack_half2(f[j * 8 + 2 * k2] - t.x, f[j * 8 + 2 * k2 + 1] - t.y);
             e1 += t.x + t.y;                 // statistics of the values as stored (what the consumer reads)
             e2 = fmaf(t.x, t.x, e2);
@@ -611,7 +616,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
         tma_store_commit();
       }
     }
-    if (etid == 0) stage_residual(tile + tile_step, obuf ^ (S::kOutBufs - 1));
+    if (etid == 0 && !res_late) stage_residual(tile + tile_step, obuf ^ (S::kOutBufs - 1));
     obuf ^= S::kOutBufs - 1;
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
@@ -706,7 +711,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     }
   } else if (warp == 1 && leader) {
     // ===================== MMA issuer (leader CTA only) =====================
-    constexpr uint32_t idesc = make_idesc_f16(2 * kBM, BN, false);
+    const uint32_t idesc = make_idesc_f16(2 * kBM, BN, false) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;

@@ -19,7 +19,7 @@ namespace nope {
 // the "exact weights" K-segments of the split-precision modes (22 significant bits per weight).
 __global__ void pack_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst,
                                    int cout, int cin, int taps, int dst_row_stride,
-                                   int dst_col_off, int lo_off = 0) {
+                                   int dst_col_off, int lo_off = 0, int bf16 = 0) {
   const long long total = (long long)cout * cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -27,8 +27,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __half* __rest
     const int t = (int)((i / cin) % taps);
     const int o = (int)(i / ((long long)cin * taps));
     const float w = src[((long long)o * cin + c) * taps + t];
-    const __half hi = __float2half_rn(w);
     __half* d = dst + (long long)o * dst_row_stride + dst_col_off + t * cin + c;
+    if (bf16) { st16(d, w, true); continue; }
+    const __half hi = __float2half_rn(w);
     d[0] = hi;
     if (lo_off > 0) d[lo_off] = __float2half_rn(w - __half2float(hi));
   }
@@ -69,7 +70,7 @@ __global__ void fold_upconv_kernel(const float* __restrict__ src, float* __restr
 // ----------------------------------------------------------------------------
 __global__ void pose_embed_kernel(const float* __restrict__ poses, const float* __restrict__ w,
                                   const float* __restrict__ b, __half* __restrict__ cs, int n_hyp,
-                                  int rot_dim, int cemb) {
+                                  int rot_dim, int cemb, bool bf = false) {
   const int h = blockIdx.x;
   if (h >= n_hyp) return;
   __shared__ float sp[8];      // rot_dim <= 8 (6-D rotations); padded so vectorised reads stay inside
@@ -78,7 +79,7 @@ __global__ void pose_embed_kernel(const float* __restrict__ poses, const float* 
   for (int j = threadIdx.x; j < cemb; j += blockDim.x) {
     float a = b[j];
     for (int i = 0; i < rot_dim; ++i) a = fmaf(w[j * rot_dim + i], sp[i], a);
-    cs[(long long)h * cemb + j] = __float2half_rn(silu_f(a));
+    st16(cs + (long long)h * cemb + j, silu_f(a), bf);
   }
 }
 
@@ -88,7 +89,8 @@ __global__ void pose_embed_kernel(const float* __restrict__ poses, const float* 
 // ----------------------------------------------------------------------------
 __global__ void init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ bias, __half* __restrict__ out, int B,
-                                 int Cl, int H, int W, int Cout, __half* __restrict__ out_lo = nullptr) {
+                                 int Cl, int H, int W, int Cout, __half* __restrict__ out_lo = nullptr,
+                                 bool bf = false) {
   const long long total = (long long)B * H * W * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -108,6 +110,7 @@ __global__ void init_conv_kernel(const float* __restrict__ x, const float* __res
                      w[((o * Cl + c) * 3 + ky) * 3 + kx], acc);
         }
       }
+    if (bf) { st16(out + i, acc, true); continue; }
     const __half hi = __float2half_rn(acc);
     out[i] = hi;
     if (out_lo) out_lo[i] = __float2half_rn(acc - __half2float(hi));
@@ -125,7 +128,7 @@ __global__ void bcast_add_kernel(const __half* __restrict__ src, const int* __re
                                  const __half* __restrict__ pb, int pb_stride, int pb_off,
                                  __half* __restrict__ out, int n_hyp, int hw, int C,
                                  const __half* __restrict__ src_lo = nullptr,
-                                 __half* __restrict__ out_lo = nullptr) {
+                                 __half* __restrict__ out_lo = nullptr, bool bf = false) {
   const int octs = C / 8;
   const long long total = (long long)n_hyp * hw * octs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -180,12 +183,12 @@ __global__ void bcast_add_kernel(const __half* __restrict__ src, const int* __re
     }
     if (pb) {
       const uint4 a = *reinterpret_cast<const uint4*>(pb + (long long)h * pb_stride + pb_off + o * 8);
-      __half2* vv = reinterpret_cast<__half2*>(&v);
-      const __half2* aa = reinterpret_cast<const __half2*>(&a);
+      uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
+      const uint32_t* aa = reinterpret_cast<const uint32_t*>(&a);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 x = __half22float2(vv[q]), y = __half22float2(aa[q]);
-        vv[q] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+        const float2 x = unpack2(vv[q], bf), y = unpack2(aa[q], bf);
+        vv[q] = pack2(x.x + y.x, x.y + y.y, bf);
       }
     }
     *reinterpret_cast<uint4*>(out + ((long long)h * hw + p) * C + o * 8) = v;
@@ -285,6 +288,7 @@ struct GnApplyArgs {
   int hw, C, G, nslab;
   int silu;
   float eps;
+  int bf16;               // 16-bit storage format of x / y / pb / res
 };
 
 __device__ __forceinline__ uint4 ld_stream16(const __half* p) {
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
   const int r = threadIdx.x / octs;
   const int slab = blockIdx.x, h = blockIdx.y;
   float scale[8], shift[8], pbv[8];
+  const bool bf = a.bf16 != 0;
   if (a.stats) {
     // independent loads first (affine parameters), then the partial statistics
     float4 g0 = *reinterpret_cast<const float4*>(a.gamma + o * 8);
@@ -358,10 +363,10 @@ __global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
   }
   if (PB) {
     const uint4 pv = *reinterpret_cast<const uint4*>(a.pb + (long long)h * a.pb_stride + a.pb_off + o * 8);
-    const __half2* hp = reinterpret_cast<const __half2*>(&pv);
+    const uint32_t* hp = reinterpret_cast<const uint32_t*>(&pv);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 t = __half22float2(hp[q]);
+      const float2 t = unpack2(hp[q], bf);
       pbv[2 * q] = t.x;
       pbv[2 * q + 1] = t.y;
     }
@@ -395,11 +400,11 @@ __global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
       for (int u = 0; u < kGnUnroll; ++u) {
         const int p = p0 + u * rows;
         if (p >= pend) break;
-        const __half2* hv = reinterpret_cast<const __half2*>(&xv[u]);
+        const uint32_t* hv = reinterpret_cast<const uint32_t*>(&xv[u]);
         float f[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 t = __half22float2(hv[q]);
+          const float2 t = unpack2(hv[q], bf);
           f[2 * q] = t.x;
           f[2 * q + 1] = t.y;
         }
@@ -411,26 +416,26 @@ __global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
           f[i] = t;
         }
         if (RES) {
-          const __half2* hr = reinterpret_cast<const __half2*>(&rv[u]);
+          const uint32_t* hr = reinterpret_cast<const uint32_t*>(&rv[u]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 t = __half22float2(hr[q]);
+            const float2 t = unpack2(hr[q], bf);
             f[2 * q] += t.x;
             f[2 * q + 1] += t.y;
           }
         }
         uint4 w;
-        w.x = pack_half2(f[0], f[1]);
-        w.y = pack_half2(f[2], f[3]);
-        w.z = pack_half2(f[4], f[5]);
-        w.w = pack_half2(f[6], f[7]);
+        w.x = pack2(f[0], f[1], bf);
+        w.y = pack2(f[2], f[3], bf);
+        w.z = pack2(f[4], f[5], bf);
+        w.w = pack2(f[6], f[7], bf);
         *reinterpret_cast<uint4*>(yp + (long long)p * a.C) = w;
         if (a.emit) {
           // statistics of the values as stored (fp16-rounded), what the consumer will read
-          const __half2* hw2 = reinterpret_cast<const __half2*>(&w);
+          const uint32_t* hw2 = reinterpret_cast<const uint32_t*>(&w);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 t = __half22float2(hw2[q]);
+            const float2 t = unpack2(hw2[q], bf);
             es += t.x + t.y;
             ess = fmaf(t.x, t.x, ess);
             ess = fmaf(t.y, t.y, ess);
@@ -484,14 +489,14 @@ inline cudaError_t launch_gn_apply(const GnApplyArgs& a, dim3 grid, int threads,
 constexpr int kLinAttnThreads = 256;
 constexpr int kLinAttnTile = 128;
 
-__device__ __forceinline__ void load32h(const __half* p, float (&f)[32]) {
+__device__ __forceinline__ void load32h(const __half* p, float (&f)[32], bool bf = false) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint4 v = *reinterpret_cast<const uint4*>(p + j * 8);
-    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+    const uint32_t* hv = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 t = __half22float2(hv[q]);
+      const float2 t = unpack2(hv[q], bf);
       f[j * 8 + 2 * q] = t.x;
       f[j * 8 + 2 * q + 1] = t.y;
     }
@@ -499,7 +504,7 @@ __device__ __forceinline__ void load32h(const __half* p, float (&f)[32]) {
 }
 
 __global__ void __launch_bounds__(kLinAttnThreads)
-linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) {
+linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n, bool bf = false) {
   __shared__ float s_red[kLinAttnThreads / 32][32];
   __shared__ float s_kmax[32];
   __shared__ float s_ksum[32];
@@ -519,7 +524,7 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
   for (int d = 0; d < 32; ++d) mx[d] = -INFINITY;
   for (int i = tid; i < n; i += kLinAttnThreads) {
     float f[32];
-    load32h(kb + (long long)i * 384, f);
+    load32h(kb + (long long)i * 384, f, bf);
 #pragma unroll
     for (int d = 0; d < 32; ++d) mx[d] = fmaxf(mx[d], f[d]);
   }
@@ -557,12 +562,12 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
       const int t = idx >> 2, oc = (idx & 3) * 8;
       const uint4 kv = *reinterpret_cast<const uint4*>(kb + (long long)(t0 + t) * 384 + oc);
       const uint4 vv = *reinterpret_cast<const uint4*>(vb + (long long)(t0 + t) * 384 + oc);
-      const __half2* hk = reinterpret_cast<const __half2*>(&kv);
-      const __half2* hv = reinterpret_cast<const __half2*>(&vv);
+      const uint32_t* hk = reinterpret_cast<const uint32_t*>(&kv);
+      const uint32_t* hv = reinterpret_cast<const uint32_t*>(&vv);
       float ek[8], vf[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 a = __half22float2(hk[q]), b = __half22float2(hv[q]);
+        const float2 a = unpack2(hk[q], bf), b = unpack2(hv[q], bf);
         ek[2 * q] = __expf(a.x - s_kmax[oc + 2 * q]);
         ek[2 * q + 1] = __expf(a.y - s_kmax[oc + 2 * q + 1]);
         vf[2 * q] = b.x;
@@ -615,7 +620,7 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
   const float scale = 0.17677669529663687f;  // 32^-0.5
   for (int i = tid; i < n; i += kLinAttnThreads) {
     float q[32];
-    load32h(qb + (long long)i * 384, q);
+    load32h(qb + (long long)i * 384, q, bf);
     float m = q[0];
 #pragma unroll
     for (int d = 1; d < 32; ++d) m = fmaxf(m, q[d]);
@@ -642,10 +647,10 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 w;
-      w.x = pack_half2(o[j * 8 + 0], o[j * 8 + 1]);
-      w.y = pack_half2(o[j * 8 + 2], o[j * 8 + 3]);
-      w.z = pack_half2(o[j * 8 + 4], o[j * 8 + 5]);
-      w.w = pack_half2(o[j * 8 + 6], o[j * 8 + 7]);
+      w.x = pack2(o[j * 8 + 0], o[j * 8 + 1], bf);
+      w.y = pack2(o[j * 8 + 2], o[j * 8 + 3], bf);
+      w.z = pack2(o[j * 8 + 4], o[j * 8 + 5], bf);
+      w.w = pack2(o[j * 8 + 6], o[j * 8 + 7], bf);
       *reinterpret_cast<uint4*>(op + j * 8) = w;
     }
   }
@@ -657,17 +662,17 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
 // One CTA per hypothesis, one warp per head.
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-midattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) {
+midattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n, bool bf = false) {
   __shared__ float s_k[4][32][32];
   __shared__ float s_v[4][32][32];
   const int h = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __half* base = qkv + (long long)h * n * 384;
   for (int t = lane; t < n; t += 32) {
     float f[32];
-    load32h(base + (long long)t * 384 + 128 + head * 32, f);
+    load32h(base + (long long)t * 384 + 128 + head * 32, f, bf);
 #pragma unroll
     for (int d = 0; d < 32; ++d) s_k[head][t][d] = f[d];
-    load32h(base + (long long)t * 384 + 256 + head * 32, f);
+    load32h(base + (long long)t * 384 + 256 + head * 32, f, bf);
 #pragma unroll
     for (int d = 0; d < 32; ++d) s_v[head][t][d] = f[d];
   }
@@ -675,7 +680,7 @@ midattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
   const float scale = 0.17677669529663687f;
   for (int i = lane; i < n; i += 32) {
     float q[32];
-    load32h(base + (long long)i * 384 + head * 32, q);
+    load32h(base + (long long)i * 384 + head * 32, q, bf);
 #pragma unroll
     for (int d = 0; d < 32; ++d) q[d] *= scale;
     float sim[32];
@@ -702,10 +707,10 @@ midattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 w;
-      w.x = pack_half2(o[j * 8 + 0], o[j * 8 + 1]);
-      w.y = pack_half2(o[j * 8 + 2], o[j * 8 + 3]);
-      w.z = pack_half2(o[j * 8 + 4], o[j * 8 + 5]);
-      w.w = pack_half2(o[j * 8 + 6], o[j * 8 + 7]);
+      w.x = pack2(o[j * 8 + 0], o[j * 8 + 1], bf);
+      w.y = pack2(o[j * 8 + 2], o[j * 8 + 3], bf);
+      w.z = pack2(o[j * 8 + 4], o[j * 8 + 5], bf);
+      w.w = pack2(o[j * 8 + 6], o[j * 8 + 7], bf);
       *reinterpret_cast<uint4*>(op + j * 8) = w;
     }
   }
@@ -757,7 +762,8 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
                         const float* __restrict__ bias, float* __restrict__ emb,
                         const float* __restrict__ query, const int* __restrict__ ref_of,
                         float* __restrict__ partial, int hw, int C, int Cl,
-                        const __half* __restrict__ x_lo = nullptr, int metric = 0, float occ_thr = 0.f) {
+                        const __half* __restrict__ x_lo = nullptr, int metric = 0, float occ_thr = 0.f,
+                        bool bf = false) {
   extern __shared__ float s_w[];  // [Cl][C]
   __shared__ float s_part[kScoreParts][kFinalThreads / 32];
   const int slab = blockIdx.x, h = blockIdx.y, nslab = gridDim.x;
@@ -773,11 +779,11 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
     const __half* xl = x_lo ? x_lo + ((long long)h * hw + p) * C : nullptr;
     for (int k0 = 0; k0 < C; k0 += 8) {
       const uint4 v = *reinterpret_cast<const uint4*>(xp + k0);
-      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+      const uint32_t* hv = reinterpret_cast<const uint32_t*>(&v);
       float f[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 t = __half22float2(hv[q]);
+        const float2 t = unpack2(hv[q], bf);
         f[2 * q] = t.x;
         f[2 * q + 1] = t.y;
       }
@@ -1083,7 +1089,8 @@ __global__ void conv_simt_kernel(const SimtConvArgs a) {
 
 // fp32 NCHW <-> fp16 NHWC helpers for the per-op test entry points
 __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y,
-                                            int n_img, int C, int hw, __half* __restrict__ y_lo = nullptr) {
+                                            int n_img, int C, int hw, __half* __restrict__ y_lo = nullptr,
+                                            bool bf = false) {
   const long long total = (long long)n_img * C * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1091,6 +1098,7 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half*
     const int p = (int)((i / C) % hw);
     const int b = (int)(i / ((long long)C * hw));
     const float v = x[((long long)b * C + c) * hw + p];
+    if (bf) { st16(y + i, v, true); continue; }
     const __half hi = __float2half_rn(v);
     y[i] = hi;
     if (y_lo) y_lo[i] = __float2half_rn(v - __half2float(hi));
@@ -1098,7 +1106,7 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half*
 }
 __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y,
                                             int n_img, int C, int hw,
-                                            const __half* __restrict__ x_lo = nullptr) {
+                                            const __half* __restrict__ x_lo = nullptr, bool bf = false) {
   const long long total = (long long)n_img * C * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1106,7 +1114,7 @@ __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float*
     const int c = (int)((i / hw) % C);
     const int b = (int)(i / ((long long)C * hw));
     const long long j = ((long long)b * hw + p) * C + c;
-    y[i] = __half2float(x[j]) + (x_lo ? __half2float(x_lo[j]) : 0.f);
+    y[i] = ld16(x + j, bf) + (x_lo ? __half2float(x_lo[j]) : 0.f);
   }
 }
 

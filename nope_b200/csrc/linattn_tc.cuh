@@ -29,6 +29,7 @@ struct LinAttnParams {
   CUtensorMap qkv;        // [n_img][n_tok][384], box {64, 128, 1}
   CUtensorMap out;        // [n_img][n_tok][128], box {64, 128, 1}
   int n_img, n_tok;
+  int bf16;               // qkv / out (and the ek / qs / ctxm operands written here) are bf16
 };
 
 struct LinAttnSmem {
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t smem_base = smem_u32(smem);
+    const uint32_t fmt = p.bf16 ? ((1u << 7) | (1u << 10)) : 0u;       // A / B format bits of the instruction descriptor
     uint32_t item = 0, n_img_done = 0, dcount = 0;
     for (int img = blockIdx.x; img < p.n_img; img += gridDim.x, ++n_img_done) {
       // parity waits only work for a thread that observes EVERY phase of a barrier: this warp walks the
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
           const uint64_t bdesc = kDescMN | ((smem_base + sv * kLaSlotBytes) >> 4);
 #pragma unroll
           for (int k = 0; k < kBM / 16; ++k)        // 16 tokens = two 8-row atoms = 2048 B
-            umma_f16(t_ctx, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), kIdescMN, (t | k) != 0 ? 1u : 0u);
+            umma_f16(t_ctx, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), kIdescMN | fmt, (t | k) != 0 ? 1u : 0u);
           umma_commit(&empty[sk]);
           umma_commit(&empty[sv]);
           if (t == T - 1) umma_commit(ctx_full);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
 #pragma unroll
           for (int k = 0; k < 8; ++k) {             // K = 128 channels d: 4 steps of 16 per 64-channel box
             const uint32_t off = (k >> 2) * ((kBM * 128) >> 4) + (k & 3) * 2;
-            umma_f16(t_d0 + db * 128, kDescHi | (a_lo + off), kDescHi | (b_lo + off), kIdescK, k != 0 ? 1u : 0u);
+            umma_f16(t_d0 + db * 128, kDescHi | (a_lo + off), kDescHi | (b_lo + off), kIdescK | fmt, k != 0 ? 1u : 0u);
           }
           umma_commit(&empty[sq]);
           umma_commit(&d_full[db]);
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
     const int box = cx >> 3, cin = cx & 7;
     const int q4 = w8 & 3, ch = w8 >> 2;           // TMEM lane quarter / 64-column half of this warp
     const float scale = 0.17677669529663687f;      // 32^-0.5
+    const bool bf = p.bf16 != 0;
     uint32_t item = 0, n_img_done = 0, dcount = 0;
     for (int img = blockIdx.x; img < p.n_img; img += gridDim.x, ++n_img_done) {
       // ---- pass 1: per-channel max of k over the image's tokens
@@ -203,10 +206,10 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 16 * i;
           const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128 + ((cin ^ (r & 7)) << 4));
-          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+          const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
-            const float2 f = __half22float2(h2[k2]);
+            const float2 f = unpack2(h2[k2], bf);
             mx[2 * k2] = fmaxf(mx[2 * k2], f.x);
             mx[2 * k2 + 1] = fmaxf(mx[2 * k2 + 1], f.y);
           }
@@ -240,12 +243,12 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
           const int r = r0 + 16 * i;
           uint4* pv = reinterpret_cast<uint4*>(tile + r * 128 + ((cin ^ (r & 7)) << 4));
           uint4 v = *pv;
-          __half2* h2 = reinterpret_cast<__half2*>(&v);
+          uint32_t* h2 = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
-            const float2 f = __half22float2(h2[k2]);
-            const __half2 e2 = __floats2half2_rn(__expf(f.x - km[2 * k2]), __expf(f.y - km[2 * k2 + 1]));
-            const float2 b = __half22float2(e2);
+            const float2 f = unpack2(h2[k2], bf);
+            const uint32_t e2 = pack2(__expf(f.x - km[2 * k2]), __expf(f.y - km[2 * k2 + 1]), bf);
+            const float2 b = unpack2(e2, bf);
             ks[2 * k2] += b.x;
             ks[2 * k2 + 1] += b.y;
             h2[k2] = e2;
@@ -294,8 +297,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
           for (int j = 0; j < 32; ++j) {
             const int e = e0 + j;                               // row of the operand
             const float val = same_head ? __uint_as_float(v[j]) * inv : 0.f;
-            *reinterpret_cast<__half*>(cbox + e * 128 + ((((d & 63) >> 3) ^ (e & 7)) << 4) + (d & 7) * 2) =
-                __float2half_rn(val);
+            st16(reinterpret_cast<__half*>(cbox + e * 128 + ((((d & 63) >> 3) ^ (e & 7)) << 4) + (d & 7) * 2), val, bf);
           }
         }
       }
@@ -320,10 +322,10 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 w;
-            w.x = pack_half2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-            w.y = pack_half2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-            w.z = pack_half2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-            w.w = pack_half2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+            w.x = pack2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]), bf);
+            w.y = pack2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]), bf);
+            w.z = pack2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]), bf);
+            w.w = pack2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]), bf);
             *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = w;
           }
         }
@@ -351,10 +353,10 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               v[c4] = *reinterpret_cast<const uint4*>(rowp + (((hd * 4 + c4) ^ (r & 7)) << 4));
-              const __half2* h2 = reinterpret_cast<const __half2*>(&v[c4]);
+              const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&v[c4]);
 #pragma unroll
               for (int k2 = 0; k2 < 4; ++k2) {
-                const float2 t2 = __half22float2(h2[k2]);
+                const float2 t2 = unpack2(h2[k2], bf);
                 f[c4 * 8 + 2 * k2] = t2.x;
                 f[c4 * 8 + 2 * k2 + 1] = t2.y;
               }
@@ -369,10 +371,10 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               uint4 w;
-              w.x = pack_half2(f[c4 * 8 + 0] * qs, f[c4 * 8 + 1] * qs);
-              w.y = pack_half2(f[c4 * 8 + 2] * qs, f[c4 * 8 + 3] * qs);
-              w.z = pack_half2(f[c4 * 8 + 4] * qs, f[c4 * 8 + 5] * qs);
-              w.w = pack_half2(f[c4 * 8 + 6] * qs, f[c4 * 8 + 7] * qs);
+              w.x = pack2(f[c4 * 8 + 0] * qs, f[c4 * 8 + 1] * qs, bf);
+              w.y = pack2(f[c4 * 8 + 2] * qs, f[c4 * 8 + 3] * qs, bf);
+              w.z = pack2(f[c4 * 8 + 4] * qs, f[c4 * 8 + 5] * qs, bf);
+              w.w = pack2(f[c4 * 8 + 6] * qs, f[c4 * 8 + 7] * qs, bf);
               *reinterpret_cast<uint4*>(rowp + (((hd * 4 + c4) ^ (r & 7)) << 4)) = w;
             }
           }
@@ -401,7 +403,8 @@ inline int make_token_map(CUtensorMap* out, const void* base, int n_img, int n_t
   return make_tmap_f16(out, base, 3, dims, str, box);
 }
 
-inline int launch_linattn_tc(const __half* qkv, __half* out, int n_img, int n_tok, int num_sms, cudaStream_t st) {
+inline int launch_linattn_tc(const __half* qkv, __half* out, int n_img, int n_tok, int num_sms, cudaStream_t st,
+                             bool bf16 = false) {
   if (n_tok % kBM != 0) return fail("linattn_tc: n_tok must be a multiple of 128");
   static bool attr_set[kMaxDevices];
   int dev = 0;
@@ -415,6 +418,7 @@ inline int launch_linattn_tc(const __half* qkv, __half* out, int n_img, int n_to
   if (make_token_map(&p.qkv, qkv, n_img, n_tok, 384) || make_token_map(&p.out, out, n_img, n_tok, 128)) return -1;
   p.n_img = n_img;
   p.n_tok = n_tok;
+  p.bf16 = bf16 ? 1 : 0;
   const int grid = n_img < num_sms ? n_img : num_sms;
   linattn_tc_kernel<<<grid, kLaThreads, LinAttnSmem::kTotal, st>>>(p);
   NOPE_CUDA(cudaGetLastError());

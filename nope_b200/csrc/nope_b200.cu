@@ -98,7 +98,8 @@ struct nope_unet {
   int conv_impl = 2;   // 0: tcgen05 1-CTA tiles, 1: SIMT debug twin, 2: tcgen05 CTA pairs (default)
   bool fuse_gn = true; // GroupNorm / SiLU / pose bias / residual in the conv epilogue (conv_impl 2 only)
   // 0: fp16 operands; 1: exact weights (W_hi + W_lo K-segments, 2x the MMA work); 2: split precision
-  // (exact weights + activations carried as hi + lo: A_hi W_hi + A_hi W_lo + A_lo W_hi, 3x)
+  // (exact weights + activations carried as hi + lo: A_hi W_hi + A_hi W_lo + A_lo W_hi, 3x);
+  // 3: bf16 operands and activations (8-bit mantissa: its own, looser tolerance)
   int precision = 0;
   int attn_impl = 0;         // LinearAttention core: 0 tcgen05 (token counts >= 128), 1 CUDA cores
   int metric = 0;            // NOPE_METRIC_* of the fused scoring
@@ -159,6 +160,7 @@ struct nope_unet {
   }
   bool fused() const { return fuse_gn && conv_impl == 2; }
   bool split() const { return precision == 2 && fused(); }
+  bool bf() const { return precision == 3; }     // bf16 storage (BASELINE configs[2]); fp16 otherwise
 
   // ------------------------------------------------------------------ schema
   void expect(const std::string& k, std::vector<int64_t> s) { expected[k] = std::move(s); }
@@ -261,7 +263,8 @@ struct nope_unet {
     const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
     L.cin = mode == 2 ? (int)sh[1] / 4 : (int)sh[1];
     L.K = L.cin * taps;
-    L.Kp = precision >= 1 ? 2 * L.K : L.K;
+    const bool wlo = precision == 1 || precision == 2;
+    L.Kp = wlo ? 2 * L.K : L.K;
     NOPE_CHECK(L.cin % 64 == 0, wkey + ": input channels must be a multiple of 64");
     L.bn = pick_bn(L.cout);
     NOPE_CHECK(L.bn != 0, wkey + ": output channels must be a multiple of 64");
@@ -281,7 +284,7 @@ struct nope_unet {
     NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w), npack * sizeof(__half)));
     owned.push_back(L.w);
     pack_weight_kernel<<<ew_grid((long long)rows * L.K), 256>>>(src, L.w, rows, L.cin, taps, L.Kp, 0,
-                                                                precision >= 1 ? L.K : 0);
+                                                                wlo ? L.K : 0, bf() ? 1 : 0);
     NOPE_CUDA(cudaGetLastError());
     NOPE_CUDA(cudaDeviceSynchronize());
     NOPE_CUDA(cudaFree(tmp));
@@ -334,9 +337,18 @@ struct nope_unet {
         const float w = W.data[(size_t)o * cin + k];
         const float wf = w * gm[k];
         Wf.data[(size_t)o * cin + k] = wf;
-        const __half hi = __float2half_rn(wf);
-        s1 += (double)__half2float(hi);
-        if (precision >= 1) s1 += (double)__half2float(__float2half_rn(wf - __half2float(hi)));
+        if (precision == 3) {
+          uint32_t u;
+          std::memcpy(&u, &wf, 4);
+          u = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;        // round to nearest even bf16
+          float r;
+          std::memcpy(&r, &u, 4);
+          s1 += (double)r;
+        } else {
+          const __half hi = __float2half_rn(wf);
+          s1 += (double)__half2float(hi);
+          if (precision >= 1) s1 += (double)__half2float(__float2half_rn(wf - __half2float(hi)));
+        }
         sb += (double)w * (double)bt[k];
       }
       w1[o] = (float)s1;
@@ -400,6 +412,7 @@ struct nope_unet {
     for (const auto& kv : expected)
       NOPE_CHECK(host.count(kv.first), "state_dict is missing " + kv.first);
     NOPE_CHECK(precision == 0 || conv_impl != 1, "the SIMT debug convolution only runs fp16 weights");
+    NOPE_CHECK(precision < 2 || fused(), "split precision / bf16 need the fused schedule on the CTA-pair kernel");
     NOPE_CUDA(cudaSetDevice(device));
     if (upload_f32("pose_mlp.0.weight", &pose_w) || upload_f32("pose_mlp.0.bias", &pose_b) ||
         upload_f32("init_conv.weight", &init_w) || upload_f32("init_conv.bias", &init_b) ||
@@ -647,6 +660,7 @@ struct nope_unet {
     }
     p.bmap = L.wmap;
     p.bmap_half = L.wmap_half;
+    p.bf16 = bf() ? 1 : 0;
     if (L.mode == 3) {
       for (int t = 0; t < 4; ++t) {
         if (get_map(&m, out.hi, cap_img, L.cout, g, t)) return -1;   // stride-2 sub-lattice (py, px)
@@ -831,7 +845,7 @@ struct nope_unet {
     a.pb = pb_offset >= 0 ? pb : nullptr; a.pb_stride = P; a.pb_off = pb_offset >= 0 ? pb_offset : 0;
     a.res = res; a.res_of = res_map; a.emit = emit; a.emit_parts = emit_parts_of(hw);
     a.hw = hw; a.C = C; a.G = N ? N->G : 1; a.nslab = nslab;
-    a.silu = silu ? 1 : 0; a.eps = 1e-5f;
+    a.silu = silu ? 1 : 0; a.eps = 1e-5f; a.bf16 = bf() ? 1 : 0;
     NOPE_CUDA(launch_gn_apply(a, dim3(nslab, n_img), threads, st));
     ++launches;
     return 0;
@@ -849,7 +863,7 @@ struct nope_unet {
     if (tap_out == nullptr || tap_name != name || tap_hit) return 0;
     NOPE_CHECK((int64_t)n * C * S * S <= tap_cap, "debug tap: output buffer too small");
     nhwc_f16_to_nchw_f32_kernel<<<ew_grid((long long)n * C * S * S), 256, 0, st>>>(buf.hi, tap_out, n, C, S * S,
-                                                                                   buf.lo);
+                                                                                   buf.lo, bf());
     NOPE_CUDA(cudaGetLastError());
     tap_C = C; tap_S = S; tap_hit = true;
     return 0;
@@ -929,9 +943,9 @@ struct nope_unet {
       if (conv(convs.at(p + ".qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
     }
     if (attn_impl == 0 && S * S >= kBM) {
-      if (launch_linattn_tc(TD.hi, TC.hi, n, S * S, num_sms, st)) return -1;
+      if (launch_linattn_tc(TD.hi, TC.hi, n, S * S, num_sms, st, bf())) return -1;
     } else {
-      linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD.hi, TC.hi, S * S);
+      linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD.hi, TC.hi, S * S, bf());
       NOPE_CUDA(cudaGetLastError());
     }
     ++launches;
@@ -964,7 +978,7 @@ struct nope_unet {
         return -1;
       if (conv(convs.at("mid_attn.qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
     }
-    midattn_kernel<<<n, 128, 0, st>>>(TD.hi, TC.hi, S * S);
+    midattn_kernel<<<n, 128, 0, st>>>(TD.hi, TC.hi, S * S, bf());
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     if (fused()) {
@@ -980,7 +994,7 @@ struct nope_unet {
   // g1 = SiLU(GN(downs.0.0.block1.proj(x0)))   (u_net.py:161; model_utils.py:272)
   int prestage(const float* ref_feat, int B, cudaStream_t st) {
     init_conv_kernel<<<ew_grid((long long)B * S0 * S0 * dim), 256, 0, st>>>(ref_feat, init_w, init_b, x0.hi,
-                                                                            B, Cl, S0, S0, dim, split() ? x0.lo : nullptr);
+                                                                            B, Cl, S0, S0, dim, split() ? x0.lo : nullptr, bf());
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     const Act xin(x0.hi, dim, split() ? x0.lo : nullptr);
@@ -1005,7 +1019,7 @@ struct nope_unet {
     iota_div(ref_of, hyp0, N, n, st);
     // pose embedding + all 19 pose projections in one GEMM
     pose_embed_kernel<<<n, 256, 0, st>>>(poses + (size_t)hyp0 * rot_dim, pose_w,
-                                                               pose_b, cs, n, rot_dim, cemb);
+                                                               pose_b, cs, n, rot_dim, cemb, bf());
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     if (conv_pose(n, st)) return -1;
@@ -1013,9 +1027,10 @@ struct nope_unet {
     // r (= init_conv output) and the hoisted block1 output, broadcast per hypothesis
     const int hw0 = S0 * S0;
     bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-        x0.hi, ref_of, nullptr, 0, 0, RB.hi, n, hw0, dim, sp ? x0.lo : nullptr, sp ? RB.lo : nullptr);
+        x0.hi, ref_of, nullptr, 0, 0, RB.hi, n, hw0, dim, sp ? x0.lo : nullptr, sp ? RB.lo : nullptr, bf());
     bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-        g1.hi, ref_of, pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, sp ? g1.lo : nullptr, sp ? TB.lo : nullptr);
+        g1.hi, ref_of, pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, sp ? g1.lo : nullptr, sp ? TB.lo : nullptr,
+        bf());
     NOPE_CUDA(cudaGetLastError());
     launches += 2;
     if (tap("init_conv", A(RB, dim), dim, S0, n, st)) return -1;
@@ -1093,7 +1108,7 @@ struct nope_unet {
     final_conv_score_kernel<<<dim3(nslab, n), kFinalThreads, (size_t)Cl * dim * sizeof(float), st>>>(
         curb.hi, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat, ref_of,
         score_part ? score_part + (size_t)hyp0 * nslab * kScoreParts : nullptr, hw, dim, Cl, sp ? curb.lo : nullptr,
-        metric, occ_threshold);
+        metric, occ_threshold, bf());
     NOPE_CUDA(cudaGetLastError());
     ++launches;
     return 0;
@@ -1220,14 +1235,14 @@ int nope_unet_set_conv_impl(nope_unet_t* u, int impl) {
 int nope_unet_set_option(nope_unet_t* u, const char* name, int value) {
   NOPE_CHECK(u && name, "null argument");
   if (std::strcmp(name, "fuse_gn") == 0) {
-    NOPE_CHECK(value != 0 || u->precision < 2, "split precision needs the fused GroupNorm epilogue");
+    NOPE_CHECK(value != 0 || u->precision < 2, "split precision / bf16 need the fused GroupNorm epilogue");
     u->fuse_gn = value != 0;
     return 0;
   }
   if (std::strcmp(name, "precision") == 0) {
     NOPE_CHECK(!u->finalized, "precision must be set before nope_unet_finalize");
     NOPE_CHECK(value == 0 || u->conv_impl != 1, "the SIMT debug convolution only runs fp16 weights");
-    NOPE_CHECK(value >= 0 && value <= 2, "precision must be 0 (fp16), 1 (exact weights) or 2 (split)");
+    NOPE_CHECK(value >= 0 && value <= 3, "precision must be 0 (fp16), 1 (exact weights), 2 (split) or 3 (bf16)");
     u->precision = value;
     return 0;
   }
