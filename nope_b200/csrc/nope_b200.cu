@@ -1461,9 +1461,21 @@ int nope_encoder_finalize(nope_encoder_t* e) {
 
 int nope_encoder_encode(nope_encoder_t* e, const float* images, int B, float* out, void* stream) {
   NOPE_CHECK(e && e->finalized, "encoder not finalized");
-  NOPE_CHECK(images && out && B >= 1 && B <= 64, "bad arguments");
+  NOPE_CHECK(images && out, "null images / out pointer");
+  NOPE_CHECK(B >= 1, "B must be >= 1");
   NOPE_CUDA(cudaSetDevice(e->device));
-  return e->encode(images, B, out, static_cast<cudaStream_t>(stream));
+  // The workspace is sized by the largest chunk (~80 MB per image): any B goes through, 32 images at a time.
+  constexpr int kChunk = 32;
+  int64_t launches = 0;
+  for (int lo = 0; lo < B; lo += kChunk) {
+    const int n = B - lo < kChunk ? B - lo : kChunk;
+    const int rc = e->encode(images + (size_t)lo * 3 * 256 * 256, n, out + (size_t)lo * e->D * 32 * 32,
+                             static_cast<cudaStream_t>(stream));
+    if (rc != 0) return rc;
+    launches += e->launches;
+  }
+  e->launches = launches;
+  return 0;
 }
 
 int64_t nope_encoder_last_launch_count(const nope_encoder_t* e) { return e ? e->launches : 0; }
