@@ -266,4 +266,41 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
+
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched through launch_pdl() may be scheduled while its
+// predecessor in the stream is still draining: its CTAs take the SMs the predecessor's CTAs leave, run
+// whatever precedes pdl_sync() (nothing that touches global memory) and block there until the predecessor
+// has completed and its writes are visible.  EVERY kernel launched this way must call pdl_sync() before its
+// first global access; called from a kernel launched with plain stream ordering it is a no-op.
+// NOPE_PDL=0 switches the attribute off (A/B measurements).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("NOPE_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace nope

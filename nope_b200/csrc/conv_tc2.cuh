@@ -676,6 +676,10 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   cluster_sync_all();     // barriers of BOTH CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched
+  // no global memory and may overlap the tail of the previous kernel in the stream; from here on the kernel reads
+  // what that kernel wrote.  The next kernel's CTAs may be scheduled as soon as this grid's CTAs retire.
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -855,8 +859,18 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   const int max_clusters = max_clusters_of[dev];
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
-  conv_tc2_kernel<BN, STAGES, EPI><<<2 * clusters, EPI == 3 ? gn_threads(BN) : kConvThreads, S::kTotal, stream>>>(p);
-  NOPE_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(2 * clusters, 1, 1);
+  cfg.blockDim = dim3(EPI == 3 ? gn_threads(BN) : kConvThreads, 1, 1);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  NOPE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, STAGES, EPI>, p));
   return 0;
 }
 

@@ -71,6 +71,7 @@ __global__ void fold_upconv_kernel(const float* __restrict__ src, float* __restr
 __global__ void pose_embed_kernel(const float* __restrict__ poses, const float* __restrict__ w,
                                   const float* __restrict__ b, __half* __restrict__ cs, int n_hyp,
                                   int rot_dim, int cemb, bool bf = false) {
+  pdl_sync();
   const int h = blockIdx.x;
   if (h >= n_hyp) return;
   __shared__ float sp[8];      // rot_dim <= 8 (6-D rotations); padded so vectorised reads stay inside
@@ -129,6 +130,7 @@ __global__ void bcast_add_kernel(const __half* __restrict__ src, const int* __re
                                  __half* __restrict__ out, int n_hyp, int hw, int C,
                                  const __half* __restrict__ src_lo = nullptr,
                                  __half* __restrict__ out_lo = nullptr, bool bf = false) {
+  pdl_sync();
   const int octs = C / 8;
   const long long total = (long long)n_hyp * hw * octs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -303,6 +305,7 @@ constexpr int kGnUnroll = 4;   // independent 16-byte loads in flight per thread
 
 template <bool SILU, bool PB, bool RES>
 __global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
+  pdl_sync();
   __shared__ float2 s_red[256];
   __shared__ float2 s_grp[8];
   const int octs = a.C / 8;
@@ -467,16 +470,15 @@ __global__ void __launch_bounds__(384, 2) gn_apply_kernel(const GnApplyArgs a) {
 inline cudaError_t launch_gn_apply(const GnApplyArgs& a, dim3 grid, int threads, cudaStream_t st) {
   const int key = (a.silu ? 4 : 0) | (a.pb ? 2 : 0) | (a.res ? 1 : 0);
   switch (key) {
-    case 0: gn_apply_kernel<false, false, false><<<grid, threads, 0, st>>>(a); break;
-    case 1: gn_apply_kernel<false, false, true><<<grid, threads, 0, st>>>(a); break;
-    case 2: gn_apply_kernel<false, true, false><<<grid, threads, 0, st>>>(a); break;
-    case 3: gn_apply_kernel<false, true, true><<<grid, threads, 0, st>>>(a); break;
-    case 4: gn_apply_kernel<true, false, false><<<grid, threads, 0, st>>>(a); break;
-    case 5: gn_apply_kernel<true, false, true><<<grid, threads, 0, st>>>(a); break;
-    case 6: gn_apply_kernel<true, true, false><<<grid, threads, 0, st>>>(a); break;
-    default: gn_apply_kernel<true, true, true><<<grid, threads, 0, st>>>(a); break;
+    case 0: return launch_pdl(gn_apply_kernel<false, false, false>, grid, dim3(threads), 0, st, a);
+    case 1: return launch_pdl(gn_apply_kernel<false, false, true>, grid, dim3(threads), 0, st, a);
+    case 2: return launch_pdl(gn_apply_kernel<false, true, false>, grid, dim3(threads), 0, st, a);
+    case 3: return launch_pdl(gn_apply_kernel<false, true, true>, grid, dim3(threads), 0, st, a);
+    case 4: return launch_pdl(gn_apply_kernel<true, false, false>, grid, dim3(threads), 0, st, a);
+    case 5: return launch_pdl(gn_apply_kernel<true, false, true>, grid, dim3(threads), 0, st, a);
+    case 6: return launch_pdl(gn_apply_kernel<true, true, false>, grid, dim3(threads), 0, st, a);
+    default: return launch_pdl(gn_apply_kernel<true, true, true>, grid, dim3(threads), 0, st, a);
   }
-  return cudaGetLastError();
 }
 
 // ----------------------------------------------------------------------------
@@ -505,6 +507,7 @@ __device__ __forceinline__ void load32h(const __half* p, float (&f)[32], bool bf
 
 __global__ void __launch_bounds__(kLinAttnThreads)
 linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n, bool bf = false) {
+  pdl_sync();
   __shared__ float s_red[kLinAttnThreads / 32][32];
   __shared__ float s_kmax[32];
   __shared__ float s_ksum[32];
@@ -663,6 +666,7 @@ linattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n, 
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 midattn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n, bool bf = false) {
+  pdl_sync();
   __shared__ float s_k[4][32][32];
   __shared__ float s_v[4][32][32];
   const int h = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -764,6 +768,7 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
                         float* __restrict__ partial, int hw, int C, int Cl,
                         const __half* __restrict__ x_lo = nullptr, int metric = 0, float occ_thr = 0.f,
                         bool bf = false) {
+  pdl_sync();
   extern __shared__ float s_w[];  // [Cl][C]
   __shared__ float s_part[kScoreParts][kFinalThreads / 32];
   const int slab = blockIdx.x, h = blockIdx.y, nslab = gridDim.x;
@@ -922,6 +927,7 @@ __global__ void __launch_bounds__(256)
 sim_topk_kernel(const float* __restrict__ partial, int nslab, float* __restrict__ sim, int N,
                 int k, float* __restrict__ top_val, long long* __restrict__ top_idx,
                 long long idx_base, int nparts = 1, int metric = 0, int hw = 1) {
+  pdl_sync();
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   __shared__ int s_chosen[64];

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();       // the prologue above overlapped the previous kernel's tail; its output is read from here on
   const uint32_t t_ctx = tmem_base;              // columns [0, 128)
   const uint32_t t_d0 = tmem_base + 128;         // out-tile accumulators: columns [128, 256), [256, 384)
 
@@ -420,8 +421,7 @@ inline int launch_linattn_tc(const __half* qkv, __half* out, int n_img, int n_to
   p.n_tok = n_tok;
   p.bf16 = bf16 ? 1 : 0;
   const int grid = n_img < num_sms ? n_img : num_sms;
-  linattn_tc_kernel<<<grid, kLaThreads, LinAttnSmem::kTotal, st>>>(p);
-  NOPE_CUDA(cudaGetLastError());
+  NOPE_CUDA(launch_pdl(linattn_tc_kernel, dim3(grid), dim3(kLaThreads), LinAttnSmem::kTotal, st, p));
   return 0;
 }
 

@@ -945,8 +945,7 @@ struct nope_unet {
     if (attn_impl == 0 && S * S >= kBM) {
       if (launch_linattn_tc(TD.hi, TC.hi, n, S * S, num_sms, st, bf())) return -1;
     } else {
-      linattn_kernel<<<dim3(4, n), kLinAttnThreads, 0, st>>>(TD.hi, TC.hi, S * S, bf());
-      NOPE_CUDA(cudaGetLastError());
+      NOPE_CUDA(launch_pdl(linattn_kernel, dim3(4, n), dim3(kLinAttnThreads), 0, st, TD.hi, TC.hi, S * S, bf()));
     }
     ++launches;
     // to_out (K = 128: two K-steps per tile) is bound by its epilogue, not by its GEMM: the fused
@@ -978,8 +977,7 @@ struct nope_unet {
         return -1;
       if (conv(convs.at("mid_attn.qkv"), Act(TB.hi, C), Act(), Act(TD.hi, 3 * kHeadsHidden), S, n, cap, st)) return -1;
     }
-    midattn_kernel<<<n, 128, 0, st>>>(TD.hi, TC.hi, S * S, bf());
-    NOPE_CUDA(cudaGetLastError());
+    NOPE_CUDA(launch_pdl(midattn_kernel, dim3(n), dim3(128), 0, st, TD.hi, TC.hi, S * S, bf()));
     ++launches;
     if (fused()) {
       GnSpec s;                // no normalisation: out = to_out(attn) + x
@@ -1018,20 +1016,18 @@ struct nope_unet {
     // hypothesis -> reference image
     iota_div(ref_of, hyp0, N, n, st);
     // pose embedding + all 19 pose projections in one GEMM
-    pose_embed_kernel<<<n, 256, 0, st>>>(poses + (size_t)hyp0 * rot_dim, pose_w,
-                                                               pose_b, cs, n, rot_dim, cemb, bf());
-    NOPE_CUDA(cudaGetLastError());
+    NOPE_CUDA(launch_pdl(pose_embed_kernel, dim3(n), dim3(256), 0, st, poses + (size_t)hyp0 * rot_dim, pose_w, pose_b,
+                         cs, n, rot_dim, cemb, bf()));
     ++launches;
     if (conv_pose(n, st)) return -1;
 
     // r (= init_conv output) and the hoisted block1 output, broadcast per hypothesis
     const int hw0 = S0 * S0;
-    bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-        x0.hi, ref_of, nullptr, 0, 0, RB.hi, n, hw0, dim, sp ? x0.lo : nullptr, sp ? RB.lo : nullptr, bf());
-    bcast_add_kernel<<<ew_grid((long long)n * hw0 * dim / 8), 256, 0, st>>>(
-        g1.hi, ref_of, pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, sp ? g1.lo : nullptr, sp ? TB.lo : nullptr,
-        bf());
-    NOPE_CUDA(cudaGetLastError());
+    NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)n * hw0 * dim / 8)), dim3(256), 0, st, x0.hi, ref_of,
+                         nullptr, 0, 0, RB.hi, n, hw0, dim, sp ? x0.lo : nullptr, sp ? RB.lo : nullptr, bf()));
+    NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)n * hw0 * dim / 8)), dim3(256), 0, st, g1.hi, ref_of,
+                         pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, sp ? g1.lo : nullptr,
+                         sp ? TB.lo : nullptr, bf()));
     launches += 2;
     if (tap("init_conv", A(RB, dim), dim, S0, n, st)) return -1;
 
@@ -1105,11 +1101,10 @@ struct nope_unet {
     if (tap("final_conv.0", A(curb, dim), dim, S, n, st)) return -1;
     const int hw = S * S;
     const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
-    final_conv_score_kernel<<<dim3(nslab, n), kFinalThreads, (size_t)Cl * dim * sizeof(float), st>>>(
-        curb.hi, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat, ref_of,
-        score_part ? score_part + (size_t)hyp0 * nslab * kScoreParts : nullptr, hw, dim, Cl, sp ? curb.lo : nullptr,
-        metric, occ_threshold, bf());
-    NOPE_CUDA(cudaGetLastError());
+    NOPE_CUDA(launch_pdl(final_conv_score_kernel, dim3(nslab, n), dim3(kFinalThreads), (size_t)Cl * dim * sizeof(float),
+                         st, curb.hi, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat,
+                         ref_of, score_part ? score_part + (size_t)hyp0 * nslab * kScoreParts : nullptr, hw, dim, Cl,
+                         sp ? curb.lo : nullptr, metric, occ_threshold, bf()));
     ++launches;
     return 0;
   }
@@ -1346,10 +1341,8 @@ int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, i
   }
   if (query_feat && (out_sim || k > 0)) {
     float* sim = out_sim ? out_sim : u->sim_buf;
-    sim_topk_kernel<<<B, 256, 0, st>>>(part, nslab, sim, N, k, out_topv,
-                                       reinterpret_cast<long long*>(out_topi), (long long)idx_base,
-                                       kScoreParts, u->metric, hw);
-    NOPE_CUDA(cudaGetLastError());
+    NOPE_CUDA(launch_pdl(sim_topk_kernel, dim3(B), dim3(256), 0, st, part, nslab, sim, N, k, out_topv,
+                         reinterpret_cast<long long*>(out_topi), (long long)idx_base, kScoreParts, u->metric, hw));
     ++u->launches;
   }
   return 0;
