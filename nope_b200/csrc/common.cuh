@@ -273,18 +273,19 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
 // whatever precedes pdl_sync() (nothing that touches global memory) and block there until the predecessor
 // has completed and its writes are visible.  EVERY kernel launched this way must call pdl_sync() before its
 // first global access; called from a kernel launched with plain stream ordering it is a no-op.
-// NOPE_PDL=0 switches the attribute off (A/B measurements).
+// NOPE_PDL (bit mask, see pdl_mask) switches the attribute off for A/B measurements.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-inline bool pdl_enabled() {
-  static const bool on = [] {
+// NOPE_PDL: bit 0 = the convolution kernels, bit 1 = every other kernel of the chain (default 3)
+inline int pdl_mask() {
+  static const int m = [] {
     const char* e = getenv("NOPE_PDL");
-    return !(e && e[0] == '0');
+    return e ? atoi(e) : 3;
   }();
-  return on;
+  return m;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -299,7 +300,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_mask() & 2) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -869,7 +869,7 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
   at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_mask() & 1) ? 1 : 0;
   NOPE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, STAGES, EPI>, p));
   return 0;
 }
