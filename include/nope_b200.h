@@ -249,7 +249,9 @@ int nope_ldm_set_impl(nope_ldm_t* m, int conv_impl, int attn_impl);
  * self-attention -- runs once per reference instead of once per hypothesis); before
  * nope_ldm_finalize only: "wide_tiles" (default 1: 256-channel GEMM tiles on the CTA-pair kernel),
  * "fold_residual" (default 1: residual adds ride in the GEMM as identity K-segments fed by TMA;
- * 0: added in the epilogue from global memory). */
+ * 0: added in the epilogue from global memory), "precision" (default 0: fp16 weights; 1: exact
+ * weights -- packed rows hold [W_hi | W_lo] and every GEMM accumulates A W_hi + A W_lo, 2x the MMA
+ * work; embeddings 1.1e-3 -> below the 1e-3 bar against the fp32 reference). */
 int nope_ldm_set_option(nope_ldm_t* m, const char* name, int value);
 int nope_ldm_sweep(nope_ldm_t* m, const float* ref_latent, const float* poses, int B, int N,
                    const float* query_latent, float* out_emb, float* out_sim, int k,

@@ -110,6 +110,19 @@ __device__ __forceinline__ void umma_commit_2cta_mc(uint64_t* bar, uint16_t mask
       : "memory");
 }
 
+// shared-memory map of the EPI == 4 epilogue (conv_gn2_* below), relative to Conv2Smem::kGnOffset
+template <int BN>
+struct Gn2Smem {
+  static constexpr int kOct = BN / 8;
+  static constexpr int kPart = 0;                          // fp32 [8 row segments][kOct][2]
+  static constexpr int kMr = kPart + 8 * kOct * 8;         // float2 [2][64]: (mean, rstd) per (image, group) / image
+  static constexpr int kTab = kMr + 2 * 64 * 8;            // fp32 [2][scale | shift][BN]
+  static constexpr int kOg = kTab + 2 * 2 * BN * 4;        // int [kOct]: octet -> group of the tile
+  static constexpr int kEm = kOg + kOct * 4;               // float2 [BN / 64][8]: emit partials per 16-row segment
+  static constexpr int kX = kEm + 32 * 8;                  // fp32 [256]: gathered cross-CTA partials
+  static constexpr int kBytes = kX + 256 * 4;
+};
+
 template <int BN, int STAGES, int EPI = 0>
 struct Conv2Smem {
   static constexpr int kABytes = kBM * kBK * 2;
@@ -125,7 +138,8 @@ struct Conv2Smem {
   // segment partial sums (fp32 [8][BN/8][2]) | (mean, rstd) [64] | octet -> group table [BN/8] | emit scratch |
   // gathered cross-CTA partials (fp32 [256])
   static constexpr int kGnOffset = kBiasOffset + BN * 4;
-  static constexpr int kGnBytes = EPI == 3 ? (2 * BN * 4 + 8 * BN * 2 + 8 * (BN / 8) * 8 + 64 * 8 + (BN / 8) * 4 + 32 * 8 + 256 * 4) : 0;
+  static constexpr int kGnBytes = EPI == 3 ? (2 * BN * 4 + 8 * BN * 2 + 8 * (BN / 8) * 8 + 64 * 8 + (BN / 8) * 4 + 32 * 8 + 256 * 4)
+                                            : (EPI == 4 ? Gn2Smem<BN>::kBytes : 0);
   static constexpr int kTotal = kGnOffset + kGnBytes + 1024;
 };
 
@@ -273,7 +287,7 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
   };
   static_assert(8 * kOct <= kEpiThreads, "one thread per (image, octet) of the pose-bias rows");
   fetch_pb(tile0);
-#define NOPE_TS(k) do { if (g.ts && etid == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 8 + (k)] = global_ns(); } while (0)
+#define NOPE_TS(k) do { if (g.ts && etid == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + (k)] = global_ns(); } while (0)
   for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
     NOPE_TS(0);
     const int m_pair = tile / p.n_tiles;
@@ -626,9 +640,559 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
 #undef NOPE_EPI_BAR
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// EPI == 4: the GroupNorm-fused epilogue with the bookkeeping moved off the math warps.
+//
+// EPI == 3 walks all epilogue warps through the tile in lock step: five to six block-wide barriers per tile,
+// the statistics exchange, the table build and the drain of the TMA store all sit on the critical path of the
+// warps that do the arithmetic (phase stamps, profiles/README.md: 10-11 us per tile against an 8.2 us mainloop
+// at K = 1728; the K = 192 pre-norm qkv tiles took 6.5 us because of a serial chain of eight L2 loads).
+// Here the two idle warps of the CTA take that work and talk to the math warps through mbarriers only:
+//
+//   warps 4..   math: TMEM -> registers (+bias), release the accumulator, per-octet partial sums -> s_part,
+//               arrive part_bar | wait stats_bar[b], res_bar | normalise / SiLU / pose bias / residual in place
+//               in the staging tile | arrive out_bar, tabfree_bar[b].   No block-wide barrier anywhere.
+//   warp 3      statistics: wait part_bar | per-(image, group) sums, publish {value, epoch} words, poll the peer
+//               tiles, fixed-order totals | per-channel scale / shift table (or (mean, rstd) pairs) into buffer
+//               b = tile parity | arrive stats_bar[b].  The pre-norm fold's per-image scalars are independent of
+//               the accumulator, so for those launches this warp runs a tile ahead of the math warps.
+//   warp 2      store: wait out_bar | GroupNorm(1) sums of the stored tile (emit) | TMA store | once the store has
+//               read the staging buffer: TMA load of the NEXT tile's residual into it (or a plain arrive), res_bar.
+//
+// Per-channel parameters (bias, gamma, beta, pose-bias rows) are read through the read-only L1 path instead of
+// being staged in shared memory per tile, which removes the staging barrier.  Arithmetic and summation orders
+// are those of EPI == 3: results are bit-identical between the two.
+// ---------------------------------------------------------------------------------------------
+struct Gn2Bars {
+  uint64_t* tfull;      // [2]
+  uint64_t* tempty;     // [2]
+  uint64_t* res;        // residual landed / staging free (store warp -> math warps)
+  uint64_t* part;       // s_part written (math warps -> statistics warp)
+  uint64_t* stats;      // [2] tables of tile parity b ready (statistics warp -> math warps)
+  uint64_t* tabfree;    // [2] last read of table buffer b done (math warps -> statistics warp)
+  uint64_t* out;        // staging tile written (math warps -> store warp)
+};
+
+template <int BN, int STAGES>
+__device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t* smem, uint8_t* gsm, uint32_t tmem_base,
+                                                    const Gn2Bars& B, int tile0, int tile_step, int num_tiles,
+                                                    uint32_t rank) {
+  using S = Conv2Smem<BN, STAGES, 4>;
+  using G2 = Gn2Smem<BN>;
+  constexpr int kOct = BN / 8;
+  uint8_t* ost = smem + STAGES * S::kStageBytes;
+  float* s_part = reinterpret_cast<float*>(gsm + G2::kPart);
+  const int* s_og = reinterpret_cast<const int*>(gsm + G2::kOg);
+  float2* s_em = reinterpret_cast<float2*>(gsm + G2::kEm);
+
+  const GnFuse& g = p.gn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = warp - 4;
+  const int q = e & 3, cc = e >> 2;                  // TMEM lane quarter, 64-column sub-tile of this warp
+  const int row = q * 32 + lane;
+  const bool leader = rank == 0;
+  const int hw = p.stats_hw;
+  const bool small = hw < 32;                        // 4x4 images: 16-row segments, two per warp
+  const int it = hw < kBM ? (row >> g.hw_shift) : 0; // image of this thread's row inside the tile
+  const bool use_tab = g.G > 0 && g.ipt == 1 && g.expected > 1;
+  const bool pre = g.pre_stats != nullptr;
+  const bool wait_stats = g.G > 0 || pre;
+  const bool bf = p.bf16 != 0;
+  const uint32_t gsm_off = (uint32_t)(gsm - smem);
+
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  int iter = 0;
+#define NOPE_TS(k) do { if (g.ts && e == 0 && lane == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + (k)] = global_ns(); } while (0)
+  for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
+    NOPE_TS(0);
+    const int b = iter & 1;
+    const int m_pair = tile / p.n_tiles;
+    const int n_tile = tile - m_pair * p.n_tiles;
+    const int m_tile = 2 * m_pair + (int)rank;
+    const int n_chan0 = n_tile * BN;
+    const bool live = m_tile < p.m_tiles;          // the peer of an odd last pair owns phantom tiles (its last ones)
+    int b0, y0;
+    conv_tile_coords(p, m_tile, b0, y0);
+    const int img0 = p.tiles_per_img > 0 ? m_tile / g.mt : m_tile * g.ipt;   // first image of the tile
+    const bool img_ok = img0 + it < g.n_img;
+    const __half* pb_row = g.pb + (size_t)(img_ok ? img0 + it : 0) * g.pb_stride + g.pb_off + n_chan0 + cc * 64;
+    if (g.pb && live) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb_row));
+
+    mbar_wait(&B.tfull[acc], acc_phase);
+    tc_fence_after();
+    NOPE_TS(1);
+    // ---- pass 1: TMEM -> registers, free the accumulator, per-octet partial sums
+    uint32_t a[64];
+    {
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + cc * 64;
+      tmem_ld_32x32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
+      tmem_ld_32x32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&B.tempty[acc]);
+        else mbar_arrive_remote(&B.tempty[acc], 0);
+      }
+    }
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+    if (!live) continue;
+
+    float* f = reinterpret_cast<float*>(a);
+    if (p.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_chan0 + cc * 64);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 c = __ldg(b4 + j);
+        f[4 * j + 0] += c.x;
+        f[4 * j + 1] += c.y;
+        f[4 * j + 2] += c.z;
+        f[4 * j + 3] += c.w;
+      }
+    }
+    if (g.G > 0) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float st[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* ff = f + hh * 32 + j * 8;
+          const float sm = (ff[0] + ff[1]) + (ff[2] + ff[3]) + ((ff[4] + ff[5]) + (ff[6] + ff[7]));
+          float q2 = ff[0] * ff[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) q2 = fmaf(ff[i], ff[i], q2);
+          st[2 * j] = sm;
+          st[2 * j + 1] = q2;
+        }
+        const int idx = small ? butterfly8<16>(st, lane) : butterfly8<32>(st, lane);
+        const bool writer = small ? ((lane & 1) == 0) : ((lane & 3) == 0);
+        const int segi = small ? (q * 2 + (lane >> 4)) : q;
+        if (writer) s_part[(segi * kOct + cc * 8 + hh * 4) * 2 + idx] = st[0];   // idx = octet * 2 + {sum, sumsq}
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(B.part);
+    }
+    NOPE_TS(2);
+    if (wait_stats) mbar_wait(&B.stats[b], (iter >> 1) & 1);
+    NOPE_TS(3);
+    mbar_wait(B.res, iter & 1);          // residual tile landed in the staging buffer / the buffer is free
+    NOPE_TS(4);
+
+    // ---- pass 2: normalise / activate / add, in place in the swizzled staging tile
+    float e1 = 0.f, e2 = 0.f;
+    const uint32_t tok = order_token(smem_u32(smem));          // tables below are read after the waits above
+    const uint32_t a_mr = tok + gsm_off + G2::kMr + b * 64 * 8;
+    const uint32_t a_sc = tok + gsm_off + G2::kTab + b * 2 * BN * 4 + cc * 256;
+    const uint32_t a_sh = a_sc + BN * 4;
+    const int grow = m_tile * kBM + row;            // linear output pixel
+    const bool row_ok = grow < p.m_valid;
+    const long long rpix = g.res_div > 0
+        ? (long long)((g.res_base + b0) / g.res_div) * hw + (m_tile % g.mt) * kBM + row
+        : (long long)grow;
+    uint8_t* srow = ost + cc * (kBM * 128) + row * 128;
+    const bool do_norm = g.G > 0 && !(g.dbg & 4);
+    const bool do_silu = g.silu && !(g.dbg & 2);
+    // every step runs over all 64 values of the thread with its (launch-uniform) condition tested outside the
+    // unrolled loop: one long basic block per step
+    if (pre && g.ipt > 1) {
+      const float2 mr = lds_f2(a_mr + it * 8);
+      const float nm = -mr.x * mr.y;
+      const float4* w14 = reinterpret_cast<const float4*>(g.pre_w1 + n_chan0 + cc * 64);
+      const float4* wb4 = reinterpret_cast<const float4*>(g.pre_wb + n_chan0 + cc * 64);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 w1 = __ldg(w14 + j), wb = __ldg(wb4 + j);
+        f[4 * j + 0] = fmaf(f[4 * j + 0], mr.y, fmaf(nm, w1.x, wb.x));
+        f[4 * j + 1] = fmaf(f[4 * j + 1], mr.y, fmaf(nm, w1.y, wb.y));
+        f[4 * j + 2] = fmaf(f[4 * j + 2], mr.y, fmaf(nm, w1.z, wb.z));
+        f[4 * j + 3] = fmaf(f[4 * j + 3], mr.y, fmaf(nm, w1.w, wb.w));
+      }
+    } else if ((do_norm && use_tab) || pre) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 sc = lds_f4(a_sc + j * 16), sh = lds_f4(a_sh + j * 16);
+        f[4 * j + 0] = fmaf(f[4 * j + 0], sc.x, sh.x);
+        f[4 * j + 1] = fmaf(f[4 * j + 1], sc.y, sh.y);
+        f[4 * j + 2] = fmaf(f[4 * j + 2], sc.z, sh.z);
+        f[4 * j + 3] = fmaf(f[4 * j + 3], sc.w, sh.w);
+      }
+    } else if (do_norm) {
+      const float4* gm4 = reinterpret_cast<const float4*>(g.gamma + n_chan0 + cc * 64);
+      const float4* bt4 = reinterpret_cast<const float4*>(g.beta + n_chan0 + cc * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 mr = lds_f2(a_mr + (it * g.gpt + s_og[cc * 8 + j]) * 8);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const float4 gm = __ldg(gm4 + j * 2 + h2), bt = __ldg(bt4 + j * 2 + h2);
+          float* ff = f + j * 8 + h2 * 4;
+          ff[0] = fmaf(ff[0] - mr.x, mr.y * gm.x, bt.x);
+          ff[1] = fmaf(ff[1] - mr.x, mr.y * gm.y, bt.y);
+          ff[2] = fmaf(ff[2] - mr.x, mr.y * gm.z, bt.z);
+          ff[3] = fmaf(ff[3] - mr.x, mr.y * gm.w, bt.w);
+        }
+      }
+    }
+    if (do_silu) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) f[i] = silu_ftz(f[i]);
+    }
+    if (g.pb && img_ok) {
+      const uint4* pb4 = reinterpret_cast<const uint4*>(pb_row);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 pv = __ldg(pb4 + j);
+        const uint32_t* hp = reinterpret_cast<const uint32_t*>(&pv);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float2 t = unpack2(hp[k2], bf);
+          f[j * 8 + 2 * k2] += t.x;
+          f[j * 8 + 2 * k2 + 1] += t.y;
+        }
+      }
+    }
+    if (g.has_res) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(srow + ((j ^ (row & 7)) << 4));
+        const uint32_t* hr = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float2 t = unpack2(hr[k2], bf);
+          f[j * 8 + 2 * k2] += t.x;
+          f[j * 8 + 2 * k2 + 1] += t.y;
+        }
+      }
+      if (g.res_lo && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 rl = *reinterpret_cast<const uint4*>(g.res_lo + rpix * p.n_total + n_chan0 + cc * 64 + j * 8);
+          const __half2* hl = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const float2 t = __half22float2(hl[k2]);
+            f[j * 8 + 2 * k2] += t.x;
+            f[j * 8 + 2 * k2 + 1] += t.y;
+          }
+        }
+      }
+    }
+    const bool want_lo = g.out_lo && row_ok;
+    const bool want_emit = g.emit != nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 w;
+      w.x = pack2(f[j * 8 + 0], f[j * 8 + 1], bf);
+      w.y = pack2(f[j * 8 + 2], f[j * 8 + 3], bf);
+      w.z = pack2(f[j * 8 + 4], f[j * 8 + 5], bf);
+      w.w = pack2(f[j * 8 + 6], f[j * 8 + 7], bf);
+      *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) = w;
+      if (want_lo || want_emit) {
+        const uint32_t* hw2 = reinterpret_cast<const uint32_t*>(&w);
+        uint4 wl;
+        uint32_t* pl = reinterpret_cast<uint32_t*>(&wl);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float2 t = unpack2(hw2[k2], bf);
+          pl[k2] = pack_half2(f[j * 8 + 2 * k2] - t.x, f[j * 8 + 2 * k2 + 1] - t.y);
+          e1 += t.x + t.y;                 // statistics of the values as stored (what the consumer reads)
+          e2 = fmaf(t.x, t.x, e2);
+          e2 = fmaf(t.y, t.y, e2);
+        }
+        if (want_lo)
+          *reinterpret_cast<uint4*>(g.out_lo + (size_t)grow * p.n_total + n_chan0 + cc * 64 + j * 8) = wl;
+      }
+    }
+    if (want_emit) {
+      // 16-row segments: every image is a whole number of them at every resolution
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) {
+        e1 += __shfl_xor_sync(0xffffffffu, e1, off);
+        e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+      }
+      if ((lane & 15) == 0) s_em[cc * 8 + (row >> 4)] = make_float2(e1, e2);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(B.out);
+      if (wait_stats) mbar_arrive(&B.tabfree[b]);
+    }
+    NOPE_TS(5);
+  }
+#undef NOPE_TS
+}
+
+// statistics warp (warp 3) of the EPI == 4 epilogue
+template <int BN, int STAGES>
+__device__ __forceinline__ void conv_gn2_stats_warp(const ConvParams& p, uint8_t* gsm, const Gn2Bars& B, int tile0,
+                                                    int tile_step, int num_tiles, uint32_t rank) {
+  using G2 = Gn2Smem<BN>;
+  constexpr int kOct = BN / 8;
+  const float* s_part = reinterpret_cast<const float*>(gsm + G2::kPart);
+  float2* s_mr = reinterpret_cast<float2*>(gsm + G2::kMr);
+  float* s_tab = reinterpret_cast<float*>(gsm + G2::kTab);
+  int* s_og = reinterpret_cast<int*>(gsm + G2::kOg);
+  float* s_x = reinterpret_cast<float*>(gsm + G2::kX);
+  const GnFuse& g = p.gn;
+  const int lane = threadIdx.x & 31;
+  const int hw = p.stats_hw;
+  const bool small = hw < 32;
+  const int npairs = g.ipt * g.gpt;
+  const bool use_tab = g.G > 0 && g.ipt == 1 && g.expected > 1;
+  const bool pre = g.pre_stats != nullptr;
+  if (!(g.G > 0 || pre)) return;          // residual / pose-bias-only epilogues: nothing to hand over
+  for (int o = lane; o < kOct; o += 32) s_og[o] = (g.G > 0 && g.cpg < BN) ? (o * 8) / g.cpg : 0;
+  __syncwarp();
+  int iter = 0;
+  for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
+    const int b = iter & 1;
+    const int m_pair = tile / p.n_tiles;
+    const int n_tile = tile - m_pair * p.n_tiles;
+    const int m_tile = 2 * m_pair + (int)rank;
+    if (m_tile >= p.m_tiles) break;                      // phantom tiles are this CTA's last ones
+    const int n_chan0 = n_tile * BN;
+    const int img0 = p.tiles_per_img > 0 ? m_tile / g.mt : m_tile * g.ipt;
+    float* t_sc = s_tab + b * 2 * BN;
+    float* t_sh = t_sc + BN;
+    float2* mr = s_mr + b * 64;
+    if (iter >= 2) mbar_wait(&B.tabfree[b], ((iter >> 1) - 1) & 1);   // tile iter-2 has read buffer b
+#define NOPE_TS2(k) do { if (g.ts && lane == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + (k)] = global_ns(); } while (0)
+    NOPE_TS2(8);
+    if (g.G > 0) {
+      mbar_wait(B.part, iter & 1);
+      NOPE_TS2(9);
+      // sums of this tile per (image, group) pair: fixed order over row segments and channel octets
+      float Sx[2], Qx[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int pr = lane + 32 * k;
+        Sx[k] = 0.f;
+        Qx[k] = 0.f;
+        if (pr < npairs) {
+          const int ii = pr / g.gpt, gl = pr - ii * g.gpt;
+          const int spi = hw >= kBM ? 4 : (small ? 1 : (hw >> 5));   // row segments of this image in the tile
+          const int s0 = hw >= kBM ? 0 : ii * spi;
+          const int opg = (g.cpg < BN ? g.cpg : BN) >> 3;
+          const int o0 = gl * opg;
+          for (int sgm = s0; sgm < s0 + spi; ++sgm) {
+#pragma unroll 4
+            for (int o = o0; o < o0 + opg; ++o) {
+              const float2 t = *reinterpret_cast<const float2*>(s_part + (sgm * kOct + o) * 2);
+              Sx[k] += t.x;
+              Qx[k] += t.y;
+            }
+          }
+        }
+      }
+      if (g.expected > 1) {
+        // publish {value, epoch}; poll the [slot][pair][2] block of the sync group until every word carries this
+        // launch's epoch (all loads of the warp in flight at once)
+        const int sg = (m_tile / g.mt) * (p.n_tiles / g.tpg) + n_tile / g.tpg;
+        const int slot = (m_tile % g.mt) * g.tpg + (n_tile % g.tpg);
+        uint2* xp = g.xpart + (size_t)sg * g.expected * npairs * 2;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int pr = lane + 32 * k;
+          if (pr < npairs) {
+            st_volatile_u2(xp + ((size_t)slot * npairs + pr) * 2, make_uint2(__float_as_uint(Sx[k]), g.epoch));
+            st_volatile_u2(xp + ((size_t)slot * npairs + pr) * 2 + 1, make_uint2(__float_as_uint(Qx[k]), g.epoch));
+          }
+        }
+        NOPE_TS2(10);
+        const int nw = g.expected * npairs * 2;        // <= 256 (host check)
+        uint2 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int w = lane + 32 * k;
+          u[k] = make_uint2(0u, g.epoch);
+          if (w < nw) u[k] = ld_volatile_u2(xp + w);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int w = lane + 32 * k;
+          if (w < nw) {
+            if (u[k].y != g.epoch && !(g.dbg & 1)) {
+              const long long t0 = clock64();
+              do {
+                u[k] = ld_volatile_u2(xp + w);
+                if (clock64() - t0 > 4000000000LL) {
+                  printf("nope_b200: GroupNorm tile sync timed out (block %d tile %d)\n", (int)blockIdx.x, tile);
+                  __trap();
+                }
+              } while (u[k].y != g.epoch);
+            }
+            s_x[w] = __uint_as_float(u[k].x);
+          }
+        }
+        __syncwarp();
+        NOPE_TS2(11);
+        if (use_tab) {
+          // one image per tile: totals per (group, statistic) in slot order, then per-channel scale / shift
+          float tot = 0.f;
+          if (lane < 2 * g.gpt)
+            for (int sl = 0; sl < g.expected; ++sl) tot += s_x[(sl * npairs + (lane >> 1)) * 2 + (lane & 1)];
+#pragma unroll
+          for (int c = lane; c < BN; c += 32) {
+            const int gl = s_og[c >> 3];
+            const float s1 = __shfl_sync(0xffffffffu, tot, 2 * gl);
+            const float s2 = __shfl_sync(0xffffffffu, tot, 2 * gl + 1);
+            const float mean = s1 * g.inv_cnt;
+            const float var = fmaxf(s2 * g.inv_cnt - mean * mean, 0.f);
+            const float sc = rsqrtf(var + g.eps) * __ldg(g.gamma + n_chan0 + c);
+            t_sc[c] = sc;
+            t_sh[c] = __ldg(g.beta + n_chan0 + c) - mean * sc;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int pr = lane + 32 * k;
+            if (pr < npairs) {
+              float S1 = 0.f, S2 = 0.f;
+              for (int sl = 0; sl < g.expected; ++sl) {
+                S1 += s_x[(sl * npairs + pr) * 2];
+                S2 += s_x[(sl * npairs + pr) * 2 + 1];
+              }
+              const float mean = S1 * g.inv_cnt;
+              const float var = fmaxf(S2 * g.inv_cnt - mean * mean, 0.f);
+              mr[pr] = make_float2(mean, rsqrtf(var + g.eps));
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int pr = lane + 32 * k;
+          if (pr < npairs) {
+            const float mean = Sx[k] * g.inv_cnt;
+            const float var = fmaxf(Qx[k] * g.inv_cnt - mean * mean, 0.f);
+            mr[pr] = make_float2(mean, rsqrtf(var + g.eps));
+          }
+        }
+      }
+    }
+    if (pre) {
+      // folded pre-norm: (mean, rstd) of each input image of the tile from its producer's partial sums
+      // (all loads issued together, summed in part order)
+      if (g.ipt == 1) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int k0 = 0; k0 < g.pre_parts; k0 += 32) {
+          float2 t = make_float2(0.f, 0.f);
+          if (k0 + lane < g.pre_parts) t = g.pre_stats[(size_t)img0 * g.pre_parts + k0 + lane];
+          const int n = g.pre_parts - k0 < 32 ? g.pre_parts - k0 : 32;
+          for (int k = 0; k < n; ++k) {
+            s1 += __shfl_sync(0xffffffffu, t.x, k);
+            s2 += __shfl_sync(0xffffffffu, t.y, k);
+          }
+        }
+        const float mean = s1 * g.pre_inv_cnt;
+        const float rstd = rsqrtf(fmaxf(s2 * g.pre_inv_cnt - mean * mean, 0.f) + g.eps);
+#pragma unroll
+        for (int c = lane; c < BN; c += 32) {
+          t_sc[c] = rstd;
+          t_sh[c] = __ldg(g.pre_wb + n_chan0 + c) - rstd * mean * __ldg(g.pre_w1 + n_chan0 + c);
+        }
+      } else if (lane < g.ipt) {
+        float2 t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          t[k] = make_float2(0.f, 0.f);
+          if (k < g.pre_parts && img0 + lane < g.n_img) t[k] = g.pre_stats[(size_t)(img0 + lane) * g.pre_parts + k];
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < g.pre_parts) {
+            s1 += t[k].x;
+            s2 += t[k].y;
+          }
+        const float mean = s1 * g.pre_inv_cnt;
+        mr[lane] = make_float2(mean, rsqrtf(fmaxf(s2 * g.pre_inv_cnt - mean * mean, 0.f) + g.eps));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&B.stats[b]);
+    NOPE_TS2(12);
+  }
+#undef NOPE_TS2
+}
+
+// store warp (warp 2) of the EPI == 4 epilogue
+template <int BN, int STAGES>
+__device__ __forceinline__ void conv_gn2_store_warp(const ConvParams& p, uint8_t* smem, uint8_t* gsm, const Gn2Bars& B,
+                                                    int tile0, int tile_step, int num_tiles, uint32_t rank) {
+  using S = Conv2Smem<BN, STAGES, 4>;
+  using G2 = Gn2Smem<BN>;
+  constexpr int kNS = BN / 64;
+  uint8_t* ost = smem + STAGES * S::kStageBytes;
+  const float2* s_em = reinterpret_cast<const float2*>(gsm + G2::kEm);
+  const GnFuse& g = p.gn;
+  const int lane = threadIdx.x & 31;
+  const int hw = p.stats_hw;
+  // the residual tile of tile t is TMA-loaded into the staging buffer (same box / swizzle as the store) once the
+  // previous store has read it; without a residual the same barrier just says "the buffer is free"
+  auto stage = [&](int t) {
+    const int mp = t / p.n_tiles;
+    const int nt = t - mp * p.n_tiles;
+    const int mt2 = 2 * mp + (int)rank;
+    if (g.has_res && mt2 < p.m_tiles) {
+      int bb, yy;
+      conv_tile_coords(p, mt2, bb, yy);
+      const int rb = g.res_div > 0 ? (g.res_base + bb) / g.res_div : bb;
+      mbar_expect_tx(B.res, S::kOutBytes);
+#pragma unroll 1
+      for (int c2 = 0; c2 < kNS; ++c2)
+        tma_load_4d(ost + c2 * (kBM * 128), &p.rmap, B.res, nt * BN + c2 * 64, 0, yy, rb);
+    } else {
+      mbar_arrive(B.res);
+    }
+  };
+  if (lane == 0 && tile0 < num_tiles) stage(tile0);
+  int iter = 0;
+  for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
+    const int m_pair = tile / p.n_tiles;
+    const int n_tile = tile - m_pair * p.n_tiles;
+    const int m_tile = 2 * m_pair + (int)rank;
+    if (m_tile >= p.m_tiles) break;
+    int b0, y0;
+    conv_tile_coords(p, m_tile, b0, y0);
+    const int img0 = p.tiles_per_img > 0 ? m_tile / g.mt : m_tile * g.ipt;
+    mbar_wait(B.out, iter & 1);
+    if (g.ts && lane == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + 13] = global_ns();
+    if (g.emit && lane < g.ipt && img0 + lane < g.n_img) {
+      const int r16 = hw >= kBM ? 8 : (hw >> 4);
+      float s1 = 0.f, s2 = 0.f;
+      for (int h2 = 0; h2 < kNS; ++h2)
+        for (int r = lane * r16; r < (lane + 1) * r16; ++r) {
+          s1 += s_em[h2 * 8 + r].x;
+          s2 += s_em[h2 * 8 + r].y;
+        }
+      g.emit[(size_t)(img0 + lane) * g.emit_parts + (m_tile % g.mt) * p.n_tiles + n_tile] = make_float2(s1, s2);
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll 1
+      for (int c2 = 0; c2 < kNS; ++c2)
+        tma_store_4d(&p.omap[0], ost + c2 * (kBM * 128), n_tile * BN + c2 * 64, 0, y0, b0);
+      tma_store_commit();
+      const int nt = tile + tile_step;
+      if (nt < num_tiles) {
+        tma_store_wait_read0();
+        if (g.ts && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + 14] = global_ns();
+        stage(nt);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+
 // EPI: 0 = plain epilogue (the sweep), 1 = extras (ReLU / residual / hi-lo / fp32), 2 = GEGLU
 template <int BN, int STAGES, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI == 3 ? gn_threads(BN) : kConvThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI >= 3 ? gn_threads(BN) : kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   using S = Conv2Smem<BN, STAGES, EPI>;
   constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -643,7 +1207,9 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);     // EPI == 3: residual tile landed
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);     // EPI >= 3: residual tile landed
+  uint64_t* gn2_bar = res_bar + 1;                                    // EPI == 4: part, stats[2], tabfree[2], out
+  static_assert((2 * STAGES + 4 + 2 + 6) * 8 <= 256, "barrier block overflow");
   float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
 
   const int warp = threadIdx.x >> 5;
@@ -666,9 +1232,17 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 2 * (EPI == 3 ? gn_epi_warps(BN) : kEpiWarps));
+      mbar_init(&tempty_bar[a], 2 * (EPI >= 3 ? gn_epi_warps(BN) : kEpiWarps));
     }
     mbar_init(res_bar, 1);
+    if constexpr (EPI == 4) {
+      mbar_init(&gn2_bar[0], gn_epi_warps(BN));                         // part
+      mbar_init(&gn2_bar[1], 1);                                        // stats[0]
+      mbar_init(&gn2_bar[2], 1);                                        // stats[1]
+      mbar_init(&gn2_bar[3], gn_epi_warps(BN));                         // tabfree[0]
+      mbar_init(&gn2_bar[4], gn_epi_warps(BN));                         // tabfree[1]
+      mbar_init(&gn2_bar[5], gn_epi_warps(BN));                         // out
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_2cta<kTmemCols>(tmem_slot);
@@ -721,9 +1295,13 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    int mma_iter = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++mma_iter) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
+      if constexpr (EPI == 4) {     // development: phase stamps 6 (accumulator granted) / 7 (last K-step issued)
+        if (p.gn.ts && lane == 0 && mma_iter < 64) p.gn.ts[((size_t)blockIdx.x * 64 + mma_iter) * 16 + 6] = global_ns();
+      }
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int ks = 0; ks < p.ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
@@ -740,8 +1318,22 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if constexpr (EPI == 4) {
+        if (p.gn.ts && lane == 0 && mma_iter < 64) p.gn.ts[((size_t)blockIdx.x * 64 + mma_iter) * 16 + 7] = global_ns();
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (EPI == 4 && warp >= 2) {
+    // ===================== epilogue with GroupNorm fused, bookkeeping on warps 2 / 3 =====================
+    if constexpr (EPI == 4) {
+      Gn2Bars B;
+      B.tfull = tfull_bar; B.tempty = tempty_bar; B.res = res_bar;
+      B.part = &gn2_bar[0]; B.stats = &gn2_bar[1]; B.tabfree = &gn2_bar[3]; B.out = &gn2_bar[5];
+      uint8_t* gsm = smem + S::kGnOffset;
+      if (warp == 2) conv_gn2_store_warp<BN, STAGES>(p, smem, gsm, B, tile0, tile_step, num_tiles, rank);
+      else if (warp == 3) conv_gn2_stats_warp<BN, STAGES>(p, gsm, B, tile0, tile_step, num_tiles, rank);
+      else conv_gn2_math_warps<BN, STAGES>(p, smem, gsm, tmem_base, B, tile0, tile_step, num_tiles, rank);
     }
   } else if (warp >= 4 && EPI == 3) {
     // ===================== epilogue with GroupNorm fused =====================
@@ -837,12 +1429,12 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
     NOPE_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, EPI>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     int mc = num_sms / 2;
-    if (EPI == 3) {
+    if (EPI >= 3) {
       // tiles of one image wait for each other: every cluster of the grid must be resident
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof cfg);
       cfg.gridDim = dim3(num_sms, 1, 1);
-      cfg.blockDim = dim3(EPI == 3 ? gn_threads(BN) : kConvThreads, 1, 1);
+      cfg.blockDim = dim3(EPI >= 3 ? gn_threads(BN) : kConvThreads, 1, 1);
       cfg.dynamicSmemBytes = S::kTotal;
       cudaLaunchAttribute at;
       at.id = cudaLaunchAttributeClusterDimension;
@@ -862,7 +1454,7 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(2 * clusters, 1, 1);
-  cfg.blockDim = dim3(EPI == 3 ? gn_threads(BN) : kConvThreads, 1, 1);
+  cfg.blockDim = dim3(EPI >= 3 ? gn_threads(BN) : kConvThreads, 1, 1);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute at;
@@ -878,10 +1470,23 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
 inline int launch_conv_gn(const ConvParams& p, int bn, int num_sms, cudaStream_t stream) {
   if (p.n_par != 1 || p.geglu || conv_needs_extras(p) || p.stats)
     return fail("launch_conv_gn: the fused GroupNorm epilogue takes a plain convolution");
-  switch (bn) {
-    case 192: return launch_conv_tc2_t<192, 6, 3>(p, num_sms, stream);
-    case 128: return launch_conv_tc2_t<128, 6, 3>(p, num_sms, stream);
-    case 64: return launch_conv_tc2_t<64, 8, 3>(p, num_sms, stream);
+  // NOPE_GN_EPI=3 selects the lock-step epilogue (EPI == 3) for A/B measurements; default: EPI == 4
+  static const int epi = [] {
+    const char* e = getenv("NOPE_GN_EPI");
+    return e && atoi(e) == 3 ? 3 : 4;
+  }();
+  if (epi == 3) {
+    switch (bn) {
+      case 192: return launch_conv_tc2_t<192, 6, 3>(p, num_sms, stream);
+      case 128: return launch_conv_tc2_t<128, 6, 3>(p, num_sms, stream);
+      case 64: return launch_conv_tc2_t<64, 8, 3>(p, num_sms, stream);
+    }
+  } else {
+    switch (bn) {
+      case 192: return launch_conv_tc2_t<192, 6, 4>(p, num_sms, stream);
+      case 128: return launch_conv_tc2_t<128, 6, 4>(p, num_sms, stream);
+      case 64: return launch_conv_tc2_t<64, 8, 4>(p, num_sms, stream);
+    }
   }
   return fail("launch_conv_gn: unsupported BN");
 }

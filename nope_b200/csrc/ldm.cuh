@@ -75,6 +75,9 @@ struct nope_ldm {
   bool wide_tiles = true;   // 256-channel tiles on the 2-CTA kernel where Cout % 256 == 0 (set before finalize)
   bool hoist = true;        // pose-independent prefix once per reference (prestage)
   bool fuse_geglu = true;   // GEGLU in the projection's epilogue (2-CTA kernel); false: separate kernel
+  int precision = 0;        // 0: fp16 weights; 1: exact weights -- every packed row is [W_hi | W_lo] and the K loop
+                            // walks its segment list twice (A W_hi + A W_lo), 2x the MMA work (set before finalize)
+  int kp(int K) const { return precision ? 2 * K : K; }
   int chunk = 256;
   int64_t launches = 0;
 
@@ -288,7 +291,7 @@ struct nope_ldm {
       rows = 4 * cout;
     }
     pack_weight_kernel<<<ew_grid((long long)rows * cin * taps), 256>>>(
-        src, dst + (size_t)row_off * K, rows, cin, taps, K, col_off);
+        src, dst + (size_t)row_off * kp(K), rows, cin, taps, kp(K), col_off, precision ? K : 0);
     NOPE_CUDA(cudaGetLastError());
     NOPE_CUDA(cudaDeviceSynchronize());
     NOPE_CUDA(cudaFree(tmp));
@@ -302,13 +305,13 @@ struct nope_ldm {
     L.bn = (!L.geglu && L.cout % 256 == 0 && wide_tiles) ? 256 : L.bn1;
     NOPE_CHECK(L.bn != 0 && L.K % 64 == 0, name + ": channel counts must be multiples of 64");
     if (!bias.empty() && upload(bias, &L.bias)) return -1;
-    if (make_weight_map(&L.wmap, L.w, rows, L.K, L.bn1)) return -1;
-    if (make_weight_map(&L.wmap_half, L.w, rows, L.K, L.bn / 2)) return -1;
+    if (make_weight_map(&L.wmap, L.w, rows, kp(L.K), L.bn1)) return -1;
+    if (make_weight_map(&L.wmap_half, L.w, rows, kp(L.K), L.bn / 2)) return -1;
     convs[name] = L;
     return 0;
   }
   int alloc_w(nope::LdmConv& L, int rows) {
-    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w), (size_t)rows * L.K * sizeof(__half)));
+    NOPE_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w), (size_t)rows * kp(L.K) * sizeof(__half)));
     owned.push_back(L.w);
     return 0;
   }
@@ -695,7 +698,17 @@ struct nope_ldm {
     p.tiles_per_img = g.tiles_per_img;
     p.h_cnt = g.h_cnt;
     p.b_cnt = g.b_cnt;
-    NOPE_CHECK(nseg <= kMaxSeg && ksteps * 64 == L.K, "conv: K mismatch");
+    NOPE_CHECK(ksteps * 64 == L.K, "conv: K mismatch");
+    if (precision) {
+      // exact weights: the same segments again over the W_lo columns (weight columns simply continue past K)
+      NOPE_CHECK(2 * nseg <= kMaxSeg, "conv: segment table overflow");
+      for (int i = 0; i < nseg; ++i) p.seg[nseg + i] = p.seg[i];
+      nseg *= 2;
+      ksteps *= 2;
+    }
+    NOPE_CHECK(nseg <= kMaxSeg, "conv: segment table overflow");
+    p.nseg = nseg;
+    p.ksteps = ksteps;
     NOPE_CHECK(!((stats || res) && L.mode == 3), "upsample conv has no fused statistics / residual");
     if (profile && prof_begin(st)) return -1;
     const int rc = conv_impl == 2 ? launch_conv_tc2(p, bn, num_sms, st) : launch_conv_tc(p, bn, num_sms, st);

@@ -761,8 +761,8 @@ struct nope_unet {
       static const int ts_k = std::getenv("NOPE_GN_TS") ? std::atoi(std::getenv("NOPE_GN_TS")) : -1;
       static int ts_count = 0;
       if (ts_k >= 0 && ts_count++ == ts_k) {
-        cudaMalloc(reinterpret_cast<void**>(&ts_dev), (size_t)num_sms * 64 * 8 * sizeof(unsigned long long));
-        cudaMemset(ts_dev, 0, (size_t)num_sms * 64 * 8 * sizeof(unsigned long long));
+        cudaMalloc(reinterpret_cast<void**>(&ts_dev), (size_t)num_sms * 64 * 16 * sizeof(unsigned long long));
+        cudaMemset(ts_dev, 0, (size_t)num_sms * 64 * 16 * sizeof(unsigned long long));
         p.gn.ts = ts_dev;
       }
     }
@@ -773,7 +773,7 @@ struct nope_unet {
     if (ts_dev) {
       const int rc = launch();
       cudaDeviceSynchronize();
-      std::vector<unsigned long long> h((size_t)num_sms * 64 * 8);
+      std::vector<unsigned long long> h((size_t)num_sms * 64 * 16);
       cudaMemcpy(h.data(), ts_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       cudaFree(ts_dev);
       if (FILE* f = std::fopen(std::getenv("NOPE_GN_TS_FILE") ? std::getenv("NOPE_GN_TS_FILE") : "gn_ts.csv", "w")) {
@@ -781,9 +781,13 @@ struct nope_unet {
                      p.gn.expected, p.m_tiles, p.n_tiles);
         for (int c = 0; c < num_sms; ++c)
           for (int it = 0; it < 64; ++it) {
-            const unsigned long long* r = &h[((size_t)c * 64 + it) * 8];
+            const unsigned long long* r = &h[((size_t)c * 64 + it) * 16];
             if (r[0] == 0) continue;
-            std::fprintf(f, "%d,%d,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c, it, r[0], r[1], r[2], r[3], r[4], r[5], r[6]);
+            {
+              std::fprintf(f, "%d,%d", c, it);
+              for (int k = 0; k < 16; ++k) std::fprintf(f, ",%llu", r[k]);
+              std::fprintf(f, "\n");
+            }
           }
         std::fclose(f);
       }
@@ -1840,6 +1844,12 @@ int nope_ldm_set_option(nope_ldm_t* m, const char* name, int value) {
   if (std::strcmp(name, "fold_residual") == 0) {
     NOPE_CHECK(!m->finalized, "fold_residual must be set before finalize");
     m->fold_residual = value != 0;
+    return 0;
+  }
+  if (std::strcmp(name, "precision") == 0) {
+    NOPE_CHECK(!m->finalized, "precision must be set before finalize");
+    NOPE_CHECK(value == 0 || value == 1, "LDM precision: 0 (fp16 weights) or 1 (exact weights, W_hi + W_lo)");
+    m->precision = value;
     return 0;
   }
   if (std::strcmp(name, "wide_tiles") == 0) {

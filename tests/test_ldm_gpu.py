@@ -5,8 +5,10 @@ Every module is also driven in isolation (nope_ldm_run_block): it gets the ORACL
 that module and must reproduce the oracle's output, so one failing kernel does not hide the rest.
 
 Tolerances (fp16 storage of activations / weights / softmax probabilities, fp32 accumulation,
-statistics, softmax and LayerNorm): per module rel-L2 <= BLOCK_TOL; whole network embeddings
-rel-L2 <= EMB_TOL, l2 scores max-rel <= SIM_TOL."""
+statistics, softmax and LayerNorm): per module rel-L2 <= BLOCK_TOL; l2 scores max-rel <= SIM_TOL;
+whole network embeddings rel-L2 <= EMB_TOL = the north-star 1e-3 in the exact-weights mode
+(precision="fp16_w2": W = W_hi + W_lo K-segments), <= EMB_TOL_FP16 in the fast fp16-weights mode, whose
+weight rounding alone is 0.62e-3 of its measured 1.08e-3 (CPU experiment on the oracle)."""
 import numpy as np
 import pytest
 import torch
@@ -16,7 +18,8 @@ from _util import log, max_rel, rel_l2
 pytestmark = pytest.mark.gpu
 
 BLOCK_TOL = 1e-3    # measured 3.0e-4 .. 4.1e-4 per module
-EMB_TOL = 2.5e-3    # measured 1.07e-3 end to end (cumulative 1.3e-3 at the bottleneck)
+EMB_TOL = 1e-3      # exact-weights mode: the north-star tolerance
+EMB_TOL_FP16 = 1.5e-3   # fp16-weights mode: measured 1.07e-3 end to end (cumulative 1.3e-3 at the bottleneck)
 SIM_TOL = 1e-3      # measured 2.9e-5
 N_HYP = 2
 
@@ -128,7 +131,7 @@ def test_forward_vs_oracle(ldm_model, oracle_taps, golden, attn):
         ldm_model.set_impl()
     e = rel_l2(emb, oracle_taps["emb"])
     log("ldm_forward_vs_oracle", attn=attn, emb_rel_l2=e, launches=ldm_model.last_launch_count)
-    assert e < EMB_TOL
+    assert e < EMB_TOL_FP16
 
 
 def test_geglu_fusion_matches_separate_kernel(ldm_model, oracle_taps):
@@ -156,7 +159,7 @@ def test_taps_vs_oracle(ldm_model, oracle_taps, golden):
         e = rel_l2(got, oracle_taps[tap])
         log("ldm_tap", tap=tap, rel_l2=e)
         worst = max(worst, e)
-    assert worst < 2 * EMB_TOL
+    assert worst < 2 * EMB_TOL_FP16
 
 
 def test_sweep_golden(ldm_model, golden):
@@ -169,7 +172,7 @@ def test_sweep_golden(ldm_model, golden):
     e_sim = max_rel(out["sim"], torch.from_numpy(golden["similarity"]))
     order = torch.from_numpy(golden["similarity"]).argsort(dim=1, descending=True)
     log("ldm_sweep_golden", emb_rel_l2=e_emb, sim_max_rel=e_sim, topi=out["topi"].tolist(), ref_order=order.tolist())
-    assert e_emb < EMB_TOL and e_sim < SIM_TOL
+    assert e_emb < EMB_TOL_FP16 and e_sim < SIM_TOL
     assert torch.equal(out["topi"].cpu(), order)
     # chunking / batching invariance: two references, chunk smaller than N
     ldm_model.set_chunk(2)
@@ -210,7 +213,50 @@ def test_epilogue_residual_and_narrow_tiles(ldm_sd, oracle_taps, golden):
     emb = m(ref.expand(N_HYP, -1, -1, -1), oracle_taps["poses"])
     e = rel_l2(emb, oracle_taps["emb"])
     log("ldm_alt_gemm_config", emb_rel_l2=e)
-    assert e < EMB_TOL
+    assert e < EMB_TOL_FP16
+
+
+@pytest.fixture(scope="module")
+def ldm_model_w2(ldm_sd):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from nope_b200.ldm import UNetModelPose
+    m = UNetModelPose(device="cuda:0", chunk=8, precision="fp16_w2")
+    m.load_state_dict(ldm_sd)
+    return m
+
+
+def test_exact_weights_mode_meets_the_north_star_tolerance(ldm_model_w2, oracle_taps, golden):
+    """precision="fp16_w2": embeddings within 1e-3 of the fp32 oracle AND of the unmodified reference's golden
+    sweep, scores and ranking as in the fp16 mode"""
+    ref = torch.from_numpy(golden["ref_latent"])
+    emb = ldm_model_w2(ref.expand(N_HYP, -1, -1, -1), oracle_taps["poses"])
+    e = rel_l2(emb, oracle_taps["emb"])
+    qry = torch.from_numpy(golden["query_latent"])
+    poses = torch.from_numpy(golden["all_relativeR"])
+    out = ldm_model_w2.sweep(ref, poses, qry, want_emb=True, k=3)
+    e_emb = rel_l2(out["emb"][0], torch.from_numpy(golden["emb"]))
+    e_sim = max_rel(out["sim"], torch.from_numpy(golden["similarity"]))
+    order = torch.from_numpy(golden["similarity"]).argsort(dim=1, descending=True)
+    log("ldm_exact_weights", emb_rel_l2_vs_oracle=e, emb_rel_l2_vs_golden=e_emb, sim_max_rel=e_sim,
+        launches=ldm_model_w2.last_launch_count)
+    assert e < EMB_TOL and e_emb < EMB_TOL and e_sim < SIM_TOL
+    assert torch.equal(out["topi"].cpu(), order)
+
+
+def test_exact_weights_module_in_isolation(ldm_model_w2, oracle_taps):
+    """a ResBlock (3x3 convs + folded identity / 1x1 skip K-segments) and a SpatialTransformer (q|k|v, GEGLU,
+    residual linears) with the doubled segment list"""
+    for name, kind, in0, in1, out_tap in [("input_blocks.4.0", "res", "input_blocks.3", None, "input_blocks.4.0"),
+                                          ("input_blocks.4.1", "st", "input_blocks.4.0", None, "input_blocks.4"),
+                                          ("output_blocks.2.0", "res", "output_blocks.1", "input_blocks.6", "output_blocks.2.0")]:
+        want = oracle_taps[out_tap]
+        got = ldm_model_w2.run_block(name, oracle_taps[in0], oracle_taps[in1] if in1 else None,
+                                     poses=oracle_taps["poses"] if kind == "st" else None,
+                                     out_channels=want.shape[1], out_side=want.shape[2])
+        e = rel_l2(got, want)
+        log("ldm_module_w2", module=name, rel_l2=e)
+        assert e < BLOCK_TOL
 
 
 def test_rejects_bad_input(ldm_model):

@@ -53,7 +53,8 @@ for spec in args.specs:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     line = {"spec": spec, "ms": ms, "hyp_per_s": args.queries * args.poses / (ms * 1e-3),
-            "launches": u.last_launch_count, "top5": out["topi"][0].tolist()}
+            "launches": u.last_launch_count, "top5": out["topi"][0].tolist(),
+            "sim_crc": __import__("zlib").crc32(out["sim"].float().cpu().numpy().tobytes())}
     if base is None:
         base = out["sim"].clone()
     else:
