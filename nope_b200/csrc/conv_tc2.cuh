@@ -118,8 +118,8 @@ struct Gn2Smem {
   static constexpr int kMr = kPart + 8 * kOct * 8;         // float2 [2][64]: (mean, rstd) per (image, group) / image
   static constexpr int kTab = kMr + 2 * 64 * 8;            // fp32 [2][scale | shift][BN]
   static constexpr int kOg = kTab + 2 * 2 * BN * 4;        // int [kOct]: octet -> group of the tile
-  static constexpr int kEm = kOg + kOct * 4;               // float2 [BN / 64][8]: emit partials per 16-row segment
-  static constexpr int kX = kEm + 32 * 8;                  // fp32 [256]: gathered cross-CTA partials
+  static constexpr int kEm = kOg + kOct * 4;               // float2 [2 staging buffers][BN / 64][8]: emit partials per 16-row segment
+  static constexpr int kX = kEm + 2 * 32 * 8;                  // fp32 [256]: gathered cross-CTA partials
   static constexpr int kBytes = kX + 256 * 4;
 };
 
@@ -131,7 +131,7 @@ struct Conv2Smem {
   static constexpr int kOutBytes = (BN / 64) * kBM * 128;
   // narrow tiles double-buffer the output staging: the TMA store of tile i drains while the
   // epilogue of tile i+1 fills the other buffer (the short-K 1x1 layers are epilogue bound)
-  static constexpr int kOutBufs = BN <= 128 ? 2 : 1;
+  static constexpr int kOutBufs = (BN <= 128 || (EPI == 4 && STAGES <= 4)) ? 2 : 1;
   static constexpr int kBarOffset = STAGES * kStageBytes + kOutBufs * kOutBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;
   // EPI == 3 (GroupNorm fused): gamma | beta (fp32 [BN] each) | pose bias (fp16 [8][BN]) |
@@ -667,12 +667,101 @@ __device__ __forceinline__ void conv_gn_epilogue_loop(const ConvParams& p, uint8
 struct Gn2Bars {
   uint64_t* tfull;      // [2]
   uint64_t* tempty;     // [2]
-  uint64_t* res;        // residual landed / staging free (store warp -> math warps)
+  uint64_t* res[2];     // per staging buffer: residual landed / buffer free (store warp -> math warps)
   uint64_t* part;       // s_part written (math warps -> statistics warp)
   uint64_t* stats;      // [2] tables of tile parity b ready (statistics warp -> math warps)
   uint64_t* tabfree;    // [2] last read of table buffer b done (math warps -> statistics warp)
-  uint64_t* out;        // staging tile written (math warps -> store warp)
+  uint64_t* out;        // [staging buffers] staging tile written (math warps -> store warp)
 };
+
+// Pass 2 of the EPI == 4 epilogue for the hot epilogue shapes, one 8-channel octet at a time with every
+// launch-uniform choice a template parameter: normalise, SiLU, pose bias / residual, pack and store of an octet form
+// one straight-line block, so the MUFU chains of one octet overlap the FMA / shared-memory work of its neighbours
+// (the phase-per-step form below runs all 128 MUFU operations of a thread back to back with the FMA pipe idle).
+//   NORM 1: y = x * sc[c] + sh[c] (tables: one image per tile, or the folded pre-norm)
+//        2: y = (x - mean) * rstd * gamma[c] + beta[c] ((mean, rstd) per (image, group): several images per tile)
+//        3: folded pre-norm with several images per tile: y = x * rstd - rstd * mean * w1[c] + wb[c]
+// Shared-memory operands are read with non-volatile asm loads whose address derives from the order token taken after
+// the barrier waits: the compiler may hoist them above the in-place stores (other octets, other addresses).
+template <int NORM, bool SILU, bool PB, bool RES, bool EMIT>
+__device__ __forceinline__ void gn2_pass2_octets(float* f, uint32_t a_sc, uint32_t a_sh, uint32_t a_mr, const int* og,
+                                                 int it_gpt, const float4* gm4, const float4* bt4, const uint4* pb4,
+                                                 bool img_ok, uint8_t* srow, uint32_t a_srow, int row, bool bf,
+                                                 float& e1, float& e2) {
+  float2 mr3 = make_float2(0.f, 0.f);
+  if (NORM == 3) mr3 = lds_f2(a_mr);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float* ff = f + j * 8;
+    const int sw = (j ^ (row & 7)) << 4;
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u), pv = make_uint4(0u, 0u, 0u, 0u);
+    if (RES) rv = lds_u4(a_srow + sw);
+    if (PB && img_ok) pv = __ldg(pb4 + j);
+    if (NORM == 1) {
+      const float4 s0 = lds_f4(a_sc + j * 32), s1 = lds_f4(a_sc + j * 32 + 16);
+      const float4 h0 = lds_f4(a_sh + j * 32), h1 = lds_f4(a_sh + j * 32 + 16);
+      ff[0] = fmaf(ff[0], s0.x, h0.x); ff[1] = fmaf(ff[1], s0.y, h0.y);
+      ff[2] = fmaf(ff[2], s0.z, h0.z); ff[3] = fmaf(ff[3], s0.w, h0.w);
+      ff[4] = fmaf(ff[4], s1.x, h1.x); ff[5] = fmaf(ff[5], s1.y, h1.y);
+      ff[6] = fmaf(ff[6], s1.z, h1.z); ff[7] = fmaf(ff[7], s1.w, h1.w);
+    } else if (NORM == 2) {
+      const float2 mr = lds_f2(a_mr + (it_gpt + og[j]) * 8);
+      const float4 g0 = __ldg(gm4 + 2 * j), g1 = __ldg(gm4 + 2 * j + 1);
+      const float4 t0 = __ldg(bt4 + 2 * j), t1 = __ldg(bt4 + 2 * j + 1);
+      ff[0] = fmaf(ff[0] - mr.x, mr.y * g0.x, t0.x); ff[1] = fmaf(ff[1] - mr.x, mr.y * g0.y, t0.y);
+      ff[2] = fmaf(ff[2] - mr.x, mr.y * g0.z, t0.z); ff[3] = fmaf(ff[3] - mr.x, mr.y * g0.w, t0.w);
+      ff[4] = fmaf(ff[4] - mr.x, mr.y * g1.x, t1.x); ff[5] = fmaf(ff[5] - mr.x, mr.y * g1.y, t1.y);
+      ff[6] = fmaf(ff[6] - mr.x, mr.y * g1.z, t1.z); ff[7] = fmaf(ff[7] - mr.x, mr.y * g1.w, t1.w);
+    } else if (NORM == 3) {
+      const float nm = -mr3.x * mr3.y;
+      const float4 g0 = __ldg(gm4 + 2 * j), g1 = __ldg(gm4 + 2 * j + 1);
+      const float4 t0 = __ldg(bt4 + 2 * j), t1 = __ldg(bt4 + 2 * j + 1);
+      ff[0] = fmaf(ff[0], mr3.y, fmaf(nm, g0.x, t0.x)); ff[1] = fmaf(ff[1], mr3.y, fmaf(nm, g0.y, t0.y));
+      ff[2] = fmaf(ff[2], mr3.y, fmaf(nm, g0.z, t0.z)); ff[3] = fmaf(ff[3], mr3.y, fmaf(nm, g0.w, t0.w));
+      ff[4] = fmaf(ff[4], mr3.y, fmaf(nm, g1.x, t1.x)); ff[5] = fmaf(ff[5], mr3.y, fmaf(nm, g1.y, t1.y));
+      ff[6] = fmaf(ff[6], mr3.y, fmaf(nm, g1.z, t1.z)); ff[7] = fmaf(ff[7], mr3.y, fmaf(nm, g1.w, t1.w));
+    }
+    if (SILU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ff[i] = silu_ftz(ff[i]);
+    }
+    if (PB) {
+      const uint32_t* hp = reinterpret_cast<const uint32_t*>(&pv);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const float2 t = unpack2(hp[k2], bf);
+        ff[2 * k2] += t.x;
+        ff[2 * k2 + 1] += t.y;
+      }
+    }
+    if (RES) {
+      const uint32_t* hr = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const float2 t = unpack2(hr[k2], bf);
+        ff[2 * k2] += t.x;
+        ff[2 * k2 + 1] += t.y;
+      }
+    }
+    uint4 w;
+    w.x = pack2(ff[0], ff[1], bf);
+    w.y = pack2(ff[2], ff[3], bf);
+    w.z = pack2(ff[4], ff[5], bf);
+    w.w = pack2(ff[6], ff[7], bf);
+    *reinterpret_cast<uint4*>(srow + sw) = w;
+    if (EMIT) {
+      const uint32_t* hw2 = reinterpret_cast<const uint32_t*>(&w);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const float2 t = unpack2(hw2[k2], bf);     // statistics of the values as stored (what the consumer reads)
+        e1 += t.x + t.y;
+        e2 = fmaf(t.x, t.x, e2);
+        e2 = fmaf(t.y, t.y, e2);
+      }
+    }
+  }
+}
+
 
 template <int BN, int STAGES>
 __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t* smem, uint8_t* gsm, uint32_t tmem_base,
@@ -681,10 +770,11 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
   using S = Conv2Smem<BN, STAGES, 4>;
   using G2 = Gn2Smem<BN>;
   constexpr int kOct = BN / 8;
-  uint8_t* ost = smem + STAGES * S::kStageBytes;
+  constexpr int kNB = S::kOutBufs;                   // staging buffers: tile i uses buffer i % kNB
+  uint8_t* ost0 = smem + STAGES * S::kStageBytes;
   float* s_part = reinterpret_cast<float*>(gsm + G2::kPart);
   const int* s_og = reinterpret_cast<const int*>(gsm + G2::kOg);
-  float2* s_em = reinterpret_cast<float2*>(gsm + G2::kEm);
+  float2* s_em0 = reinterpret_cast<float2*>(gsm + G2::kEm);
 
   const GnFuse& g = p.gn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -700,6 +790,18 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
   const bool wait_stats = g.G > 0 || pre;
   const bool bf = p.bf16 != 0;
   const uint32_t gsm_off = (uint32_t)(gsm - smem);
+  // pass-2 variant: the hot epilogue shapes run gn2_pass2_octets, everything else the phase-per-step code
+  int variant = -1;
+  if (!(g.out_lo || g.res_lo || (g.dbg & 6))) {
+    if (g.G > 0 && g.silu) {
+      const int nm2 = use_tab ? 0 : 1;
+      if (g.pb && !g.has_res && !g.emit) variant = nm2;                                   // Block 1: + pose bias
+      else if (!g.pb && g.has_res) variant = 2 + 2 * nm2 + (g.emit ? 1 : 0);              // Block 2: + residual
+    } else if (pre && g.G == 0 && !g.silu && !g.pb && !g.has_res && !g.emit) {
+      variant = g.ipt > 1 ? 7 : 6;                                                        // folded pre-norm (to_qkv)
+    }
+  }
+  if (g.dbg & 32) variant = -1;
 
   int acc = 0;
   uint32_t acc_phase = 0;
@@ -708,6 +810,9 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
   for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
     NOPE_TS(0);
     const int b = iter & 1;
+    const int ob = kNB == 2 ? (iter & 1) : 0;
+    uint8_t* ost = ost0 + ob * S::kOutBytes;
+    float2* s_em = s_em0 + ob * 32;
     const int m_pair = tile / p.n_tiles;
     const int n_tile = tile - m_pair * p.n_tiles;
     const int m_tile = 2 * m_pair + (int)rank;
@@ -778,7 +883,7 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
     NOPE_TS(2);
     if (wait_stats) mbar_wait(&B.stats[b], (iter >> 1) & 1);
     NOPE_TS(3);
-    mbar_wait(B.res, iter & 1);          // residual tile landed in the staging buffer / the buffer is free
+    mbar_wait(B.res[ob], (iter / kNB) & 1);      // residual tile landed in the staging buffer / the buffer is free
     NOPE_TS(4);
 
     // ---- pass 2: normalise / activate / add, in place in the swizzled staging tile
@@ -795,6 +900,25 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
     uint8_t* srow = ost + cc * (kBM * 128) + row * 128;
     const bool do_norm = g.G > 0 && !(g.dbg & 4);
     const bool do_silu = g.silu && !(g.dbg & 2);
+    const bool want_emit = g.emit != nullptr;
+    if (variant >= 0) {
+      const uint32_t a_srow = tok + (uint32_t)(srow - smem);
+      const float4* gm4 = reinterpret_cast<const float4*>((pre ? g.pre_w1 : g.gamma) + n_chan0 + cc * 64);
+      const float4* bt4 = reinterpret_cast<const float4*>((pre ? g.pre_wb : g.beta) + n_chan0 + cc * 64);
+      const uint4* pb4 = reinterpret_cast<const uint4*>(pb_row);
+      const int* og = s_og + cc * 8;
+      const int it_gpt = it * g.gpt;
+      switch (variant) {
+        case 0: gn2_pass2_octets<1, true, true, false, false>(f, a_sc, a_sh, a_mr, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+        case 1: gn2_pass2_octets<2, true, true, false, false>(f, a_sc, a_sh, a_mr, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+        case 2: gn2_pass2_octets<1, true, false, true, false>(f, a_sc, a_sh, a_mr, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+        case 3: gn2_pass2_octets<1, true, false, true, true>(f, a_sc, a_sh, a_mr, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+        case 4: gn2_pass2_octets<2, true, false, true, false>(f, a_sc, a_sh, a_mr, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+        case 5: gn2_pass2_octets<2, true, false, true, true>(f, a_sc, a_sh, a_mr, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+        case 6: gn2_pass2_octets<1, false, false, false, false>(f, a_sc, a_sh, a_mr, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+        default: gn2_pass2_octets<3, false, false, false, false>(f, a_sc, a_sh, a_mr + it * 8, og, it_gpt, gm4, bt4, pb4, img_ok, srow, a_srow, row, bf, e1, e2); break;
+      }
+    } else {
     // every step runs over all 64 values of the thread with its (launch-uniform) condition tested outside the
     // unrolled loop: one long basic block per step
     if (pre && g.ipt > 1) {
@@ -881,7 +1005,6 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
       }
     }
     const bool want_lo = g.out_lo && row_ok;
-    const bool want_emit = g.emit != nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint4 w;
@@ -906,6 +1029,7 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
           *reinterpret_cast<uint4*>(g.out_lo + (size_t)grow * p.n_total + n_chan0 + cc * 64 + j * 8) = wl;
       }
     }
+    }   // phase-per-step pass 2
     if (want_emit) {
       // 16-row segments: every image is a whole number of them at every resolution
 #pragma unroll
@@ -918,7 +1042,7 @@ __device__ __forceinline__ void conv_gn2_math_warps(const ConvParams& p, uint8_t
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(B.out);
+      mbar_arrive(&B.out[ob]);
       if (wait_stats) mbar_arrive(&B.tabfree[b]);
     }
     NOPE_TS(5);
@@ -947,6 +1071,14 @@ __device__ __forceinline__ void conv_gn2_stats_warp(const ConvParams& p, uint8_t
   if (!(g.G > 0 || pre)) return;          // residual / pose-bias-only epilogues: nothing to hand over
   for (int o = lane; o < kOct; o += 32) s_og[o] = (g.G > 0 && g.cpg < BN) ? (o * 8) / g.cpg : 0;
   __syncwarp();
+  // register-only exchange (see `fast` below): one image per tile, 128-row tiles, groups = whole octet blocks of the lanes
+  constexpr int kOpl = kOct / 8;                       // octets per lane: 32 lanes = 4 row segments x 8 octet blocks
+  const int cpt = g.cpg < BN ? g.cpg : BN;             // channels of a group inside the tile
+  const bool fast = use_tab && hw >= kBM && cpt % (kOpl * 8) == 0 && (g.gpt & (g.gpt - 1)) == 0 && g.gpt <= 8 &&
+                    g.gpt * cpt == BN;
+  const int lpp = 32 / g.gpt;                          // lanes per (image, group) pair
+  float gam[BN / 32], bet[BN / 32];
+  int tab_n_tile = -1;
   int iter = 0;
   for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
     const int b = iter & 1;
@@ -962,6 +1094,81 @@ __device__ __forceinline__ void conv_gn2_stats_warp(const ConvParams& p, uint8_t
     if (iter >= 2) mbar_wait(&B.tabfree[b], ((iter >> 1) - 1) & 1);   // tile iter-2 has read buffer b
 #define NOPE_TS2(k) do { if (g.ts && lane == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + (k)] = global_ns(); } while (0)
     NOPE_TS2(8);
+    if (fast) {
+      // ---- one image per tile, groups aligned to the lanes' octet blocks: the whole exchange in registers.
+      // lane -> (octet block lane >> 2 of kOct / 8 octets, row segment lane & 3); xor tree over the lanes of a group
+      if (n_tile != tab_n_tile) {
+        tab_n_tile = n_tile;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          gam[j] = __ldg(g.gamma + n_chan0 + lane + 32 * j);
+          bet[j] = __ldg(g.beta + n_chan0 + lane + 32 * j);
+        }
+      }
+      mbar_wait(B.part, iter & 1);
+      NOPE_TS2(9);
+      float ax = 0.f, aq = 0.f;
+#pragma unroll
+      for (int k = 0; k < kOpl; ++k) {
+        const float2 t = *reinterpret_cast<const float2*>(s_part + ((lane & 3) * kOct + (lane >> 2) * kOpl + k) * 2);
+        ax += t.x;
+        aq += t.y;
+      }
+      for (int off = 1; off < lpp; off <<= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, off);
+        aq += __shfl_xor_sync(0xffffffffu, aq, off);
+      }
+      const int sg = (m_tile / g.mt) * (p.n_tiles / g.tpg) + n_tile / g.tpg;
+      const int slot = (m_tile % g.mt) * g.tpg + (n_tile % g.tpg);
+      uint2* xp = g.xpart + (size_t)sg * g.expected * npairs * 2;
+      if ((lane & (lpp - 1)) == 0) {
+        const int pr = lane / lpp;
+        st_volatile_u2(xp + ((size_t)slot * npairs + pr) * 2, make_uint2(__float_as_uint(ax), g.epoch));
+        st_volatile_u2(xp + ((size_t)slot * npairs + pr) * 2 + 1, make_uint2(__float_as_uint(aq), g.epoch));
+      }
+      NOPE_TS2(10);
+      // word w = (slot * npairs + pair) * 2 + stat; 2 * npairs divides 32, so every word of lane l (w = l + 32 k)
+      // belongs to (pair, stat) = l mod (2 npairs): sum over k in registers, then over the lanes of that class
+      const int nw = g.expected * npairs * 2;        // <= 256 (host check)
+      uint2 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int w = lane + 32 * k;
+        u[k] = make_uint2(0u, g.epoch);
+        if (w < nw) u[k] = ld_volatile_u2(xp + w);
+      }
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int w = lane + 32 * k;
+        if (w < nw && u[k].y != g.epoch && !(g.dbg & 1)) {
+          const long long t0 = clock64();
+          do {
+            u[k] = ld_volatile_u2(xp + w);
+            if (clock64() - t0 > 4000000000LL) {
+              printf("nope_b200: GroupNorm tile sync timed out (block %d tile %d)\n", (int)blockIdx.x, tile);
+              __trap();
+            }
+          } while (u[k].y != g.epoch);
+        }
+        tot += __uint_as_float(u[k].x);
+      }
+      for (int off = 2 * npairs; off < 32; off <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+      NOPE_TS2(11);
+      const float o1 = __shfl_sync(0xffffffffu, tot, lane & ~1), o2 = __shfl_sync(0xffffffffu, tot, lane | 1);
+      const float mean_l = o1 * g.inv_cnt;                                  // lane l: group (l mod 2 npairs) >> 1
+      const float rstd_l = rsqrtf(fmaxf(o2 * g.inv_cnt - mean_l * mean_l, 0.f) + g.eps);
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) {
+        const int c = lane + 32 * j;
+        const int gl = g.cpg < BN ? c / g.cpg : 0;
+        const float mean = __shfl_sync(0xffffffffu, mean_l, 2 * gl);
+        const float rstd = __shfl_sync(0xffffffffu, rstd_l, 2 * gl);
+        const float sc = rstd * gam[j];
+        t_sc[c] = sc;
+        t_sh[c] = bet[j] - mean * sc;
+      }
+    } else
     if (g.G > 0) {
       mbar_wait(B.part, iter & 1);
       NOPE_TS2(9);
@@ -1127,14 +1334,16 @@ __device__ __forceinline__ void conv_gn2_store_warp(const ConvParams& p, uint8_t
   using S = Conv2Smem<BN, STAGES, 4>;
   using G2 = Gn2Smem<BN>;
   constexpr int kNS = BN / 64;
-  uint8_t* ost = smem + STAGES * S::kStageBytes;
-  const float2* s_em = reinterpret_cast<const float2*>(gsm + G2::kEm);
+  constexpr int kNB = S::kOutBufs;
+  uint8_t* ost0 = smem + STAGES * S::kStageBytes;
+  const float2* s_em0 = reinterpret_cast<const float2*>(gsm + G2::kEm);
   const GnFuse& g = p.gn;
   const int lane = threadIdx.x & 31;
   const int hw = p.stats_hw;
-  // the residual tile of tile t is TMA-loaded into the staging buffer (same box / swizzle as the store) once the
-  // previous store has read it; without a residual the same barrier just says "the buffer is free"
-  auto stage = [&](int t) {
+  // the residual tile of tile t is TMA-loaded into its staging buffer (same box / swizzle as the store) once the
+  // previous store from that buffer has read it; without a residual the same barrier just says "the buffer is free"
+  auto stage = [&](int t, int ob) {
+    if (t >= num_tiles) return;
     const int mp = t / p.n_tiles;
     const int nt = t - mp * p.n_tiles;
     const int mt2 = 2 * mp + (int)rank;
@@ -1142,17 +1351,22 @@ __device__ __forceinline__ void conv_gn2_store_warp(const ConvParams& p, uint8_t
       int bb, yy;
       conv_tile_coords(p, mt2, bb, yy);
       const int rb = g.res_div > 0 ? (g.res_base + bb) / g.res_div : bb;
-      mbar_expect_tx(B.res, S::kOutBytes);
+      uint8_t* dst = ost0 + ob * S::kOutBytes;
+      mbar_expect_tx(B.res[ob], S::kOutBytes);
 #pragma unroll 1
       for (int c2 = 0; c2 < kNS; ++c2)
-        tma_load_4d(ost + c2 * (kBM * 128), &p.rmap, B.res, nt * BN + c2 * 64, 0, yy, rb);
+        tma_load_4d(dst + c2 * (kBM * 128), &p.rmap, B.res[ob], nt * BN + c2 * 64, 0, yy, rb);
     } else {
-      mbar_arrive(B.res);
+      mbar_arrive(B.res[ob]);
     }
   };
-  if (lane == 0 && tile0 < num_tiles) stage(tile0);
+  if (lane == 0) {
+    stage(tile0, 0);
+    if (kNB == 2) stage(tile0 + tile_step, 1);
+  }
   int iter = 0;
   for (int tile = tile0; tile < num_tiles; tile += tile_step, ++iter) {
+    const int ob = kNB == 2 ? (iter & 1) : 0;
     const int m_pair = tile / p.n_tiles;
     const int n_tile = tile - m_pair * p.n_tiles;
     const int m_tile = 2 * m_pair + (int)rank;
@@ -1160,9 +1374,10 @@ __device__ __forceinline__ void conv_gn2_store_warp(const ConvParams& p, uint8_t
     int b0, y0;
     conv_tile_coords(p, m_tile, b0, y0);
     const int img0 = p.tiles_per_img > 0 ? m_tile / g.mt : m_tile * g.ipt;
-    mbar_wait(B.out, iter & 1);
+    mbar_wait(&B.out[ob], (iter / kNB) & 1);
     if (g.ts && lane == 0 && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + 13] = global_ns();
     if (g.emit && lane < g.ipt && img0 + lane < g.n_img) {
+      const float2* s_em = s_em0 + ob * 32;
       const int r16 = hw >= kBM ? 8 : (hw >> 4);
       float s1 = 0.f, s2 = 0.f;
       for (int h2 = 0; h2 < kNS; ++h2)
@@ -1174,15 +1389,18 @@ __device__ __forceinline__ void conv_gn2_store_warp(const ConvParams& p, uint8_t
     }
     __syncwarp();
     if (lane == 0) {
+      uint8_t* ost = ost0 + ob * S::kOutBytes;
 #pragma unroll 1
       for (int c2 = 0; c2 < kNS; ++c2)
         tma_store_4d(&p.omap[0], ost + c2 * (kBM * 128), n_tile * BN + c2 * 64, 0, y0, b0);
       tma_store_commit();
-      const int nt = tile + tile_step;
+      // the next user of this buffer is tile iter + kNB: hand it over once this store has read the buffer (with two
+      // buffers the math warps meanwhile work in the other one)
+      const int nt = tile + kNB * tile_step;
       if (nt < num_tiles) {
         tma_store_wait_read0();
         if (g.ts && iter < 64) g.ts[((size_t)blockIdx.x * 64 + iter) * 16 + 14] = global_ns();
-        stage(nt);
+        stage(nt, ob);
       }
     }
     __syncwarp();
@@ -1208,8 +1426,8 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);     // EPI >= 3: residual tile landed
-  uint64_t* gn2_bar = res_bar + 1;                                    // EPI == 4: part, stats[2], tabfree[2], out
-  static_assert((2 * STAGES + 4 + 2 + 6) * 8 <= 256, "barrier block overflow");
+  uint64_t* gn2_bar = res_bar + 1;                                    // EPI == 4: part, stats[2], tabfree[2], out[2], res of buffer 1
+  static_assert((2 * STAGES + 4 + 2 + 8) * 8 <= 256, "barrier block overflow");
   float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
 
   const int warp = threadIdx.x >> 5;
@@ -1241,7 +1459,9 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
       mbar_init(&gn2_bar[2], 1);                                        // stats[1]
       mbar_init(&gn2_bar[3], gn_epi_warps(BN));                         // tabfree[0]
       mbar_init(&gn2_bar[4], gn_epi_warps(BN));                         // tabfree[1]
-      mbar_init(&gn2_bar[5], gn_epi_warps(BN));                         // out
+      mbar_init(&gn2_bar[5], gn_epi_warps(BN));                         // out[0]
+      mbar_init(&gn2_bar[6], gn_epi_warps(BN));                         // out[1]
+      mbar_init(&gn2_bar[7], 1);                                        // res of staging buffer 1
     }
     fence_mbar_init();
   }
@@ -1328,7 +1548,7 @@ conv_tc2_kernel(const __grid_constant__ ConvParams p) {
     // ===================== epilogue with GroupNorm fused, bookkeeping on warps 2 / 3 =====================
     if constexpr (EPI == 4) {
       Gn2Bars B;
-      B.tfull = tfull_bar; B.tempty = tempty_bar; B.res = res_bar;
+      B.tfull = tfull_bar; B.tempty = tempty_bar; B.res[0] = res_bar; B.res[1] = &gn2_bar[7];
       B.part = &gn2_bar[0]; B.stats = &gn2_bar[1]; B.tabfree = &gn2_bar[3]; B.out = &gn2_bar[5];
       uint8_t* gsm = smem + S::kGnOffset;
       if (warp == 2) conv_gn2_store_warp<BN, STAGES>(p, smem, gsm, B, tile0, tile_step, num_tiles, rank);
@@ -1483,7 +1703,10 @@ inline int launch_conv_gn(const ConvParams& p, int bn, int num_sms, cudaStream_t
     }
   } else {
     switch (bn) {
-      case 192: return launch_conv_tc2_t<192, 6, 4>(p, num_sms, stream);
+      // 1x1 layers (<= 4 K-steps per tile) are bound by their epilogue: a 4-deep ring leaves room for a second
+      // output staging buffer, so the math warps never wait for a store to drain
+      case 192: return p.ksteps <= 4 ? launch_conv_tc2_t<192, 4, 4>(p, num_sms, stream)
+                                     : launch_conv_tc2_t<192, 6, 4>(p, num_sms, stream);
       case 128: return launch_conv_tc2_t<128, 6, 4>(p, num_sms, stream);
       case 64: return launch_conv_tc2_t<64, 8, 4>(p, num_sms, stream);
     }
