@@ -1695,6 +1695,10 @@ inline int launch_conv_gn(const ConvParams& p, int bn, int num_sms, cudaStream_t
     const char* e = getenv("NOPE_GN_EPI");
     return e && atoi(e) == 3 ? 3 : 4;
   }();
+  // NOPE_GN_SHORTK=k: layers of <= k K-steps per tile take the 4-deep ring + two staging buffers.  Measured (ncu launch
+  // list, to_qkv 192 -> 384 at 32x32, 3 K-steps per tile): 275 us against 203 us on the 6-deep ring with one staging
+  // buffer -- these layers are bound by load latency (two tiles in flight beat a free staging buffer): default off
+  static const int short_k = getenv("NOPE_GN_SHORTK") ? atoi(getenv("NOPE_GN_SHORTK")) : 0;
   if (epi == 3) {
     switch (bn) {
       case 192: return launch_conv_tc2_t<192, 6, 3>(p, num_sms, stream);
@@ -1703,10 +1707,8 @@ inline int launch_conv_gn(const ConvParams& p, int bn, int num_sms, cudaStream_t
     }
   } else {
     switch (bn) {
-      // 1x1 layers (<= 4 K-steps per tile) are bound by their epilogue: a 4-deep ring leaves room for a second
-      // output staging buffer, so the math warps never wait for a store to drain
-      case 192: return p.ksteps <= 4 ? launch_conv_tc2_t<192, 4, 4>(p, num_sms, stream)
-                                     : launch_conv_tc2_t<192, 6, 4>(p, num_sms, stream);
+      case 192: return p.ksteps <= short_k ? launch_conv_tc2_t<192, 4, 4>(p, num_sms, stream)
+                                           : launch_conv_tc2_t<192, 6, 4>(p, num_sms, stream);
       case 128: return launch_conv_tc2_t<128, 6, 4>(p, num_sms, stream);
       case 64: return launch_conv_tc2_t<64, 8, 4>(p, num_sms, stream);
     }
