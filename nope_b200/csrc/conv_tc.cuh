@@ -109,6 +109,7 @@ struct ConvParams {
   // (py, px) shifts every tap by (+py, +px), reads weight rows parity * n_per_par + ..., and
   // stores through omap[parity] (the stride-2 sub-lattice of the 2H x 2W output).
   int bf16;           // operands and the stored output are bf16 instead of fp16 (plain / GroupNorm-fused epilogues)
+  int l2_prefetch;    // 2-CTA kernel: the producer prefetches the next tile's activation rows into L2
   int n_par;          // 1 or 4
   int n_tiles_par;    // channel tiles per parity (== n_tiles when n_par == 1)
   int src_w, src_hw;  // n_par == 4: width / pixels of one SOURCE image (out_lo addressing)

@@ -661,6 +661,8 @@ struct nope_unet {
     p.bmap = L.wmap;
     p.bmap_half = L.wmap_half;
     p.bf16 = bf() ? 1 : 0;
+    static const int l2pf = std::getenv("NOPE_L2_PREFETCH") ? std::atoi(std::getenv("NOPE_L2_PREFETCH")) : 0;   // measured 3 % slower when on
+    p.l2_prefetch = l2pf;
     if (L.mode == 3) {
       for (int t = 0; t < 4; ++t) {
         if (get_map(&m, out.hi, cap_img, L.cout, g, t)) return -1;   // stride-2 sub-lattice (py, px)
@@ -960,7 +962,8 @@ struct nope_unet {
     // GroupNorm(1) epilogue with its cross-tile exchange measured slower than the plain convolution plus one
     // normalisation pass (319 vs 244 us at 32x32), so this layer keeps the two-kernel form unless the
     // split-precision mode needs the (hi, lo) output pair
-    if (fused() && split()) {
+    static const bool fuse_to_out = std::getenv("NOPE_FUSE_TO_OUT") && std::atoi(std::getenv("NOPE_FUSE_TO_OUT"));   // A/B
+    if (fused() && (split() || fuse_to_out)) {
       GnSpec s;
       s.norm = &norms.at(p + ".outnorm");
       s.res = x;

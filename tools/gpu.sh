@@ -27,7 +27,7 @@ case "$step" in
   benchall) for spec in "parity:--precision parity" "cfg2_fp16:--queries 8 --poses 2562" "cfg2_bf16:--queries 8 --poses 2562 --precision bf16" "ldm:--variant ldm" "ref:--impl reference"; do
               name=${spec%%:*}; fl=${spec#*:}; run "bench $name" 900 python bench.py --steps 10 --warmup 3 $fl > gpurun_out/bench_$name.log 2>&1; tail -1 gpurun_out/bench_$name.log | cut -c 1-900; done ;;
   smoke)    run "smoke" 900 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log ;;
-  launches2) NOPE_PLAIN_EPI0=1 NOPE_GN_SHORTK=${SHORTK:-0} timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_b.csv python tools/profile_step.py > gpurun_out/ncu_list_b.log 2>&1
+  launches2) env ${ENV_B:-NOPE_FUSE_TO_OUT=1} timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_b.csv python tools/profile_step.py > gpurun_out/ncu_list_b.log 2>&1
             python tools/summarize_launches.py gpurun_out/launches_b.csv > gpurun_out/launch_summary_b.txt 2>&1; head -12 gpurun_out/launch_summary_b.txt ;;
   launches) run "ncu launch list" 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_list.log 2>&1
             python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launch_summary.txt 2>&1; head -30 gpurun_out/launch_summary.txt ;;
