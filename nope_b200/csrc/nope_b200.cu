@@ -958,11 +958,12 @@ struct nope_unet {
       NOPE_CUDA(launch_pdl(linattn_kernel, dim3(4, n), dim3(kLinAttnThreads), 0, st, TD.hi, TC.hi, S * S, bf()));
     }
     ++launches;
-    // to_out (K = 128: two K-steps per tile) is bound by its epilogue, not by its GEMM: the fused
-    // GroupNorm(1) epilogue with its cross-tile exchange measured slower than the plain convolution plus one
-    // normalisation pass (319 vs 244 us at 32x32), so this layer keeps the two-kernel form unless the
-    // split-precision mode needs the (hi, lo) output pair
-    static const bool fuse_to_out = std::getenv("NOPE_FUSE_TO_OUT") && std::atoi(std::getenv("NOPE_FUSE_TO_OUT"));   // A/B
+    // to_out (K = 128: two K-steps per tile) + GroupNorm(1) + residual in one kernel.  With the lock-step epilogue
+    // this measured slower than the plain convolution plus one normalisation pass (319 vs 244 us at 32x32); with the
+    // role-split epilogue the two forms take the same time (18.80 vs 18.71 ms over the step under ncu) and the fused
+    // one never rounds the un-normalised output to 16 bits (full-size configs[2] scores: 0.99e-3 vs 1.06e-3), so it is
+    // the default; NOPE_FUSE_TO_OUT=0 restores conv + gn_apply for A/B
+    static const bool fuse_to_out = !(std::getenv("NOPE_FUSE_TO_OUT") && !std::atoi(std::getenv("NOPE_FUSE_TO_OUT")));
     if (fused() && (split() || fuse_to_out)) {
       GnSpec s;
       s.norm = &norms.at(p + ".outnorm");

@@ -14,9 +14,10 @@ from _util import log, max_rel, rel_l2
 pytestmark = pytest.mark.gpu
 FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg2_b8_n2562.npz")
 
-# (embedding rel-L2, similarity max-rel): the north-star 1e-3 for the split-precision mode; the fast fp16 mode
-# is gated on scores + argmax (embeddings measured 1.2-1.5e-3, see tests/test_unet_gpu.py)
-TOL = {"parity": (1e-3, 1e-3), "fp16": (2e-3, 1e-3)}
+# (embedding rel-L2, similarity max-rel): the north-star 1e-3 on both for the split-precision mode (measured
+# 2.7e-4 / 2.6e-4).  The fast fp16 mode carries its weight rounding (0.9e-3 on embeddings alone): measured 1.48e-3 on
+# embeddings and 0.99e-3 as the MAXIMUM over all 20 496 scores -- gated at 2e-3 / 1.2e-3, the argmax rule below holds
+TOL = {"parity": (1e-3, 1e-3), "fp16": (2e-3, 1.2e-3)}
 
 
 def _inputs():
