@@ -31,6 +31,8 @@ case "$step" in
             python tools/summarize_launches.py gpurun_out/launches_b.csv > gpurun_out/launch_summary_b.txt 2>&1; head -12 gpurun_out/launch_summary_b.txt ;;
   pipe)     run "ncu tensor-pipe list" 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/pipe.csv python tools/profile_step.py > gpurun_out/ncu_pipe.log 2>&1
             python tools/summarize_pipe.py gpurun_out/pipe.csv gpurun_out/pipe_per_launch.csv > gpurun_out/pipe_summary.txt 2>&1; cat gpurun_out/pipe_summary.txt ;;
+  pipe_cfg2) NOPE_POSES=2562 NOPE_QUERIES=8 run "ncu tensor-pipe list, configs[2] size (first 420 launches)" 900 ncu --profile-from-start off -c 420 --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/pipe_cfg2.csv python tools/profile_step.py > gpurun_out/ncu_pipe_cfg2.log 2>&1
+            python tools/summarize_pipe.py gpurun_out/pipe_cfg2.csv gpurun_out/pipe_cfg2_per_launch.csv > gpurun_out/pipe_cfg2_summary.txt 2>&1; cat gpurun_out/pipe_cfg2_summary.txt ;;
   launches) run "ncu launch list" 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_list.log 2>&1
             python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launch_summary.txt 2>&1; head -30 gpurun_out/launch_summary.txt ;;
   ncu_conv) run "ncu full: conv" 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc -c ${NCU_COUNT:-70} -o /tmp/prof_conv -f python tools/profile_step.py > gpurun_out/ncu_conv.log 2>&1
