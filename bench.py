@@ -472,18 +472,6 @@ def main_ldm(args):
     launches = m.last_launch_count
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
-
-    # ---- BASELINE configs[3] beside the weak-scaling headline: the FIXED 10 248-pose grid (level-3 icosphere x 4
-    # in-plane rotations) split over the ranks -- the driver's `--gpus N` runs carry the strong-scaling figure too
-    strong_extra = None
-    if world > 1 and not strong and not args.no_extras:
-        poses_s = synthetic_pose_batch(10248, Q)[0].to(dev)
-        ms_s = timed(lambda: model.dist.sweep(unet, r_feat, poses_s, q_feat, k=5, want_emb=False), 3, 3)
-        strong_extra = {"workload": f"configs[3]: a FIXED 10248-pose grid sharded {world}-way "
-                                    f"({-(-10248 // world)} poses per GPU), batch={Q}, same timing rules, 3 steps",
-                        "global_poses": 10248, "value": Q * 10248 / (ms_s * 1e-3), "unit": "hyp/s",
-                        "ms_per_step": ms_s, "scaling": "strong"}
-        del poses_s
     m.profile(True)
     step_resident()
     prof = m.profile_read()
@@ -657,6 +645,18 @@ def main():
     launches_per_step = unet.last_launch_count
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    # ---- BASELINE configs[3] beside the weak-scaling headline: the FIXED 10 248-pose grid (level-3 icosphere x 4
+    # in-plane rotations) split over the ranks -- the driver's `--gpus N` runs carry the strong-scaling figure too
+    strong_extra = None
+    if world > 1 and not strong and not args.no_extras:
+        poses_s = synthetic_pose_batch(10248, Q)[0].to(dev)
+        ms_s = timed(lambda: model.dist.sweep(unet, r_feat, poses_s, q_feat, k=5, want_emb=False), 3, 3)
+        strong_extra = {"workload": f"configs[3]: a FIXED 10248-pose grid sharded {world}-way "
+                                    f"({-(-10248 // world)} poses per GPU), batch={Q}, same timing rules, 3 steps",
+                        "global_poses": 10248, "value": Q * 10248 / (ms_s * 1e-3), "unit": "hyp/s",
+                        "ms_per_step": ms_s, "scaling": "strong"}
+        del poses_s
 
     # ---- roofline of the dominant kernel (tcgen05 convolution), CUDA events per launch
     def conv_profile(u, step):

@@ -908,7 +908,7 @@ struct nope_ldm {
     ++launches;
     if (cross_terms(poses + (size_t)hyp0 * rot_dim, n, st)) return -1;
     int S = S0;
-    bcast_add_kernel<<<ew_grid((long long)n * S * S * mc / 8), 256, 0, st>>>(x0ref, ref_of, nullptr, 0, 0, HS[0], n,
+    bcast_add_kernel<<<dim3(ew_grid((long long)S * S * mc / 8 / 4), n), 256, 0, st>>>(x0ref, ref_of, nullptr, 0, 0, HS[0], n,
                                                                            S * S, mc);
     NOPE_CUDA(cudaGetLastError());
     ++launches;
@@ -921,7 +921,7 @@ struct nope_ldm {
       if (b.kind == 1 && i == 1 && hoist) {
         // prefix computed per reference in prestage(): broadcast the ResBlock output (the
         // transformer's residual) and enter the transformer at the cross-attention
-        bcast_add_kernel<<<ew_grid((long long)n * S * S * mc / 8), 256, 0, st>>>(Rref, ref_of, nullptr, 0, 0, R, n,
+        bcast_add_kernel<<<dim3(ew_grid((long long)S * S * mc / 8 / 4), n), 256, 0, st>>>(Rref, ref_of, nullptr, 0, 0, R, n,
                                                                                S * S, mc);
         NOPE_CUDA(cudaGetLastError());
         ++launches;

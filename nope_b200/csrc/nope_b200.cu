@@ -1035,9 +1035,9 @@ struct nope_unet {
 
     // r (= init_conv output) and the hoisted block1 output, broadcast per hypothesis
     const int hw0 = S0 * S0;
-    NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)n * hw0 * dim / 8)), dim3(256), 0, st, x0.hi, ref_of,
+    NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)hw0 * dim / 8 / 4), n), dim3(256), 0, st, x0.hi, ref_of,
                          nullptr, 0, 0, RB.hi, n, hw0, dim, sp ? x0.lo : nullptr, sp ? RB.lo : nullptr, bf()));
-    NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)n * hw0 * dim / 8)), dim3(256), 0, st, g1.hi, ref_of,
+    NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)hw0 * dim / 8 / 4), n), dim3(256), 0, st, g1.hi, ref_of,
                          pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, sp ? g1.lo : nullptr,
                          sp ? TB.lo : nullptr, bf()));
     launches += 2;
@@ -1113,7 +1113,7 @@ struct nope_unet {
     if (tap("final_conv.0", A(curb, dim), dim, S, n, st)) return -1;
     const int hw = S * S;
     const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
-    NOPE_CUDA(launch_pdl(final_conv_score_kernel, dim3(nslab, n), dim3(kFinalThreads), (size_t)Cl * dim * sizeof(float),
+    NOPE_CUDA(launch_pdl(final_conv_score_kernel, dim3(nslab, n), dim3(kFinalThreads), (size_t)kMaxLatent * dim * sizeof(float),
                          st, curb.hi, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat,
                          ref_of, score_part ? score_part + (size_t)hyp0 * nslab * kScoreParts : nullptr, hw, dim, Cl,
                          sp ? curb.lo : nullptr, metric, occ_threshold, bf()));

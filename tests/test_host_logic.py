@@ -59,3 +59,43 @@ def test_loss_type_and_compute_loss():
     assert float(m.compute_loss(a, b)) == 1.0
     m1 = PoseConditional(_unet(), optim_config={"loss_type": "l1"})
     assert float(m1.compute_loss(a * 3, b)) == 3.0
+
+
+def test_scripts_have_no_undefined_names():
+    """bench.py / __graft_entry__.py paths that only run on a multi-GPU box (torchrun legs) cannot be exercised
+    here; at least every name a function loads must be bound in it, at module level, or be a builtin."""
+    import ast
+    import builtins
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for script in ("bench.py", "__graft_entry__.py"):
+        tree = ast.parse(open(os.path.join(root, script)).read())
+
+        def bound_in(scope):
+            out = set()
+            for n in ast.walk(scope):
+                if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store):
+                    out.add(n.id)
+                elif isinstance(n, ast.arg):
+                    out.add(n.arg)
+                elif isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                    out.add(n.name)
+                elif isinstance(n, (ast.Import, ast.ImportFrom)):
+                    out.update((a.asname or a.name).split(".")[0] for a in n.names)
+                elif isinstance(n, ast.ExceptHandler) and n.name:
+                    out.add(n.name)
+            return out
+
+        module_names = set(dir(builtins))
+        for n in tree.body:                      # module level only (not the bodies of other functions)
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                module_names.add(n.name)
+            elif isinstance(n, (ast.Import, ast.ImportFrom)):
+                module_names.update((a.asname or a.name).split(".")[0] for a in n.names)
+            elif isinstance(n, (ast.Assign, ast.AugAssign, ast.AnnAssign, ast.If, ast.Try, ast.With, ast.For)):
+                module_names |= bound_in(n)
+        for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+            names = module_names | bound_in(fn)
+            missing = {n.id for n in ast.walk(fn) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)
+                       and n.id not in names}
+            assert not missing, (script, fn.name, sorted(missing))
