@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--conv-impl", default=os.environ.get("NOPE_CONV_IMPL", "tcgen05_2cta"),
                     choices=["tcgen05", "tcgen05_2cta"])
     ap.add_argument("--precision", default=os.environ.get("NOPE_PRECISION", "fp16"),
-                    choices=["fp16", "fp16_w2", "parity", "bf16"],
+                    choices=["fp16", "fp16_w2", "parity", "parity_fast", "bf16"],
                     help="engine precision of the headline number (config.precision); the other modes are timed "
                          "beside it under `modes` at N=1")
     ap.add_argument("--global-poses", type=int, default=0,
@@ -239,6 +239,8 @@ PRECISION_NOTES = {
     "fp16": "fp16 operands, fp32 accumulate/statistics; GroupNorm+SiLU fused into the conv epilogue",
     "fp16_w2": "exact weights: W = W_hi + W_lo fp16 K-segments (2x MMA work), fp16 activations",
     "parity": "split precision: exact weights + activations as fp16 (hi, lo) pairs, 3 products per tap (3x MMA work)",
+    "parity_fast": "split precision on the residual stream / skips / resampled maps (fp16 (hi, lo) pairs, exact weights); "
+                   "the tensor inside each ResnetBlock is a single fp16: 2 products per tap in block2, 3 elsewhere",
     "bf16": "bf16 weights and activations (BASELINE configs[2] names bf16), fp32 accumulate/statistics; embeddings "
             "1e-2 / scores 7e-3 of the fp32 reference -- outside the 1e-3 bar, as bf16 autocast is on the reference itself",
 }
@@ -685,7 +687,7 @@ def main():
     if extras:
         del model, unet
         torch.cuda.empty_cache()
-        for mode in ("fp16", "fp16_w2", "parity", "bf16"):
+        for mode in ("fp16", "fp16_w2", "parity", "parity_fast", "bf16"):
             if mode in modes:
                 continue
             try:

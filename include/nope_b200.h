@@ -78,7 +78,9 @@ int nope_unet_set_conv_impl(nope_unet_t* u, int impl);
  *       each convolution accumulates A W_hi + A W_lo (2x the tensor-core work), 2 = split precision:
  *       exact weights and activations carried as fp16 pairs, A_hi W_hi + A_hi W_lo + A_lo W_hi (3x;
  *       the "parity" mode that meets the 1e-3 embedding tolerance with margin), 3 = bf16 operands and
- *       activations (BASELINE configs[2]; 8-bit mantissa: embeddings ~1e-2 of the fp32 reference);
+ *       activations (BASELINE configs[2]; 8-bit mantissa: embeddings ~1e-2 of the fp32 reference),
+ *       4 = split precision with single-fp16 tensors inside the ResnetBlocks (block2 convolutions run two
+ *       products instead of three; embeddings ~5e-4: the fastest mode inside the 1e-3 tolerance);
  *   "fuse_gn" (default 1): GroupNorm + SiLU + pose bias + residual run in the epilogue of the producing
  *       convolution (Block.forward / ResnetBlock.forward, model_utils.py:237-279); 0 = separate
  *       gn_apply pass (round-1 schedule; also what conv_impl 0 / 1 use);

@@ -159,7 +159,11 @@ struct nope_unet {
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   }
   bool fused() const { return fuse_gn && conv_impl == 2; }
-  bool split() const { return precision == 2 && fused(); }
+  bool split() const { return (precision == 2 || precision == 4) && fused(); }
+  // precision 4: the residual stream, skip tensors and resampled maps keep their (hi, lo) pair, the tensor INSIDE a
+  // ResnetBlock (block1's output h, consumed only by block2's convolution) is a single fp16 value -- block2 runs two
+  // products per tap instead of three.  CPU budget (tools/precision_sim.py): h alone costs 4.3e-4 on the embeddings.
+  bool h_lo() const { return precision == 2 && fused(); }
   bool bf() const { return precision == 3; }     // bf16 storage (BASELINE configs[2]); fp16 otherwise
 
   // ------------------------------------------------------------------ schema
@@ -263,7 +267,7 @@ struct nope_unet {
     const int taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
     L.cin = mode == 2 ? (int)sh[1] / 4 : (int)sh[1];
     L.K = L.cin * taps;
-    const bool wlo = precision == 1 || precision == 2;
+    const bool wlo = precision == 1 || precision == 2 || precision == 4;
     L.Kp = wlo ? 2 * L.K : L.K;
     NOPE_CHECK(L.cin % 64 == 0, wkey + ": input channels must be a multiple of 64");
     L.bn = pick_bn(L.cout);
@@ -462,7 +466,7 @@ struct nope_unet {
   }
   size_t layout(Bump& b, int c_hyp, int c_ref, int n_total_scores) {
     const size_t c = (size_t)c_hyp, r = (size_t)c_ref;
-    const bool lo = precision == 2;
+    const bool lo = precision == 2 || precision == 4;
     // temporaries hold the widest full-resolution tensor: a concat-conv output (<= 2*dim
     // channels) or the attention qkv tensor (3 x 128 channels, independent of dim)
     const size_t big = (size_t)S0 * S0 * std::max(dim * 2, 3 * kHeadsHidden);
@@ -889,9 +893,10 @@ struct nope_unet {
     const int parts = st_parts_of(S);
     auto it = convs.find(p + ".res");
     if (fused()) {
-      Act h(TB.hi, co, split() ? TB.lo : nullptr);
+      Act h(TB.hi, co, h_lo() ? TB.lo : nullptr);
       if (hoisted_h) {
         h = *hoisted_h;
+        if (!h_lo()) h.lo = nullptr;
       } else {
         GnSpec s1;
         s1.norm = &norms.at(p + ".norm1");
@@ -1012,7 +1017,7 @@ struct nope_unet {
       GnSpec s;
       s.norm = &norms.at("downs.0.0.norm1");
       s.silu = true;
-      return conv(convs.at("downs.0.0.block1"), xin, Act(), Act(g1.hi, dim, split() ? g1.lo : nullptr), S0, B,
+      return conv(convs.at("downs.0.0.block1"), xin, Act(), Act(g1.hi, dim, h_lo() ? g1.lo : nullptr), S0, B,
                   cap_ref, st, nullptr, &s);
     }
     if (conv(convs.at("downs.0.0.block1"), xin, Act(), Act(pt, dim), S0, B, cap_ref, st, SA)) return -1;
@@ -1038,8 +1043,8 @@ struct nope_unet {
     NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)hw0 * dim / 8 / 4), n), dim3(256), 0, st, x0.hi, ref_of,
                          nullptr, 0, 0, RB.hi, n, hw0, dim, sp ? x0.lo : nullptr, sp ? RB.lo : nullptr, bf()));
     NOPE_CUDA(launch_pdl(bcast_add_kernel, dim3(ew_grid((long long)hw0 * dim / 8 / 4), n), dim3(256), 0, st, g1.hi, ref_of,
-                         pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, sp ? g1.lo : nullptr,
-                         sp ? TB.lo : nullptr, bf()));
+                         pb, P, pb_off.at("downs.0.0"), TB.hi, n, hw0, dim, h_lo() ? g1.lo : nullptr,
+                         h_lo() ? TB.lo : nullptr, bf()));
     launches += 2;
     if (tap("init_conv", A(RB, dim), dim, S0, n, st)) return -1;
 
@@ -1249,7 +1254,7 @@ int nope_unet_set_option(nope_unet_t* u, const char* name, int value) {
   if (std::strcmp(name, "precision") == 0) {
     NOPE_CHECK(!u->finalized, "precision must be set before nope_unet_finalize");
     NOPE_CHECK(value == 0 || u->conv_impl != 1, "the SIMT debug convolution only runs fp16 weights");
-    NOPE_CHECK(value >= 0 && value <= 3, "precision must be 0 (fp16), 1 (exact weights), 2 (split) or 3 (bf16)");
+    NOPE_CHECK(value >= 0 && value <= 4, "precision must be 0 (fp16), 1 (exact weights), 2 (split), 3 (bf16) or 4 (split, fp16 inside ResnetBlocks)");
     u->precision = value;
     return 0;
   }

@@ -227,8 +227,8 @@ def build_model(u_net_dim=192, descriptor_size=8, device="cuda:0", chunk=642,
                 similarity_metric="l2", precision="fp16"):
     """The one configuration the reference resolves: configs/model/template_base.yaml.
     precision: "fp16" (fast), "fp16_w2" (exact weights), "parity" (split precision, meets the
-    1e-3 embedding tolerance of the fp32 reference with margin) or "bf16" (BASELINE configs[2]:
-    bf16 storage, ~1e-2)."""
+    1e-3 embedding tolerance of the fp32 reference with margin: 2.2e-4), "parity_fast" (the same with single-fp16
+    tensors inside the ResnetBlocks: ~5e-4, 15 % faster) or "bf16" (BASELINE configs[2]: bf16 storage, ~1e-2)."""
     from .encoder import FeatureExtractor
     from .unet import UNet
     enc = FeatureExtractor(descriptor_size=descriptor_size, threshold=0.2, normalize=False)

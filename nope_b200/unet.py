@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 # precision option of the engine (include/nope_b200.h, nope_unet_set_option)
-PRECISIONS = {"fp16": 0, "fp16_w2": 1, "parity": 2, "bf16": 3}
+PRECISIONS = {"fp16": 0, "fp16_w2": 1, "parity": 2, "bf16": 3, "parity_fast": 4}
 
 
 class _Incompatible:

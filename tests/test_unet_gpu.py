@@ -221,6 +221,31 @@ def test_parity_mode_meets_the_north_star_tolerance(gpu_model_parity, gpu_model,
     assert torch.equal(out4["sim"], out3["sim"]) and torch.equal(out4["topi"], out3["topi"])
 
 
+def test_parity_fast_mode_meets_the_north_star_tolerance(seeded_state_dict, golden_dir):
+    """precision="parity_fast": (hi, lo) pairs on the residual stream, skips and resampled maps, a single fp16 inside
+    each ResnetBlock (block2 runs two products per tap).  Budget from tools/precision_sim.py: 4.3e-4 from those tensors
+    on top of the parity mode's 2.2e-4; gated at the same north-star 1e-3 on embeddings and scores, top-5 identical."""
+    from nope_b200.model import build_model
+    m = build_model(device="cuda:0", precision="parity_fast")
+    m.load_state_dict(seeded_state_dict)
+    g = np.load(f"{golden_dir}/cfg1_b1_n6.npz")
+    out = m.u_net.sweep(torch.from_numpy(g["ref_feat"]), torch.from_numpy(g["all_relativeR"]),
+                        query_feat=torch.from_numpy(g["query_feat"]), want_emb=True, k=5)
+    e1 = rel_l2(out["emb"], torch.from_numpy(g["emb"]))
+    s1 = max_rel(out["sim"], torch.from_numpy(g["similarity"]))
+    g3 = np.load(f"{golden_dir}/level2_642_b1.npz")
+    out3 = m.u_net.sweep(torch.from_numpy(g3["ref_feat"]), torch.from_numpy(g3["all_relativeR"]),
+                         query_feat=torch.from_numpy(g3["query_feat"]), want_emb=True, k=5)
+    e3 = max(rel_l2(out3["emb"][0, 0], torch.from_numpy(g3["emb_n0"])),
+             rel_l2(out3["emb"][0, 641], torch.from_numpy(g3["emb_n641"])))
+    s3 = max_rel(out3["sim"], torch.from_numpy(g3["similarity"]))
+    log("parity_fast_mode", cfg1_emb=e1, cfg1_sim=s1, level2_642_emb=e3, level2_642_sim=s3,
+        swaps_642=_swaps(g3["nearest_idx"], out3["topi"]), launches=m.u_net.last_launch_count)
+    assert e1 < EMB_TOL_PARITY and s1 < SIM_TOL and e3 < EMB_TOL_PARITY and s3 < SIM_TOL
+    assert torch.equal(out["topi"].cpu(), torch.from_numpy(g["nearest_idx"]))
+    assert torch.equal(out3["topi"].cpu(), torch.from_numpy(g3["nearest_idx"]))
+
+
 def test_exact_weights_mode(seeded_state_dict, golden_dir):
     """precision="fp16_w2" (W_hi + W_lo K-segments, fp16 activations): measured between the two other
     modes; gated at the fast mode's tolerance."""
