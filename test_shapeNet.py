@@ -44,7 +44,7 @@ def main(argv=None):
     ap.add_argument("--grid", type=int, default=642, help="pose-grid size (642 = level 2 'all'; 26/341 'upper')")
     ap.add_argument("--categories", default="bottle,mug", help="comma list out of the reference's test_cats, or 'all'")
     ap.add_argument("--metric", default="l2", choices=["l2", "cosine", "cosine_occlusion"])
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16_w2", "parity", "bf16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16_w2", "parity", "parity_fast", "bf16"])
     ap.add_argument("--save-dir", default=None, help="predictions/pred_<cat>_step<k>_rank<r>.npz are written here")
     ap.add_argument("--json-out", default=None)
     args = ap.parse_args(argv)

@@ -42,6 +42,14 @@ case "$step" in
   dist)     N=${NGPU:-2}; run "dist_check N=$N" 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; tail -12 gpurun_out/dist_check_$N.log ;;
   benchN)   N=${NGPU:-2}; run "bench N=$N weak" 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.log 2>&1; tail -1 gpurun_out/bench_n$N.log | cut -c 1-600
             run "bench N=$N strong 10248" 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --global-poses 10248 > gpurun_out/bench_strong_n$N.log 2>&1; tail -1 gpurun_out/bench_strong_n$N.log | cut -c 1-600 ;;
+  shapenet) N=${NGPU:-2}; run "test_shapeNet.py 1 GPU" 600 python test_shapeNet.py --batches 1 --batch-size 2 --grid 642 --categories bottle,mug --json-out gpurun_out/shapenet_n1.json > gpurun_out/shapenet_n1.log 2>&1
+            run "test_shapeNet.py $N GPUs" 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 test_shapeNet.py --batches 1 --batch-size 2 --grid 642 --categories bottle,mug --json-out gpurun_out/shapenet_n$N.json > gpurun_out/shapenet_n$N.log 2>&1
+            python -c "
+import json
+a=json.load(open('gpurun_out/shapenet_n1.json')); b=json.load(open('gpurun_out/shapenet_n$N.json'))
+print('top-1 pose indices, 1 GPU :', a['top1_idx']); print('top-1 pose indices, $N GPUs:', b['top1_idx'])
+print('scores equal:', a['scores']==b['scores'], ' top-1 equal:', a['top1_idx']==b['top1_idx'])
+" | tee gpurun_out/shapenet_compare.txt ;;
   sanitize) run "memcheck smoke" 1200 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck.log 2>&1; tail -5 gpurun_out/sanitizer_memcheck.log ;;
   *) echo "unknown step $step" ;;
 esac
