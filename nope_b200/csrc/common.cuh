@@ -71,6 +71,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // default limit is a few tens of ns: the wait loops of the idle roles then issue an instruction stream of their own
 // -- 60 % of all instructions of the fused-epilogue convolution were PHASECHK / clock / compare / branch)
 constexpr uint32_t kMbarSuspendNs = 20000;
+__constant__ uint32_t c_mbar_suspend_ns = kMbarSuspendNs;      // NOPE_MBAR_HINT overrides it (A/B measurements)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -78,7 +79,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(c_mbar_suspend_ns)
       : "memory");
   return ok != 0;
 }

@@ -1672,6 +1672,10 @@ inline int launch_conv_tc2_t(const ConvParams& p, int num_sms, cudaStream_t stre
   NOPE_CUDA(cudaGetDevice(&dev));
   NOPE_CHECK(dev >= 0 && dev < kMaxDevices, "device index out of range");
   if (max_clusters_of[dev] == 0) {
+    if (const char* e = getenv("NOPE_MBAR_HINT")) {
+      const uint32_t v = (uint32_t)atoi(e);
+      NOPE_CUDA(cudaMemcpyToSymbol(c_mbar_suspend_ns, &v, sizeof v));
+    }
     NOPE_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, EPI>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     int mc = num_sms / 2;
