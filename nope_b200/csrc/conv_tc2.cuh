@@ -15,9 +15,11 @@
 // exactly the 128 B/clk shared-memory limit, a 256-wide one 32 KB per 128), 128 / 64 (template
 // encoder, GEGLU).  Tiles of <= 128 columns double-buffer the output staging.  EPI selects the
 // epilogue at compile time: 0 plain (+ GroupNorm partial sums), 1 extras (ReLU, residual add,
-// (hi, lo) split, fp32 store: template encoder, LDM out conv), 2 GEGLU (conv_tc.cuh), 3 GroupNorm
-// fused (GnFuse, conv_tc.cuh): the default UNet's Block / ResnetBlock / to_out epilogues -- the
-// normalised, activated tensor is the only thing that reaches HBM.
+// (hi, lo) split, fp32 store: template encoder, LDM out conv), 2 GEGLU (conv_tc.cuh), 4 GroupNorm
+// fused (GnFuse, conv_tc.cuh) with the CTA split into math / statistics / store roles (conv_gn2_* below):
+// the default UNet's Block / ResnetBlock / to_qkv / to_out epilogues -- the normalised, activated tensor
+// is the only thing that reaches HBM.  3 is the same epilogue in lock step (all epilogue warps walk through
+// the tile together; kept behind NOPE_GN_EPI=3 as the A/B baseline the role split was measured against).
 //
 // Protocol (per CTA unless noted; barriers live at identical smem offsets in both CTAs):
 //   full[s]   leader only, count 2: leader's arrive.expect_tx(bytes of BOTH CTAs) + the
