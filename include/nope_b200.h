@@ -167,8 +167,9 @@ int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_top
 /* Multi-GPU merge: each rank sweeps a contiguous slice of the pose grid and contributes
  * ONE packed record to a single all-gather:
  *   [ topv: B*k f32 | 1 pad float if B*k is odd | topi: B*k int64 (GLOBAL indices, -1 = padding) |
- *     similarity slice: B * n_local f32 (optional) ]
- * nope_topk_pack_floats gives the record length in floats (n_local_max = ceil(N / world)).
+ *     similarity slice: B * n_local f32 (optional) | pad to a multiple of 4 floats ]
+ * nope_topk_pack_floats gives the record length in floats (n_local_max = ceil(N / world)); records sit back to back
+ * in the gathered buffer, so the length keeps every record's int64 block 8-byte aligned.
  * nope_topk_merge turns the `world` gathered records (each pack_floats long) into the global top-k
  * per batch row (descending, ties -> lowest index; identical on every rank) and, when has_sim, the
  * full similarity rows [B, N].  Rank r owns poses [r*per, min(N, (r+1)*per)). */

@@ -750,6 +750,8 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 // One thread per pixel, 128 pixels per CTA.
 // ----------------------------------------------------------------------------
 constexpr int kFinalThreads = 128;
+constexpr int kFinalPPT = 4;                               // pixels per thread of final_conv_score_kernel
+constexpr int kFinalPix = kFinalThreads * kFinalPPT;       // pixels per CTA (slab)
 constexpr int kMaxLatent = 8;
 constexpr int kScoreParts = 3;     // partial sums per (hypothesis, pixel slab): metric-dependent
 // Similarity metrics (include/nope_b200.h): 0 the reference's "l2" (model.py:260-262); 1 cosine of the
@@ -772,8 +774,8 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
                         bool bf = false) {
   pdl_sync();
   // weights transposed to [C][kMaxLatent] (zero beyond Cl): the 8 outputs of one input channel are two aligned 16-byte
-  // broadcast loads.  With the [Cl][C] layout every FMA had its own 4-byte shared-memory load and the kernel ran at
-  // 1.5 TB/s, bound by the load-store unit instead of HBM.
+  // broadcast loads, and every loaded weight serves the kFinalPPT pixels of the thread.  (With a [Cl][C] table and one
+  // pixel per thread every FMA had its own 4-byte shared-memory load: 1.5 TB/s, bound by the load-store unit.)
   extern __shared__ __align__(16) float s_w[];
   __shared__ float s_part[kScoreParts][kFinalThreads / 32];
   const int slab = blockIdx.x, h = blockIdx.y, nslab = gridDim.x;
@@ -782,49 +784,61 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
     s_w[i] = c < Cl ? w[c * C + k] : 0.f;
   }
   __syncthreads();
-  const int p = slab * kFinalThreads + threadIdx.x;
-  float acc[kMaxLatent];
+  static_assert(kMaxLatent == 8, "two float4 per input channel");
+  float acc[kFinalPPT][kMaxLatent];
+  int pix[kFinalPPT];
 #pragma unroll
-  for (int c = 0; c < kMaxLatent; ++c) acc[c] = (c < Cl) ? bias[c] : 0.f;
-  float dist = 0.f, d1 = 0.f, d2 = 0.f;      // metric-dependent partial sums of this pixel
-  if (p < hw) {
-    const __half* xp = x + ((long long)h * hw + p) * C;
-    const __half* xl = x_lo ? x_lo + ((long long)h * hw + p) * C : nullptr;
-    for (int k0 = 0; k0 < C; k0 += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(xp + k0);
+  for (int u = 0; u < kFinalPPT; ++u) {
+    pix[u] = slab * kFinalPix + u * kFinalThreads + threadIdx.x;      // consecutive threads: consecutive pixels
+#pragma unroll
+    for (int c = 0; c < kMaxLatent; ++c) acc[u][c] = (c < Cl) ? bias[c] : 0.f;
+  }
+  for (int k0 = 0; k0 < C; k0 += 8) {
+    float f[kFinalPPT][8];
+#pragma unroll
+    for (int u = 0; u < kFinalPPT; ++u) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (pix[u] < hw) v = *reinterpret_cast<const uint4*>(x + ((long long)h * hw + pix[u]) * C + k0);
       const uint32_t* hv = reinterpret_cast<const uint32_t*>(&v);
-      float f[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 t = unpack2(hv[q], bf);
-        f[2 * q] = t.x;
-        f[2 * q + 1] = t.y;
+        f[u][2 * q] = t.x;
+        f[u][2 * q + 1] = t.y;
       }
-      if (xl) {
-        const uint4 l = *reinterpret_cast<const uint4*>(xl + k0);
+      if (x_lo && pix[u] < hw) {
+        const uint4 l = *reinterpret_cast<const uint4*>(x_lo + ((long long)h * hw + pix[u]) * C + k0);
         const __half2* hl = reinterpret_cast<const __half2*>(&l);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 t = __half22float2(hl[q]);
-          f[2 * q] += t.x;
-          f[2 * q + 1] += t.y;
+          f[u][2 * q] += t.x;
+          f[u][2 * q + 1] += t.y;
         }
       }
-      static_assert(kMaxLatent == 8, "two float4 per input channel");
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {       // per output the channels are still accumulated in ascending order
-        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (k0 + i) * kMaxLatent);
-        const float4 w1 = *reinterpret_cast<const float4*>(s_w + (k0 + i) * kMaxLatent + 4);
-        acc[0] = fmaf(f[i], w0.x, acc[0]); acc[1] = fmaf(f[i], w0.y, acc[1]);
-        acc[2] = fmaf(f[i], w0.z, acc[2]); acc[3] = fmaf(f[i], w0.w, acc[3]);
-        acc[4] = fmaf(f[i], w1.x, acc[4]); acc[5] = fmaf(f[i], w1.y, acc[5]);
-        acc[6] = fmaf(f[i], w1.z, acc[6]); acc[7] = fmaf(f[i], w1.w, acc[7]);
+    for (int i = 0; i < 8; ++i) {       // per output the channels are accumulated in ascending order
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + (k0 + i) * kMaxLatent);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + (k0 + i) * kMaxLatent + 4);
+#pragma unroll
+      for (int u = 0; u < kFinalPPT; ++u) {
+        acc[u][0] = fmaf(f[u][i], w0.x, acc[u][0]); acc[u][1] = fmaf(f[u][i], w0.y, acc[u][1]);
+        acc[u][2] = fmaf(f[u][i], w0.z, acc[u][2]); acc[u][3] = fmaf(f[u][i], w0.w, acc[u][3]);
+        acc[u][4] = fmaf(f[u][i], w1.x, acc[u][4]); acc[u][5] = fmaf(f[u][i], w1.y, acc[u][5]);
+        acc[u][6] = fmaf(f[u][i], w1.z, acc[u][6]); acc[u][7] = fmaf(f[u][i], w1.w, acc[u][7]);
       }
     }
+  }
+  float dist = 0.f, d1 = 0.f, d2 = 0.f;      // metric-dependent partial sums over this thread's pixels
+#pragma unroll
+  for (int u = 0; u < kFinalPPT; ++u) {
+    const int p = pix[u];
+    if (p >= hw) continue;
     if (emb) {
 #pragma unroll
       for (int c = 0; c < kMaxLatent; ++c)
-        if (c < Cl) emb[((long long)h * Cl + c) * hw + p] = acc[c];
+        if (c < Cl) emb[((long long)h * Cl + c) * hw + p] = acc[u][c];
     }
     if (query) {
       const float* qp = query + (long long)ref_of[h] * Cl * hw + p;
@@ -833,20 +847,20 @@ final_conv_score_kernel(const __half* __restrict__ x, const float* __restrict__ 
       for (int c = 0; c < kMaxLatent; ++c)
         if (c < Cl) {
           const float qv = qp[(long long)c * hw];
-          const float d = qv - acc[c];
+          const float d = qv - acc[u][c];
           const float dd = d * d;
           s4 = fmaf(dd, dd, s4);
-          qe = fmaf(qv, acc[c], qe);
+          qe = fmaf(qv, acc[u][c], qe);
           qq = fmaf(qv, qv, qq);
-          ee = fmaf(acc[c], acc[c], ee);
+          ee = fmaf(acc[u][c], acc[u][c], ee);
         }
       if (metric == 0) {                 // reference "l2" (model.py:260-262)
-        dist = sqrtf(s4);
+        dist += sqrtf(s4);
       } else if (metric == 1) {          // cosine of the flattened descriptors: three global sums
-        dist = qe; d1 = qq; d2 = ee;
+        dist += qe; d1 += qq; d2 += ee;
       } else {                           // per-pixel cosine over channels, occlusion threshold
         const float sc = qe / (fmaxf(sqrtf(qq), 1e-8f) * fmaxf(sqrtf(ee), 1e-8f));
-        dist = sc > occ_thr ? sc : 0.f;
+        dist += sc > occ_thr ? sc : 0.f;
       }
     }
   }

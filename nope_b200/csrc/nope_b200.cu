@@ -495,7 +495,7 @@ struct nope_unet {
     // <= 64 (slot, image, group) entries of two {value, epoch} words per image
     if (b.base) xpart_words = (m + 8) * 64 * 2;
     b.take(&xpart, (m + 8) * 64 * 2);
-    const int nslab = (S0 * S0 + kFinalThreads - 1) / kFinalThreads;
+    const int nslab = (S0 * S0 + kFinalPix - 1) / kFinalPix;
     b.take(&score_partial, (size_t)n_total_scores * nslab * kScoreParts);
     b.take(&sim_buf, (size_t)n_total_scores);
     return b.off;
@@ -1117,7 +1117,7 @@ struct nope_unet {
     std::swap(curb, othb);
     if (tap("final_conv.0", A(curb, dim), dim, S, n, st)) return -1;
     const int hw = S * S;
-    const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
+    const int nslab = (hw + kFinalPix - 1) / kFinalPix;
     NOPE_CUDA(launch_pdl(final_conv_score_kernel, dim3(nslab, n), dim3(kFinalThreads), (size_t)kMaxLatent * dim * sizeof(float),
                          st, curb.hi, final_w, final_b, out_emb ? out_emb + (size_t)hyp0 * Cl * hw : nullptr, query_feat,
                          ref_of, score_part ? score_part + (size_t)hyp0 * nslab * kScoreParts : nullptr, hw, dim, Cl,
@@ -1349,7 +1349,7 @@ int nope_unet_sweep(nope_unet_t* u, const float* ref_feat, const float* poses, i
   if (u->ensure_workspace(cap, B, query_feat ? total : 0)) return -1;
   if (u->prepare_stream(st)) return -1;
   const int hw = u->S0 * u->S0;
-  const int nslab = (hw + kFinalThreads - 1) / kFinalThreads;
+  const int nslab = (hw + kFinalPix - 1) / kFinalPix;
   float* part = query_feat ? u->score_partial : nullptr;
   if (u->prestage(ref_feat, B, st)) return -1;
   for (int h0 = 0; h0 < total; h0 += cap) {
@@ -1406,7 +1406,9 @@ int nope_topk(float* sim, int B, int N, int k, float* out_topv, int64_t* out_top
 int64_t nope_topk_pack_floats(int B, int k, int n_local_max, int want_sim) {
   if (B < 1 || k < 1 || n_local_max < 0) return -1;
   const int64_t kk = ((int64_t)B * k + 1) & ~(int64_t)1;
-  return kk + 2 * (int64_t)B * k + (want_sim ? (int64_t)B * n_local_max : 0);
+  // rounded up to 4 floats: records sit back to back in the gathered buffer and every record's int64 block must
+  // stay 8-byte aligned (an odd length misaligned every second record: 10 248 poses on 8 GPUs = 16 + 1281 floats)
+  return (kk + 2 * (int64_t)B * k + (want_sim ? (int64_t)B * n_local_max : 0) + 3) & ~(int64_t)3;
 }
 
 int nope_topk_merge(const float* gathered, int world, int64_t pack_floats, int B, int k, int N, int per,
@@ -1414,7 +1416,9 @@ int nope_topk_merge(const float* gathered, int world, int64_t pack_floats, int B
   NOPE_CHECK(gathered && out_topv && out_topi, "null argument");
   NOPE_CHECK(world >= 1 && B >= 1 && k >= 1 && k <= N && world * k <= 1024, "bad merge geometry (world * k <= 1024)");
   NOPE_CHECK(per >= 1 && (int64_t)per * world >= N, "per-rank pose count does not cover the grid");
-  NOPE_CHECK(pack_floats >= nope_topk_pack_floats(B, k, has_sim ? per : 0, has_sim), "packed record too short");
+  NOPE_CHECK(pack_floats >= nope_topk_pack_floats(B, k, has_sim ? per : 0, has_sim) - 3, "packed record too short");
+  NOPE_CHECK(pack_floats % 2 == 0 && (reinterpret_cast<uintptr_t>(gathered) & 7) == 0,
+             "packed records must be 8-byte aligned: use nope_topk_pack_floats for the record length");
   NOPE_CHECK(!has_sim || out_sim, "similarity output missing");
   topk_merge_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       gathered, world, (long long)pack_floats, B, k, N, per, has_sim, out_sim, out_topv,

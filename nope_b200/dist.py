@@ -25,10 +25,13 @@ def shard_range(n_poses, rank, world):
 
 
 def record_layout(B, k, per, want_sim):
-    """Offsets (in floats) of the packed record: topv | pad | topi (int64) | sim slice."""
+    """Offsets (in floats) of the packed record: topv | pad | topi (int64) | sim slice | pad.
+    The record length is a multiple of 4 floats: records sit back to back in the gathered buffer and the merge
+    kernel reads the int64 indices of EVERY rank's record in place (an odd length -- e.g. the 10 248-pose grid on
+    8 GPUs: 16 + 1281 floats -- put every second record's indices on a 4-byte boundary: misaligned address)."""
     kk = (B * k + 1) & ~1
     off_i, off_s = kk, kk + 2 * B * k
-    return off_i, off_s, off_s + (B * per if want_sim else 0)
+    return off_i, off_s, (off_s + (B * per if want_sim else 0) + 3) & ~3
 
 
 def merge_topk(vals, idx, k):

@@ -74,3 +74,18 @@ def test_merge_topk_ties():
     idx = torch.tensor([[9], [7], [4], [1], [-1]])
     v, i = merge_topk(vals, idx, 3)
     assert i.tolist() == [[4, 7, 1]] and v.tolist() == [[3.0, 3.0, 2.0]]
+
+
+def test_record_length_keeps_int64_blocks_aligned():
+    """records are concatenated by the all-gather and read in place by the CUDA merge: every record length must be
+    a multiple of 2 floats (we pad to 4) for any batch / k / shard size -- 10 248 poses on 8 ranks (1281 per rank)
+    once produced 1297 floats and a misaligned-address fault on every second record"""
+    from nope_b200.dist import record_layout
+    for B in (1, 2, 3, 8):
+        for k in (1, 3, 5):
+            for per in (1, 81, 321, 642, 1281, 2562):
+                for want_sim in (False, True):
+                    off_i, off_s, pack = record_layout(B, k, per, want_sim)
+                    assert off_i % 2 == 0 and pack % 4 == 0
+                    assert off_i >= B * k and off_s == off_i + 2 * B * k
+                    assert pack >= off_s + (B * per if want_sim else 0)
