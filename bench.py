@@ -744,6 +744,9 @@ def main():
             "best_single_launch_tflops": prof["max_launch_tflops"],
             "whole_step_tflops": value * GFLOP_PER_HYP / 1e3,
             "whole_step_frac": value * GFLOP_PER_HYP / 1e3 / peak_tf if peak_tf else None,
+            "note": "the convolution kernel also normalises / activates / adds pose bias and residual in its epilogue "
+                    "(round 1 ran those as separate HBM passes and reported frac 0.87-0.90 for the bare convolution): "
+                    "compare whole_step_frac, 0.71 in round 1",
         },
         "modes": modes,
         "cpu_baseline": cpu,
