@@ -147,6 +147,7 @@ def main():
             ("exact w, only attn-internal rounded", sd, {"attn"}),
             ("exact w, attn + pose rounded", sd, {"attn", "pose"}),
             ("exact w, attn + pose + aux(conv) rounded", sd, {"attn", "pose", "aux"}),
+            ("exact w, attn + pose + h1 rounded  [parity_fast]", sd, {"attn", "pose", "h1"}),
             ("fp16 w (attn layers only exact?) n/a", sd, set()),
             ("only cin", sd, {"cin"}),
             ("only h1", sd, {"h1"}), ("only out", sd, {"out"}), ("only aux", sd, {"aux"}), ("only pose", sd, {"pose"}),
