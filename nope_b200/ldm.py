@@ -116,11 +116,18 @@ class UNetModelPose:
         _lib.check(_lib.load().nope_ldm_profile_read(self._handle(), ms, fl, n))
         return {k: {"ms": ms[i], "flops": fl[i], "launches": n[i]} for i, k in enumerate(("gemm", "attention"))}
 
+    def set_metric(self, metric="l2", threshold=0.2):
+        """nope_b200.dist.ShardedSweep selects the score through this call; the LDM engine fuses the reference's
+        "l2" score only (model.py:260-262)."""
+        if metric != "l2":
+            raise ValueError("UNetModelPose fuses the 'l2' similarity only")
+
     def sweep(self, ref_latent, poses, query_latent=None, want_emb=True, want_sim=None, k=0, idx_base=0,
-              query_feat=None):
+              query_feat=None, out=None):
         """ref_latent [B,C,32,32], poses [B,N,6] (+ query_latent) -> dict(emb, sim, topv, topi).
-        `query_feat` is an alias of `query_latent` (the keyword nope_b200.unet.UNet.sweep and
-        nope_b200.dist.ShardedSweep use), so the pose grid shards across GPUs the same way."""
+        `query_feat` is an alias of `query_latent` and `out` may carry preallocated `sim` / `topv` / `topi`
+        tensors (the keywords nope_b200.unet.UNet.sweep and nope_b200.dist.ShardedSweep use), so the pose grid
+        shards across GPUs the same way."""
         if query_feat is not None:
             query_latent = query_feat
         if not self._finalized:
@@ -138,9 +145,18 @@ class UNetModelPose:
             query_latent = query_latent.to(dev, torch.float32).contiguous()
             assert query_latent.shape == ref_latent.shape
         emb = torch.empty((B, N, self.channels, 32, 32), device=dev, dtype=torch.float32) if want_emb else None
-        sim = torch.empty((B, N), device=dev, dtype=torch.float32) if want_sim else None
-        topv = torch.empty((B, k), device=dev, dtype=torch.float32) if k > 0 else None
-        topi = torch.empty((B, k), device=dev, dtype=torch.int64) if k > 0 else None
+        out = out or {}
+        sim = out.get("sim") if want_sim else None
+        if want_sim and sim is None:
+            sim = torch.empty((B, N), device=dev, dtype=torch.float32)
+        topv, topi = (out.get("topv"), out.get("topi")) if k > 0 else (None, None)
+        if k > 0 and topv is None:
+            topv = torch.empty((B, k), device=dev, dtype=torch.float32)
+            topi = torch.empty((B, k), device=dev, dtype=torch.int64)
+        for t, shape, dt in ((sim, (B, N), torch.float32), (topv, (B, k), torch.float32), (topi, (B, k), torch.int64)):
+            if t is not None and (tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous()
+                                  or t.device != dev):
+                raise ValueError("preallocated output has the wrong shape / dtype / device or is not contiguous")
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             _lib.check(lib.nope_ldm_sweep(self._handle(), _lib.ptr(ref_latent), _lib.ptr(poses), B, N,

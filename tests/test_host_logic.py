@@ -99,3 +99,16 @@ def test_scripts_have_no_undefined_names():
             missing = {n.id for n in ast.walk(fn) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)
                        and n.id not in names}
             assert not missing, (script, fn.name, sorted(missing))
+
+
+def test_both_unets_offer_the_interface_the_sharded_sweep_drives():
+    """nope_b200.dist.ShardedSweep calls set_metric() and sweep(query_feat=, want_emb=, want_sim=, k=, idx_base=,
+    out=) on whichever UNet it is given; the LDM mirror once lagged behind (multi-GPU LDM sweeps raised)."""
+    import inspect
+    from nope_b200.ldm import UNetModelPose
+    from nope_b200.unet import UNet
+    need = {"query_feat", "want_emb", "want_sim", "k", "idx_base", "out"}
+    for cls in (UNet, UNetModelPose):
+        assert callable(getattr(cls, "set_metric", None)), cls.__name__
+        params = set(inspect.signature(cls.sweep).parameters)
+        assert need <= params, (cls.__name__, sorted(need - params))
